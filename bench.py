@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the correlation hot path (BASELINE.json metric).
+
+Workload (configs[1] of BASELINE.json): RAFT inference at Sintel resolution 436x1024
+(padded to 440x1024 -> 55x128 tokens at 1/8 resolution), D = 256, 4 levels, radius 4,
+batch 8 pairs per GPU.  One STEP = one pass of the hot path over one batch:
+CorrBlock(fmap1, fmap2) [all-pairs volume + pyramid] followed by ``--iters`` (12)
+lookups at fresh coordinates, exactly the calls raft.py:105-107,124 makes per forward.
+The convolutional encoder / GRU of RAFT are not part of this path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference      # the reference's CPU path (oracle port) on host cores
+
+Prints ONE JSON line (rank 0).  Keys are described in DESIGN.md ("Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LEVELS, RADIUS, DIM = 4, 4, 256
+K_CH = LEVELS * (2 * RADIUS + 1) ** 2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--iters", type=int, default=12, help="GRU iterations = lookups per pair")
+    ap.add_argument("--batch", type=int, default=8, help="image pairs per GPU")
+    ap.add_argument("--height", type=int, default=436)
+    ap.add_argument("--width", type=int, default=1024)
+    ap.add_argument("--math", default=os.environ.get("FLOWCORR_MATH", "fp32"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def token_grid(h, w):
+    ph, pw = (h + 7) // 8 * 8, (w + 7) // 8 * 8          # InputPadder, utils.py:7-16
+    return ph // 8, pw // 8
+
+
+def synth(B, H, W, iters, seed, device="cpu", pin=False):
+    """Feature maps ~ N(0, 1.57^2) (random-init fnet statistics) and a
+    coordinate sequence grid + N(0, 5^2) 1/8-px flow (the locality-hostile law)."""
+    gen = torch.Generator().manual_seed(seed)
+    f1 = 1.57 * torch.randn(B, DIM, H, W, generator=gen)
+    f2 = 1.57 * torch.randn(B, DIM, H, W, generator=gen)
+    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    grid = torch.stack([xs, ys], 0).float()[None]
+    coords = torch.stack([grid + 5.0 * torch.randn(B, 2, H, W, generator=gen) for _ in range(iters)])
+    if pin:
+        f1, f2, coords = f1.pin_memory(), f2.pin_memory(), coords.pin_memory()
+    return f1.to(device), f2.to(device), coords.to(device)
+
+
+def lookup_bytes(B, H, W, inbounds_elems=None):
+    """Algorithmic bytes of ONE lookup launch: discounted footprint read +
+    output write + coords, fp32."""
+    n = B * H * W
+    foot = inbounds_elems if inbounds_elems is not None else LEVELS * (2 * RADIUS + 2) ** 2
+    return n * (foot * 4 + K_CH * 4 + 8)
+
+
+def inbounds_footprint(coords, H, W):
+    """Mean number of in-bounds footprint elements per query (all levels) for the actual
+    coordinates: the 'discounted' read of SURVEY.md 8d."""
+    tot = 0.0
+    c = coords.float()
+    for l in range(LEVELS):
+        Hl, Wl = H >> l, W >> l
+        x0 = torch.floor(c[:, :, 0] / 2 ** l) - RADIUS
+        y0 = torch.floor(c[:, :, 1] / 2 ** l) - RADIUS
+        nx = (torch.clamp(x0 + 2 * RADIUS + 2, max=Wl) - torch.clamp(x0, min=0)).clamp(min=0)
+        ny = (torch.clamp(y0 + 2 * RADIUS + 2, max=Hl) - torch.clamp(y0, min=0)).clamp(min=0)
+        tot += float((nx * ny).mean())
+    return tot
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return p["hbm_gbs"], p["bf16_tflops"], p["bf16_tflops_sustained"], "measured"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+# ------------------------------------------------------------------------------ CPU arms
+def cpu_path_rate(H, W, iters, batch, budget_s, threads):
+    """The reference's CPU CorrBlock path (oracle/corr_torch.py: the same torch library
+    calls as corr.py) on the host cores: pairs/s over a bounded sample."""
+    from oracle import corr_torch
+    torch.set_num_threads(threads)
+    f1, f2, coords = synth(batch, H, W, iters, seed=0)
+    def one():
+        blk = corr_torch.TorchCorrBlock(f1, f2, LEVELS, RADIUS)
+        for t in range(iters):
+            out = blk(coords[t])
+        return out
+    one()
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        one(); reps += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or reps >= 8:
+            break
+    return batch * reps / el, reps, el
+
+
+def run_reference(args, H, W):
+    """--impl reference: the reference's own CPU implementation of the path (library-call
+    port in oracle/corr_torch.py; the reference itself is Python and does not travel to
+    the GPU box).  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    from oracle import corr_torch
+    sample_b = 2
+    f1, f2, coords = synth(sample_b, H, W, args.iters, seed=0)
+    def step():
+        blk = corr_torch.TorchCorrBlock(f1, f2, LEVELS, RADIUS)
+        for t in range(args.iters):
+            blk(coords[t])
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    v = sample_b * args.steps / el
+    line = {
+        "impl": "reference", "metric": "RAFT corr-path pairs/s @436x1024 (12 iters)", "value": v,
+        "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"CorrBlock build + {args.iters} lookups, {H}x{W} tokens, D=256, L=4, r=4",
+                   "sample": f"{sample_b} pairs per step on CPU (GPU arm: {args.batch} per GPU)"},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps x {sample_b} pairs, torch {torch.__version__} CPU ops"},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    H, W = token_grid(args.height, args.width)
+    if args.impl == "reference":
+        run_reference(args, H, W)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (GPU arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import flow_supervisor_b200 as fsb
+    from flow_supervisor_b200 import ops, _lib
+    fsb.CorrBlock.math = args.math
+    math_id = {"fp32": _lib.MATH_FP32, "3xbf16": _lib.MATH_TC_3XBF16, "bf16": _lib.MATH_TC_BF16}[args.math]
+
+    B, iters = args.batch, args.iters
+    f1h, f2h, ch = synth(B, H, W, iters, seed=rank, pin=True)           # host (pinned)
+    f1, f2, coords = f1h.cuda(), f2h.cuda(), ch.cuda()                  # resident copies
+    foot = inbounds_footprint(ch, H, W)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident step: value
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(iters + 2)] for _ in range(args.steps)]
+
+    def step_resident(events=None):
+        if events: events[0].record()
+        blk = fsb.CorrBlock(f1, f2, LEVELS, RADIUS)
+        if events: events[1].record()
+        out = None
+        for t in range(iters):
+            out = blk(coords[t])
+            if events: events[t + 2].record()
+        return out
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    t_start.record()
+    for s in range(args.steps):
+        step_resident(ev[s])
+    t_end.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = t_start.elapsed_time(t_end)
+    build_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    look_ms = sum(e[t + 1].elapsed_time(e[t + 2]) for e in ev for t in range(iters)) / (args.steps * iters)
+
+    # ---- end-to-end step through the public API with HOST buffers: e2e
+    out_host = torch.empty(iters, B, K_CH, H, W, dtype=torch.float32).pin_memory()
+    h2d = f1h.numel() * 4 * 2 + ch.numel() * 4
+    d2h = out_host.numel() * 4
+
+    def step_e2e():
+        a, b = f1h.cuda(non_blocking=True), f2h.cuda(non_blocking=True)
+        c = ch.cuda(non_blocking=True)
+        blk = fsb.CorrBlock(a, b, LEVELS, RADIUS)
+        for t in range(iters):
+            out_host[t].copy_(blk(c[t]), non_blocking=True)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_e2e = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(n_e2e):
+        step_e2e()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / n_e2e
+
+    # ---- max over ranks
+    t = torch.tensor([elapsed_ms, e2e_ms, build_ms, look_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms, build_ms, look_ms = t.tolist()
+
+    if rank == 0:
+        hbm, tf_burst, tf_sust, peak_src = peaks()
+        ms_step = elapsed_ms / args.steps
+        value = world * B * args.steps / (elapsed_ms * 1e-3)
+        lb = lookup_bytes(B, H, W, foot)
+        look = {"kernel": "lookup_fwd_kernel", "bound": "hbm", "achieved": lb / (look_ms * 1e-3) / 1e9,
+                "peak": hbm, "unit": "GB/s", "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": lb, "bytes_nominal": lookup_bytes(B, H, W), "ms_per_launch": look_ms,
+                "share_of_step": iters * look_ms / ms_step}
+        look["frac"] = look["achieved"] / hbm
+        N = H * W
+        flop = 2.0 * B * N * N * DIM
+        pyr_bytes, _ = _lib.pyramid_layout(B, H, W, LEVELS, _lib.VOL_F32)
+        bld = {"kernel": "build (gemm + pyramid)", "bound": "tensor" if math_id else "fp32-simt",
+               "achieved": flop / (build_ms * 1e-3) / 1e12, "peak": tf_sust, "unit": "TFLOP/s",
+               "traffic": None, "peak_source": peak_src, "flop_per_launch": flop,
+               "hbm_bytes_per_launch": pyr_bytes + 2 * B * DIM * N * 4,
+               "hbm_gbs": (pyr_bytes + 2 * B * DIM * N * 4) / (build_ms * 1e-3) / 1e9,
+               "ms_per_launch": build_ms, "share_of_step": build_ms / ms_step}
+        bld["frac"] = bld["achieved"] / tf_sust
+        dominant, other = (look, bld) if look["share_of_step"] >= bld["share_of_step"] else (bld, look)
+        line = {
+            "metric": "RAFT corr-path pairs/s @436x1024 (12 iters)", "value": value, "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"CorrBlock build + {iters} lookups per pair, {args.height}x{args.width} px "
+                                   f"-> {H}x{W} tokens, D={DIM}, L={LEVELS}, r={RADIUS}, batch {B}/GPU",
+                       "math": args.math, "volume": "f32", "parallelism": f"batch-sharded x{world}, no collective",
+                       "l2": f"inputs larger than L2 (pyramid {pyr_bytes / 1e9:.2f} GB/GPU)",
+                       "coords": "grid + N(0,5^2) 1/8-px flow"},
+            "lookups_per_s": world * B * N * iters * args.steps / (elapsed_ms * 1e-3),
+            "wall_s": wall,
+            "roofline": dominant, "roofline_other": other,
+            "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": args.steps * (iters + (4 if math_id == 0 else 2)),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rate, reps, el = cpu_path_rate(H, W, iters, batch=1, budget_s=12.0, threads=threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                    "sample": f"{reps} x 1 pair (build + {iters} lookups) in {el:.1f} s, "
+                                              f"oracle/corr_torch.py on torch {torch.__version__} CPU ops"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,164 @@
+"""Host-side mirror of the reference's correlation interface.
+
+``CorrBlock`` / ``AlternateCorrBlock`` keep the constructor and call signature of
+/root/reference/pytorch/core/corr.py:12-91 (and its GMA twin gma_corr.py:15-63) so
+RAFT / L2L / RAFTGMA / GMAL2L and the train / evaluate scripts run unchanged:
+
+    corr_fn = CorrBlock(fmap1, fmap2, num_levels=4, radius=4)   # raft.py:105-107
+    corr = corr_fn(coords1)                                    # raft.py:124
+
+Arithmetic lives in libflowcorr.so (CUDA, sm_100a).  Differences to the reference
+that a caller can observe are listed in DESIGN.md ("Behavioural notes").
+
+Modes (class attributes, or environment variables read at import):
+    CorrBlock.math       'fp32' | '3xbf16' | 'bf16'   (FLOWCORR_MATH;  default fp32-parity)
+    CorrBlock.volume     'f32'  | 'bf16'              (FLOWCORR_VOLUME)
+    CorrBlock.coord_mode 'cuda' | 'cpu'               (FLOWCORR_COORD; which device's
+                          rounding of utils.py:61-62 to reproduce; default 'cuda')
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib, ops
+
+_MATH = {"fp32": _lib.MATH_FP32, "3xbf16": _lib.MATH_TC_3XBF16, "bf16": _lib.MATH_TC_BF16}
+_VOL = {"f32": _lib.VOL_F32, "bf16": _lib.VOL_BF16}
+_COORD = {"cuda": _lib.COORD_CUDA, "cpu": _lib.COORD_CPU}
+
+
+def coords_grid(batch, ht, wd, device=None):
+    """utils.py:74-77: (B, 2, H, W) fp32, channel 0 = x, channel 1 = y."""
+    ys, xs = torch.meshgrid(torch.arange(ht, device=device), torch.arange(wd, device=device), indexing="ij")
+    return torch.stack([xs, ys], dim=0).float()[None].repeat(batch, 1, 1, 1)
+
+
+class _BlockState:
+    """Per-CorrBlock state shared by the autograd nodes: the volume itself (never an
+    autograd leaf) and ONE lazily zeroed gradient pyramid that every lookup's backward
+    accumulates into (the reference materialises a volume-sized gradient per lookup
+    per level)."""
+
+    __slots__ = ("pyramid", "grad_pyramid", "B", "H", "W", "L", "radius", "math", "coord")
+
+    def __init__(self):
+        self.pyramid = None
+        self.grad_pyramid = None
+
+
+class _Build(torch.autograd.Function):
+    """fmap1, fmap2 -> 1-element token.  The token carries the autograd dependency of
+    every lookup on the feature maps; the volume travels in ``state``."""
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, state):
+        state.pyramid = ops.build(fmap1, fmap2, state.L, state.math, _lib.VOL_F32)
+        ctx.save_for_backward(fmap1, fmap2)
+        ctx.state = state
+        return fmap1.new_zeros(1)
+
+    @staticmethod
+    def backward(ctx, _grad_token):
+        state = ctx.state
+        fmap1, fmap2 = ctx.saved_tensors
+        if state.grad_pyramid is None:            # no lookup contributed a gradient
+            return torch.zeros_like(fmap1), torch.zeros_like(fmap2), None
+        gp, state.grad_pyramid = state.grad_pyramid, None      # consumed; a second backward re-accumulates
+        d1, d2 = ops.build_bwd(gp, fmap1, fmap2, state.L, state.math)
+        return d1, d2, None
+
+
+class _Lookup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, token, coords, state):
+        ctx.save_for_backward(coords)
+        ctx.state = state
+        return ops.lookup(state.pyramid, coords, state.L, state.radius, state.coord)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        state = ctx.state
+        (coords,) = ctx.saved_tensors
+        if state.grad_pyramid is None:
+            state.grad_pyramid = torch.zeros(state.pyramid.numel(), dtype=torch.float32,
+                                             device=state.pyramid.device)
+        ops.lookup_bwd(grad_out, coords, state.grad_pyramid, state.L, state.radius, state.coord)
+        # coords get no gradient: the reference always passes them detached (raft.py:123)
+        return grad_out.new_zeros(1), None, None
+
+
+class CorrBlock:
+    math = os.environ.get("FLOWCORR_MATH", "fp32")
+    volume = os.environ.get("FLOWCORR_VOLUME", "f32")
+    coord_mode = os.environ.get("FLOWCORR_COORD", "cuda")
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+        if not (fmap1.is_cuda and fmap2.is_cuda):
+            raise RuntimeError("flow_supervisor_b200.CorrBlock needs CUDA feature maps: this package "
+                               "has no CPU fallback (use the reference on CPU)")
+        if fmap1.shape != fmap2.shape or fmap1.dim() != 4:
+            raise ValueError(f"fmap1/fmap2 must both be (B, D, H, W); got {tuple(fmap1.shape)} "
+                             f"and {tuple(fmap2.shape)}")
+        self.num_levels = num_levels
+        self.radius = radius
+        st = self._state = _BlockState()
+        st.B, _, st.H, st.W = fmap1.shape
+        st.L, st.radius = num_levels, radius
+        st.math, st.coord = _MATH[self.math], _COORD[self.coord_mode]
+        self._vol_dtype = _VOL[self.volume]
+        fmap1, fmap2 = fmap1.float(), fmap2.float()
+        self._token = None
+        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+            if self._vol_dtype != _lib.VOL_F32:
+                raise RuntimeError("training needs the fp32 volume (CorrBlock.volume = 'f32')")
+            self._token = _Build.apply(fmap1, fmap2, st)
+        else:
+            st.pyramid = ops.build(fmap1.detach(), fmap2.detach(), num_levels, st.math, self._vol_dtype)
+
+    @property
+    def corr_pyramid(self):
+        """corr.py:16,24,27: list of (B*N, 1, Hl, Wl) levels (strided views, no copy)."""
+        st = self._state
+        return ops.level_views(st.pyramid, st.B, st.H, st.W, st.L)
+
+    def __call__(self, coords):
+        st = self._state
+        if coords.dim() != 4 or coords.shape[1] != 2 or coords.shape[0] != st.B \
+                or coords.shape[2] != st.H or coords.shape[3] != st.W:
+            raise ValueError(f"coords must be ({st.B}, 2, {st.H}, {st.W}); got {tuple(coords.shape)}")
+        if self._token is not None and torch.is_grad_enabled():
+            return _Lookup.apply(self._token, coords.detach(), st)
+        return ops.lookup(st.pyramid, coords.detach(), st.L, st.radius, st.coord)
+
+    def lookup_debug(self, coords):
+        """(out, x0, y0, corner_mask): the lookup plus its integer part, for parity tests."""
+        st = self._state
+        return ops.lookup_debug(st.pyramid, coords.detach(), st.L, st.radius, st.coord)
+
+    @staticmethod
+    def corr(fmap1, fmap2):
+        """corr.py:52-60: (B, H, W, 1, H, W) all-pairs volume (level 0 only)."""
+        B, D, H, W = fmap1.shape
+        pyr = ops.build(fmap1.detach().float(), fmap2.detach().float(), 1, _MATH[CorrBlock.math], _lib.VOL_F32)
+        return ops.level_views(pyr, B, H, W, 1)[0].reshape(B, H, W, 1, H, W)
+
+
+class AlternateCorrBlock:
+    """On-demand correlation (corr.py:63-91): nothing volume-sized is stored.  Like the
+    reference's, this block is inference-only (alt_cuda_corr.forward is a raw call with
+    no autograd, corr.py:86)."""
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+        if not (fmap1.is_cuda and fmap2.is_cuda):
+            raise RuntimeError("flow_supervisor_b200.AlternateCorrBlock needs CUDA feature maps "
+                               "(no CPU fallback)")
+        self.num_levels = num_levels
+        self.radius = radius
+        self._shape = tuple(fmap1.shape)
+        self._ws = ops.ondemand_prepare(fmap1.detach().float(), fmap2.detach().float(), num_levels)
+
+    def __call__(self, coords):
+        B, D, H, W = self._shape
+        return ops.ondemand_lookup(self._ws, coords.detach(), D, self.num_levels, self.radius)

@@ -1,0 +1,106 @@
+// C ABI entry points that are not kernels themselves: error plumbing, geometry,
+// and the math-mode dispatch of fc_build / fc_build_bwd.  See include/flowcorr.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cmath>
+
+#include "fc_common.cuh"
+
+namespace fc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error in %s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return FC_ECUDA;
+}
+
+// fc_simt.cu
+int simt_build(const float* f1, const float* f2, float* pyramid, const Pyramid& pyr,
+               int D, int H, int W, cudaStream_t s);
+int simt_fold(float* gpyr, const Pyramid& pyr, cudaStream_t s);
+int simt_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float* d2,
+                   const Pyramid& pyr, int D, int H, int W, cudaStream_t s);
+// fc_build_tc.cu
+size_t tc_build_workspace_bytes(int B, int D, int H, int W, int L, int math);
+int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr, int D, int H, int W,
+             int vol_dtype, int math, void* ws, size_t ws_bytes, cudaStream_t s);
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace fc
+
+using namespace fc;
+
+extern "C" int fc_abi_version(void) { return FC_ABI_VERSION; }
+
+extern "C" const char* fc_last_error(void) { return g_err; }
+
+extern "C" int fc_level_dims(int H, int W, int level, int* Hl, int* Wl, int* Wp) {
+    FC_REQUIRE(H > 0 && W > 0 && level >= 0 && level < FC_MAX_LEVELS, "fc_level_dims: bad arguments");
+    const int h = H >> level, w = W >> level;
+    FC_REQUIRE(h >= 1 && w >= 1, "fc_level_dims: level %d of %dx%d is empty", level, H, W);
+    if (Hl) *Hl = h;
+    if (Wl) *Wl = w;
+    if (Wp) *Wp = round_up(w, 8);
+    return FC_OK;
+}
+
+extern "C" size_t fc_pyramid_bytes(int B, int H, int W, int num_levels, int vol_dtype,
+                                   size_t* level_offsets) {
+    Pyramid pyr;
+    if (!make_pyramid(pyr, B, H, W, num_levels) || (vol_dtype != FC_VOL_F32 && vol_dtype != FC_VOL_BF16)) {
+        set_error("fc_pyramid_bytes: bad geometry B=%d H=%d W=%d L=%d dtype=%d", B, H, W, num_levels, vol_dtype);
+        return 0;
+    }
+    const size_t es = vol_dtype == FC_VOL_F32 ? 4 : 2;
+    if (level_offsets)
+        for (int l = 0; l < num_levels; ++l) level_offsets[l] = (size_t)pyr.lv[l].offset * es;
+    return (size_t)pyr.total * es;
+}
+
+extern "C" size_t fc_build_workspace_bytes(int B, int D, int H, int W, int num_levels, int math) {
+    if (math == FC_MATH_FP32) return 0;
+    return tc_build_workspace_bytes(B, D, H, W, num_levels, math);
+}
+
+extern "C" int fc_build(const float* fmap1, const float* fmap2, void* pyramid,
+                        int B, int D, int H, int W, int num_levels,
+                        int vol_dtype, int math,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    FC_REQUIRE(fmap1 && fmap2 && pyramid, "fc_build: null pointer");
+    FC_REQUIRE(aligned16(fmap1) && aligned16(fmap2) && aligned16(pyramid), "fc_build: pointers must be 16-byte aligned");
+    FC_REQUIRE(D >= 1, "fc_build: D=%d", D);
+    Pyramid pyr;
+    FC_REQUIRE(make_pyramid(pyr, B, H, W, num_levels), "fc_build: bad geometry B=%d H=%d W=%d L=%d", B, H, W, num_levels);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (math == FC_MATH_FP32) {
+        FC_REQUIRE(vol_dtype == FC_VOL_F32, "fc_build: FC_MATH_FP32 writes an fp32 volume only");
+        return simt_build(fmap1, fmap2, static_cast<float*>(pyramid), pyr, D, H, W, s);
+    }
+    FC_REQUIRE(math == FC_MATH_TC_3XBF16 || math == FC_MATH_TC_BF16, "fc_build: unknown math mode %d", math);
+    return tc_build(fmap1, fmap2, pyramid, pyr, D, H, W, vol_dtype, math, workspace, workspace_bytes, s);
+}
+
+extern "C" int fc_build_bwd(float* grad_pyramid, const float* fmap1, const float* fmap2,
+                            float* dfmap1, float* dfmap2,
+                            int B, int D, int H, int W, int num_levels, int math,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace; (void)workspace_bytes;
+    FC_REQUIRE(grad_pyramid && fmap1 && fmap2, "fc_build_bwd: null pointer");
+    Pyramid pyr;
+    FC_REQUIRE(make_pyramid(pyr, B, H, W, num_levels), "fc_build_bwd: bad geometry B=%d H=%d W=%d L=%d", B, H, W, num_levels);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    FC_REQUIRE(math == FC_MATH_FP32 || math == FC_MATH_TC_3XBF16 || math == FC_MATH_TC_BF16,
+               "fc_build_bwd: unknown math mode %d", math);
+    if (int e = simt_fold(grad_pyramid, pyr, s)) return e;
+    // gradient contractions currently always run in fp32 on the CUDA cores
+    return simt_build_bwd(grad_pyramid, fmap1, fmap2, dfmap1, dfmap2, pyr, D, H, W, s);
+}

@@ -1,0 +1,110 @@
+// Shared device/host helpers for libflowcorr (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/flowcorr.h"
+
+namespace fc {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define FC_REQUIRE(cond, ...)                 \
+    do {                                      \
+        if (!(cond)) {                        \
+            fc::set_error(__VA_ARGS__);       \
+            return FC_EINVAL;                 \
+        }                                     \
+    } while (0)
+
+#define FC_CUDA(call)                                         \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return fc::cuda_fail(e__, #call); \
+    } while (0)
+
+#define FC_LAUNCH_CHECK(name)                                 \
+    do {                                                      \
+        cudaError_t e__ = cudaPeekAtLastError();              \
+        if (e__ != cudaSuccess) return fc::cuda_fail(e__, name); \
+    } while (0)
+
+// ---------------------------------------------------------------- pyramid geometry
+struct Level {
+    int H, W, Wp;          // rows, valid columns, row pitch (elements)
+    long long offset;      // ELEMENT offset of the level inside the pyramid buffer
+};
+
+struct Pyramid {
+    int L;
+    int B, N;              // samples, queries per sample (H*W of level 0)
+    Level lv[FC_MAX_LEVELS];
+    long long total;       // total elements
+};
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+inline bool make_pyramid(Pyramid& P, int B, int H, int W, int L) {
+    if (B <= 0 || H <= 0 || W <= 0 || L < 1 || L > FC_MAX_LEVELS) return false;
+    P.L = L; P.B = B; P.N = H * W;
+    long long off = 0;
+    for (int l = 0; l < L; ++l) {
+        int Hl = H >> l, Wl = W >> l;
+        if (Hl < 1 || Wl < 1) return false;
+        P.lv[l].H = Hl; P.lv[l].W = Wl; P.lv[l].Wp = round_up(Wl, 8);
+        P.lv[l].offset = off;
+        off += (long long)B * P.N * Hl * P.lv[l].Wp;
+    }
+    P.total = off;
+    return true;
+}
+
+// ---------------------------------------------------------------- tap arithmetic
+// One window sample on one axis, rounded exactly where the reference rounds
+// (corr.py:41-43, utils.py:61-62, ATen GridSampler.cuh unnormalise/floor/weights;
+// restated in oracle/corr_spec.py::axis_taps).  The *_rn intrinsics are never
+// contracted into FMAs, so the integer index is reproducible bit for bit.
+struct AxisConst {
+    float den;   // size - 1
+    float inv;   // fl(1 / (size - 1))   (ATen CUDA div-by-scalar fast path)
+};
+
+__host__ __device__ inline AxisConst make_axis(int size) {
+    AxisConst a;
+    a.den = (float)(size - 1);
+    a.inv = 1.0f / a.den;
+    return a;
+}
+
+template <int COORD_MODE>
+__device__ __forceinline__ void axis_tap(float c_l, int off, AxisConst ax,
+                                         int& i0, float& w0, float& w1) {
+    float X = __fadd_rn(c_l, (float)off);
+    float t = __fmul_rn(2.0f, X);
+    float g = (COORD_MODE == FC_COORD_CUDA) ? __fmul_rn(t, ax.inv) : __fdiv_rn(t, ax.den);
+    g = __fadd_rn(g, -1.0f);
+    float u = __fmul_rn(__fadd_rn(g, 1.0f), 0.5f);
+    float ix = __fmul_rn(u, ax.den);
+    float f = floorf(ix);
+    w1 = __fsub_rn(ix, f);
+    w0 = __fsub_rn(__fadd_rn(f, 1.0f), ix);
+    i0 = (int)f;            // saturating; NaN -> 0 (such queries are masked as "far")
+}
+
+// ---------------------------------------------------------------- small PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+}  // namespace fc

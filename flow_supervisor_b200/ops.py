@@ -1,0 +1,249 @@
+"""torch custom ops over the C ABI (``torch.ops.flowcorr.*``).
+
+PyTorch is plumbing here: it owns device memory (caching allocator) and the
+current stream; every op forwards raw pointers to ``libflowcorr.so`` and launches
+on ``torch.cuda.current_stream()``.  No op synchronises or touches the host, so
+the lookup is CUDA-graph capturable.  CPU tensors are rejected: there is no
+fallback path.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+from torch import Tensor
+from torch.library import custom_op
+
+from . import _lib
+
+_VOL_TORCH = {_lib.VOL_F32: torch.float32, _lib.VOL_BF16: torch.bfloat16}
+
+
+def geometry(H: int, W: int, L: int):
+    """[(Hl, Wl, Wp_l)] -- mirrors fc_level_dims (include/flowcorr.h) without the library,
+    so fake/meta tracing needs no CUDA."""
+    return [(H >> l, W >> l, ((W >> l) + 7) // 8 * 8) for l in range(L)]
+
+
+def pyramid_numel(B: int, H: int, W: int, L: int) -> int:
+    return sum(B * H * W * h * wp for h, _, wp in geometry(H, W, L))
+
+
+def level_views(pyramid: Tensor, B: int, H: int, W: int, L: int) -> List[Tensor]:
+    """The reference's ``corr_pyramid`` list ((B*N, 1, Hl, Wl), corr.py:14-27) as strided
+    views into the flat pyramid buffer (pad columns sliced away)."""
+    views, off, Q = [], 0, B * H * W
+    for h, w, wp in geometry(H, W, L):
+        n = Q * h * wp
+        views.append(pyramid[off:off + n].view(Q, 1, h, wp)[..., :w])
+        off += n
+    return views
+
+
+def _need_cuda(*tensors: Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("flowcorr ops run on CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor")
+
+
+def _f32c(t: Tensor) -> Tensor:
+    return t.contiguous().float()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ----------------------------------------------------------------------------- build
+@custom_op("flowcorr::build", mutates_args=())
+def build(fmap1: Tensor, fmap2: Tensor, num_levels: int, math: int, vol_dtype: int) -> Tensor:
+    """CorrBlock.__init__ (corr.py:13-27) -> flat pyramid buffer."""
+    _need_cuda(fmap1, fmap2)
+    f1, f2 = _f32c(fmap1), _f32c(fmap2)
+    B, D, H, W = f1.shape
+    lib = _lib.load()
+    with torch.cuda.device(f1.device):
+        pyr = torch.empty(pyramid_numel(B, H, W, num_levels), dtype=_VOL_TORCH[vol_dtype], device=f1.device)
+        ws_bytes = lib.fc_build_workspace_bytes(B, D, H, W, num_levels, math)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=f1.device)
+        _lib.check(lib.fc_build(f1.data_ptr(), f2.data_ptr(), pyr.data_ptr(), B, D, H, W, num_levels,
+                                vol_dtype, math, ws.data_ptr(), ws_bytes, _stream()), "fc_build")
+    return pyr
+
+
+@build.register_fake
+def _(fmap1, fmap2, num_levels, math, vol_dtype):
+    B, D, H, W = fmap1.shape
+    return fmap1.new_empty(pyramid_numel(B, H, W, num_levels), dtype=_VOL_TORCH[vol_dtype])
+
+
+# ----------------------------------------------------------------------------- lookup
+@custom_op("flowcorr::lookup", mutates_args=())
+def lookup(pyramid: Tensor, coords: Tensor, num_levels: int, radius: int, coord_mode: int) -> Tensor:
+    """CorrBlock.__call__ (corr.py:29-50): (B, 2, H, W) -> (B, L*(2r+1)^2, H, W) fp32."""
+    _need_cuda(pyramid, coords)
+    c = _f32c(coords)
+    B, _, H, W = c.shape
+    vol_dtype = _lib.VOL_F32 if pyramid.dtype == torch.float32 else _lib.VOL_BF16
+    with torch.cuda.device(c.device):
+        out = torch.empty(B, num_levels * (2 * radius + 1) ** 2, H, W, dtype=torch.float32, device=c.device)
+        _lib.check(_lib.load().fc_lookup_fwd(pyramid.data_ptr(), c.data_ptr(), out.data_ptr(), B, H, W,
+                                             num_levels, radius, vol_dtype, coord_mode,
+                                             None, None, None, _stream()), "fc_lookup_fwd")
+    return out
+
+
+@lookup.register_fake
+def _(pyramid, coords, num_levels, radius, coord_mode):
+    B, _, H, W = coords.shape
+    return coords.new_empty(B, num_levels * (2 * radius + 1) ** 2, H, W, dtype=torch.float32)
+
+
+@custom_op("flowcorr::lookup_debug", mutates_args=())
+def lookup_debug(pyramid: Tensor, coords: Tensor, num_levels: int, radius: int,
+                 coord_mode: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Lookup plus the integer part: x0/y0 (B*N, L, 2r+1) int32 and the corner-mask
+    bytes (B*N, L, 2r+1, 2r+1) (bit layout in include/flowcorr.h)."""
+    _need_cuda(pyramid, coords)
+    c = _f32c(coords)
+    B, _, H, W = c.shape
+    R = 2 * radius + 1
+    vol_dtype = _lib.VOL_F32 if pyramid.dtype == torch.float32 else _lib.VOL_BF16
+    with torch.cuda.device(c.device):
+        out = torch.empty(B, num_levels * R * R, H, W, dtype=torch.float32, device=c.device)
+        x0 = torch.empty(B * H * W, num_levels, R, dtype=torch.int32, device=c.device)
+        y0 = torch.empty_like(x0)
+        mask = torch.empty(B * H * W, num_levels, R, R, dtype=torch.uint8, device=c.device)
+        _lib.check(_lib.load().fc_lookup_fwd(pyramid.data_ptr(), c.data_ptr(), out.data_ptr(), B, H, W,
+                                             num_levels, radius, vol_dtype, coord_mode,
+                                             x0.data_ptr(), y0.data_ptr(), mask.data_ptr(), _stream()),
+                   "fc_lookup_fwd")
+    return out, x0, y0, mask
+
+
+@lookup_debug.register_fake
+def _(pyramid, coords, num_levels, radius, coord_mode):
+    B, _, H, W = coords.shape
+    R = 2 * radius + 1
+    out = coords.new_empty(B, num_levels * R * R, H, W, dtype=torch.float32)
+    x0 = coords.new_empty(B * H * W, num_levels, R, dtype=torch.int32)
+    return out, x0, torch.empty_like(x0), coords.new_empty(B * H * W, num_levels, R, R, dtype=torch.uint8)
+
+
+# ----------------------------------------------------------------------------- backward
+@custom_op("flowcorr::lookup_bwd", mutates_args=("grad_pyramid",))
+def lookup_bwd(grad_out: Tensor, coords: Tensor, grad_pyramid: Tensor, num_levels: int, radius: int,
+               coord_mode: int) -> None:
+    """Scatter-add one lookup's output gradient into the block's gradient pyramid."""
+    _need_cuda(grad_out, coords, grad_pyramid)
+    g, c = _f32c(grad_out), _f32c(coords)
+    B, _, H, W = c.shape
+    with torch.cuda.device(c.device):
+        _lib.check(_lib.load().fc_lookup_bwd(g.data_ptr(), c.data_ptr(), grad_pyramid.data_ptr(), B, H, W,
+                                             num_levels, radius, coord_mode, _stream()), "fc_lookup_bwd")
+
+
+@custom_op("flowcorr::build_bwd", mutates_args=("grad_pyramid",))
+def build_bwd(grad_pyramid: Tensor, fmap1: Tensor, fmap2: Tensor, num_levels: int,
+              math: int) -> Tuple[Tensor, Tensor]:
+    """Fold the gradient pyramid (consumed) and contract with both feature maps."""
+    _need_cuda(grad_pyramid, fmap1, fmap2)
+    f1, f2 = _f32c(fmap1), _f32c(fmap2)
+    B, D, H, W = f1.shape
+    lib = _lib.load()
+    with torch.cuda.device(f1.device):
+        d1, d2 = torch.empty_like(f1), torch.empty_like(f2)
+        _lib.check(lib.fc_build_bwd(grad_pyramid.data_ptr(), f1.data_ptr(), f2.data_ptr(), d1.data_ptr(),
+                                    d2.data_ptr(), B, D, H, W, num_levels, math, None, 0, _stream()),
+                   "fc_build_bwd")
+    return d1, d2
+
+
+@build_bwd.register_fake
+def _(grad_pyramid, fmap1, fmap2, num_levels, math):
+    return torch.empty_like(fmap1, dtype=torch.float32), torch.empty_like(fmap2, dtype=torch.float32)
+
+
+# ----------------------------------------------------------------------------- on-demand
+@custom_op("flowcorr::ondemand_prepare", mutates_args=())
+def ondemand_prepare(fmap1: Tensor, fmap2: Tensor, num_levels: int) -> Tensor:
+    """AlternateCorrBlock.__init__ (corr.py:64-72): channels-last fmap1 + pooled fmap2 pyramid."""
+    _need_cuda(fmap1, fmap2)
+    f1, f2 = _f32c(fmap1), _f32c(fmap2)
+    B, D, H, W = f1.shape
+    lib = _lib.load()
+    with torch.cuda.device(f1.device):
+        nbytes = lib.fc_ondemand_workspace_bytes(B, D, H, W, num_levels)
+        if nbytes == 0:
+            _lib.check(-1, "fc_ondemand_workspace_bytes")
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=f1.device)
+        _lib.check(lib.fc_ondemand_prepare(f1.data_ptr(), f2.data_ptr(), B, D, H, W, num_levels,
+                                           ws.data_ptr(), nbytes, _stream()), "fc_ondemand_prepare")
+    return ws
+
+
+@ondemand_prepare.register_fake
+def _(fmap1, fmap2, num_levels):
+    B, D, H, W = fmap1.shape
+    n = B * H * W * D + sum(B * (H >> l) * (W >> l) * D for l in range(num_levels))
+    return fmap1.new_empty(n, dtype=torch.float32)
+
+
+@custom_op("flowcorr::ondemand_lookup", mutates_args=())
+def ondemand_lookup(workspace: Tensor, coords: Tensor, dim: int, num_levels: int, radius: int) -> Tensor:
+    """AlternateCorrBlock.__call__ (corr.py:74-91), all levels, scaled by 1/sqrt(D)."""
+    _need_cuda(workspace, coords)
+    c = _f32c(coords)
+    B, _, H, W = c.shape
+    with torch.cuda.device(c.device):
+        out = torch.empty(B, num_levels * (2 * radius + 1) ** 2, H, W, dtype=torch.float32, device=c.device)
+        _lib.check(_lib.load().fc_ondemand_fwd(workspace.data_ptr(), c.data_ptr(), out.data_ptr(), B, dim, H, W,
+                                               num_levels, radius, _stream()), "fc_ondemand_fwd")
+    return out
+
+
+@ondemand_lookup.register_fake
+def _(workspace, coords, dim, num_levels, radius):
+    B, _, H, W = coords.shape
+    return coords.new_empty(B, num_levels * (2 * radius + 1) ** 2, H, W, dtype=torch.float32)
+
+
+@custom_op("flowcorr::altcorr_fwd", mutates_args=())
+def altcorr_fwd(fmap1: Tensor, fmap2: Tensor, coords: Tensor, radius: int) -> Tensor:
+    """alt_cuda_corr.forward (correlation.cpp:23-33): one level, channels-last, unscaled."""
+    B, H1, W1, Cc = fmap1.shape
+    _, H2, W2, _ = fmap2.shape
+    R = 2 * radius + 1
+    with torch.cuda.device(fmap1.device):
+        corr = torch.empty(B, 1, R * R, H1, W1, dtype=torch.float32, device=fmap1.device)
+        _lib.check(_lib.load().fc_altcorr_fwd(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr(),
+                                              corr.data_ptr(), B, H1, W1, H2, W2, Cc, radius, _stream()),
+                   "fc_altcorr_fwd")
+    return corr
+
+
+@altcorr_fwd.register_fake
+def _(fmap1, fmap2, coords, radius):
+    B, H1, W1, _ = fmap1.shape
+    R = 2 * radius + 1
+    return fmap1.new_empty(B, 1, R * R, H1, W1, dtype=torch.float32)
+
+
+@custom_op("flowcorr::altcorr_bwd", mutates_args=())
+def altcorr_bwd(fmap1: Tensor, fmap2: Tensor, coords: Tensor, corr_grad: Tensor,
+                radius: int) -> Tuple[Tensor, Tensor]:
+    """alt_cuda_corr.backward (correlation.cpp:36-48) -> (fmap1_grad, fmap2_grad)."""
+    B, H1, W1, Cc = fmap1.shape
+    _, H2, W2, _ = fmap2.shape
+    with torch.cuda.device(fmap1.device):
+        d1, d2 = torch.empty_like(fmap1), torch.empty_like(fmap2)
+        _lib.check(_lib.load().fc_altcorr_bwd(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr(),
+                                              corr_grad.data_ptr(), d1.data_ptr(), d2.data_ptr(),
+                                              B, H1, W1, H2, W2, Cc, radius, _stream()), "fc_altcorr_bwd")
+    return d1, d2
+
+
+@altcorr_bwd.register_fake
+def _(fmap1, fmap2, coords, corr_grad, radius):
+    return torch.empty_like(fmap1), torch.empty_like(fmap2)

@@ -288,6 +288,48 @@ def ondemand_lookup(fmap1, fmap2, coords, num_levels=4, radius=4, scale=True):
     return np.ascontiguousarray(out, dtype=F32)
 
 
+def ondemand_backward(fmap1, fmap2, coords, grad_corr, radius=4):
+    """Adjoint of ONE unscaled level of ``ondemand_lookup`` w.r.t. both feature maps:
+    the semantics of corr_backward_kernel (correlation_kernel.cu:122-256; exported by
+    correlation.cpp:53 but never called by the reference).  grad_corr: (B, R*R, H, W)
+    with channel = ix*R + iy.  fp64.  coords get no gradient (the reference leaves
+    coords_grad at zero, correlation_kernel.cu:307)."""
+    B, D, H, W = fmap1.shape
+    N = H * W
+    R = 2 * radius + 1
+    f1 = fmap1.reshape(B, D, N).astype(np.float64)
+    f2 = fmap2.reshape(B, D, N).astype(np.float64)
+    g = grad_corr.reshape(B, R, R, N).astype(np.float64)            # [ix][iy]
+    cx = coords[:, 0].reshape(B, N).astype(F32)
+    cy = coords[:, 1].reshape(B, N).astype(F32)
+    xf, yf = np.floor(cx), np.floor(cy)
+    dx, dy = (cx - xf).astype(np.float64), (cy - yf).astype(np.float64)
+    x0, y0 = xf.astype(np.int64), yf.astype(np.int64)
+    d1 = np.zeros_like(f1)
+    d2 = np.zeros_like(f2)
+    bidx = np.arange(B)[:, None]
+    for iy in range(R + 1):
+        for ix in range(R + 1):
+            ds = np.zeros((B, N))
+            if iy > 0 and ix > 0:
+                ds += g[:, ix - 1, iy - 1] * dy * dx
+            if iy > 0 and ix < R:
+                ds += g[:, ix, iy - 1] * dy * (1 - dx)
+            if iy < R and ix > 0:
+                ds += g[:, ix - 1, iy] * (1 - dy) * dx
+            if iy < R and ix < R:
+                ds += g[:, ix, iy] * (1 - dy) * (1 - dx)
+            h2 = y0 - radius + iy
+            w2 = x0 - radius + ix
+            ok = (h2 >= 0) & (h2 < H) & (w2 >= 0) & (w2 < W)
+            ds = np.where(ok, ds, 0.0)
+            lin = np.clip(h2, 0, H - 1) * W + np.clip(w2, 0, W - 1)
+            d1 += ds[:, None, :] * np.take_along_axis(f2, lin[:, None, :], axis=2)
+            for d in range(D):
+                np.add.at(d2[:, d], (bidx, lin), ds * f1[:, d])
+    return d1.reshape(B, D, H, W).astype(F32), d2.reshape(B, D, H, W).astype(F32)
+
+
 def coords_grid(B: int, H: int, W: int) -> np.ndarray:
     """utils.py:74-77: (B, 2, H, W) fp32, channel 0 = x, channel 1 = y."""
     ys, xs = np.meshgrid(np.arange(H, dtype=F32), np.arange(W, dtype=F32), indexing="ij")
