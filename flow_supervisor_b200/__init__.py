@@ -5,6 +5,7 @@ Host-side mirror of the reference interface for ONE path: ``pytorch/core/corr.py
 All arithmetic runs in hand-written CUDA kernels behind the C ABI of
 ``include/flowcorr.h`` (``libflowcorr.so``); there is no CPU or PyTorch fallback.
 """
+from . import ops  # noqa: F401
 from .corr import AlternateCorrBlock, CorrBlock, coords_grid  # noqa: F401
 from .patch import patch_reference  # noqa: F401
 

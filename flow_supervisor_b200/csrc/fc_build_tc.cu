@@ -1,14 +1,427 @@
-// tcgen05 / TMEM build path (placeholder until the tensor-core kernel lands).
+// Tensor-core build of the correlation volume (CorrBlock.__init__, corr.py:13-27,52-60)
+// for sm_100a: TMA-fed tcgen05.mma with TMEM accumulators.
+//
+//   pack pre-pass : (B, D, N) fp32 NCHW  ->  K-major bf16 rows [row][D], hi = bf16(x) and
+//                   lo = bf16(x - hi).  fmap1 rows = queries p; fmap2 rows = PADDED targets
+//                   q' = y*Wp + x (pad rows are zero, so pad columns of the volume come out
+//                   as exact zeros and need no masking).
+//   GEMM          : one CTA per (sample, 128-query tile).  The query operand (hi and lo, all
+//                   of K) stays resident in shared memory; target tiles of NT = 2 rows x Wp
+//                   (or 1 row when 2*Wp > 256) stream through a 4-stage TMA ring in
+//                   128-row x 64-k sub-stages.  FC_MATH_TC_3XBF16 issues hi*hi + lo*hi + hi*lo
+//                   into the same fp32 TMEM accumulator (error ~4e-6);
+//                   FC_MATH_TC_BF16 issues hi*hi only.  Two 256-column accumulators double
+//                   buffer the MMA against the epilogue.
+//   epilogue      : 4 warps, tcgen05.ld 32 lanes x 32 columns, scale by 1/sqrt(D), transpose
+//                   through shared memory so every global store instruction writes whole
+//                   128-byte rows of the (B*N, H, Wp) level-0 volume.
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 =
+// epilogue (TMEM lane quarter = warp_id % 4).
+#include <cuda.h>
+
 #include "fc_common.cuh"
 
 namespace fc {
 
-size_t tc_build_workspace_bytes(int, int, int, int, int, int) { return 0; }
+int simt_pool_levels(float* pyramid, const Pyramid& pyr, cudaStream_t s);   // fc_simt.cu
 
-int tc_build(const float*, const float*, void*, const Pyramid&, int, int, int, int, int, void*, size_t,
-             cudaStream_t) {
-    set_error("fc_build: tensor-core math modes are not available in this build");
-    return FC_EINVAL;
+constexpr int TC_THREADS = 192;
+constexpr int TC_BM = 128;           // queries per CTA (UMMA M)
+constexpr int TC_BK = 64;            // bf16 elements per 128-byte swizzle row
+constexpr int TC_SUB = 128;          // target rows per ring stage
+constexpr int TC_STAGES = 4;
+constexpr int TC_STAGE_BYTES = TC_SUB * TC_BK * 2;        // 16 KB
+constexpr int TC_ABLK_BYTES = TC_BM * TC_BK * 2;          // 16 KB per k-block of the query tile
+constexpr int TC_STG_PITCH = 36;                          // floats; staging row pitch (16B aligned, conflict-free)
+constexpr int TC_STG_BYTES = 4 * 32 * TC_STG_PITCH * 4;   // 18 KB
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 | LBO(1)<<16 | SBO(1024>>4)<<32 | version(1)<<46 | layout SWIZZLE_128B(2)<<61
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor, kind::f16: D=F32 (bit 4), A=B=BF16 (bits 7, 10), K-major both,
+// N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- pack pre-pass
+// src (B, D, N) fp32 -> hi/lo [b*rows_per_sample + row(n)][D] bf16, row(n) = (n / W) * Wp + n % W
+__global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, int D, int N, int W, int Wp,
+                                 int rows_per_sample) {
+    __shared__ float tile[64][33];
+    const int b = blockIdx.z, n0 = blockIdx.x * 32, d0 = blockIdx.y * 64;
+    const int tx = threadIdx.x, ty = threadIdx.y;            // 32 x 8
+    const float* s = src + (long long)b * D * N;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int d = d0 + ty + 8 * i, n = n0 + tx;
+        tile[ty + 8 * i][tx] = (d < D && n < N) ? s[(long long)d * N + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int nl = ty + 8 * i, n = n0 + nl;
+        const int d = d0 + 2 * tx;
+        if (n < N && d < D) {
+            const int row = (n / W) * Wp + (n % W);
+            const float x0 = tile[2 * tx][nl], x1 = tile[2 * tx + 1][nl];
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+            const long long o = ((long long)b * rows_per_sample + row) * D + d;
+            *reinterpret_cast<__nv_bfloat162*>(hi + o) = __nv_bfloat162(h0, h1);
+            if (lo != nullptr)
+                *reinterpret_cast<__nv_bfloat162*>(lo + o) = __nv_bfloat162(
+                    __float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- GEMM
+struct TcParams {
+    float* vol0;           // level 0: (B*N, NP)
+    int N, NP, H, Wp;      // queries per sample, padded targets per sample
+    int NT;                // padded targets per tile (multiple of 16, <= 256)
+    int n_tiles;           // ceil(NP / NT)
+    int m_tiles;           // ceil(N / 128)
+    int sub1;              // rows of the second ring sub-stage (NT - 128, or 0)
+    int three_pass;        // 1 = hi*hi + lo*hi + hi*lo, 0 = hi*hi
+    float scale;           // 1 / sqrt(D)
+};
+
+template <int KB>   // KB = D / 64 k-blocks
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const __grid_constant__ CUtensorMap map_b_hi1, const __grid_constant__ CUtensorMap map_b_lo1,
+                const TcParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve (all operand regions 1024-byte aligned for SWIZZLE_128B)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_hi = smem;
+    uint8_t* a_lo = a_hi + KB * TC_ABLK_BYTES;
+    uint8_t* ring = a_lo + KB * TC_ABLK_BYTES;
+    float* stg = reinterpret_cast<float*>(ring + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg) + TC_STG_BYTES);
+    uint64_t* a_full = bars;                       // 1
+    uint64_t* b_full = bars + 1;                   // TC_STAGES
+    uint64_t* b_empty = b_full + TC_STAGES;        // TC_STAGES
+    uint64_t* t_full = b_empty + TC_STAGES;        // 2
+    uint64_t* t_empty = t_full + 2;                // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y, m0 = blockIdx.x * TC_BM;
+    const int n_parts = P.three_pass ? 2 : 1;
+    const int n_subs = P.sub1 > 0 ? 2 : 1;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_expect_tx(a_full, (uint32_t)(n_parts * KB * TC_ABLK_BYTES));
+            for (int kb = 0; kb < KB; ++kb) {
+                tma_load_2d(a_hi + kb * TC_ABLK_BYTES, &map_a_hi, a_full, kb * TC_BK, b * P.N + m0);
+                if (P.three_pass) tma_load_2d(a_lo + kb * TC_ABLK_BYTES, &map_a_lo, a_full, kb * TC_BK, b * P.N + m0);
+            }
+            int it = 0;
+            for (int t = 0; t < P.n_tiles; ++t) {
+                const int row0 = b * P.NP + t * P.NT;
+                for (int kb = 0; kb < KB; ++kb)
+                    for (int part = 0; part < n_parts; ++part)
+                        for (int sub = 0; sub < n_subs; ++sub, ++it) {
+                            const int s = it % TC_STAGES;
+                            const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                            mbar_wait(b_empty + s, ph ^ 1u);
+                            const int rows = sub == 0 ? (P.NT < TC_SUB ? P.NT : TC_SUB) : P.sub1;
+                            mbar_expect_tx(b_full + s, (uint32_t)(rows * TC_BK * 2));
+                            const CUtensorMap* m = sub == 0 ? (part == 0 ? &map_b_hi : &map_b_lo)
+                                                            : (part == 0 ? &map_b_hi1 : &map_b_lo1);
+                            tma_load_2d(ring + s * TC_STAGE_BYTES, m, b_full + s, kb * TC_BK, row0 + sub * TC_SUB);
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const int rows0 = P.NT < TC_SUB ? P.NT : TC_SUB;
+            const uint32_t idesc0 = umma_idesc_bf16(TC_BM, rows0);
+            const uint32_t idesc1 = umma_idesc_bf16(TC_BM, P.sub1 > 0 ? P.sub1 : 16);
+            mbar_wait(a_full, 0);
+            tc_fence_after();
+            int it = 0;
+            for (int t = 0; t < P.n_tiles; ++t) {
+                const int buf = t & 1;
+                mbar_wait(t_empty + buf, ((uint32_t)(t >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb)
+                    for (int part = 0; part < n_parts; ++part)
+                        for (int sub = 0; sub < n_subs; ++sub, ++it) {
+                            const int s = it % TC_STAGES;
+                            mbar_wait(b_full + s, (uint32_t)(it / TC_STAGES) & 1u);
+                            tc_fence_after();
+                            const uint32_t d_addr = tmem_base + (uint32_t)(buf * 256 + sub * TC_SUB);
+                            const uint32_t idesc = sub == 0 ? idesc0 : idesc1;
+                            const uint32_t b_addr = smem_u32(ring + s * TC_STAGE_BYTES);
+                            const uint32_t ah_addr = smem_u32(a_hi + kb * TC_ABLK_BYTES);
+                            const uint32_t al_addr = smem_u32(a_lo + kb * TC_ABLK_BYTES);
+#pragma unroll
+                            for (int k = 0; k < TC_BK / 16; ++k) {
+                                const uint64_t bd = umma_desc_sw128(b_addr + k * 32);
+                                // part 0: B = hi -> A_hi*B_hi (+ A_lo*B_hi); part 1: B = lo -> A_hi*B_lo
+                                umma_bf16(d_addr, umma_desc_sw128(ah_addr + k * 32), bd, idesc,
+                                          (kb | part | k) != 0 ? 1u : 0u);
+                                if (part == 0 && P.three_pass)
+                                    umma_bf16(d_addr, umma_desc_sw128(al_addr + k * 32), bd, idesc, 1u);
+                            }
+                            umma_commit(b_empty + s);          // frees the ring slot when these MMAs retire
+                        }
+                umma_commit(t_full + buf);                      // accumulator complete
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32)
+        float* my = stg + quarter * 32 * TC_STG_PITCH;
+        const long long row_base = (long long)b * P.N + m0 + quarter * 32;
+        const int rows_valid = P.N - (m0 + quarter * 32);      // rows of this warp inside the sample
+        for (int t = 0; t < P.n_tiles; ++t) {
+            const int buf = t & 1;
+            mbar_wait(t_full + buf, (uint32_t)(t >> 1) & 1u);
+            tc_fence_after();
+            const int q0 = t * P.NT;                           // first padded target of the tile
+            const int ncols = min(P.NT, P.NP - q0);
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256 + c0), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(my + lane * TC_STG_PITCH + 4 * j) =
+                        make_float4(v[4 * j] * P.scale, v[4 * j + 1] * P.scale, v[4 * j + 2] * P.scale, v[4 * j + 3] * P.scale);
+                __syncwarp();
+                const int c4 = lane & 7;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 4 * i + (lane >> 3);
+                    if (r < rows_valid && c0 + 4 * c4 < ncols) {
+                        const float4 x = *reinterpret_cast<const float4*>(my + r * TC_STG_PITCH + 4 * c4);
+                        *reinterpret_cast<float4*>(P.vol0 + (row_base + r) * P.NP + q0 + c0 + 4 * c4) = x;
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + buf);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// 2-D bf16 row-major [rows][cols] tensor, box {64 cols, box_rows}, 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* base, long long rows, int cols, int box_rows) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FC_ECUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return FC_ECUDA; }
+    return FC_OK;
+}
+
+struct TcLayout { size_t a_hi, a_lo, b_hi, b_lo, total; long long NP; };
+
+static TcLayout tc_layout(int B, int D, int H, int W) {
+    TcLayout L;
+    const long long N = (long long)H * W, NP = (long long)H * round_up(W, 8);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
+    L.a_hi = take((size_t)B * N * D * 2);
+    L.a_lo = take((size_t)B * N * D * 2);
+    L.b_hi = take((size_t)B * NP * D * 2);
+    L.b_lo = take((size_t)B * NP * D * 2);
+    L.total = off; L.NP = NP;
+    return L;
+}
+
+size_t tc_build_workspace_bytes(int B, int D, int H, int W, int, int) {
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+    return tc_layout(B, D, H, W).total + 1024;   // slack to align the base to 1 KB
+}
+
+template <int KB>
+static int launch_tc(const CUtensorMap* maps, const TcParams& P, int B, cudaStream_t s) {
+    const size_t smem = 1024 + 2 * KB * TC_ABLK_BYTES + TC_STAGES * TC_STAGE_BYTES + TC_STG_BYTES + 256;
+    FC_CUDA(cudaFuncSetAttribute(tc_build_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(P.m_tiles, B);
+    tc_build_kernel<KB><<<grid, TC_THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], P);
+    FC_LAUNCH_CHECK("tc_build_kernel");
+    return FC_OK;
+}
+
+int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr, int D, int H, int W,
+             int vol_dtype, int math, void* ws, size_t ws_bytes, cudaStream_t s) {
+    FC_REQUIRE(vol_dtype == FC_VOL_F32, "fc_build: tensor-core modes write an fp32 volume (bf16 volume not built yet)");
+    FC_REQUIRE(D % 64 == 0 && D <= 256, "fc_build: tensor-core modes need D %% 64 == 0 and D <= 256 (got %d); use FC_MATH_FP32", D);
+    const int Wp = pyr.lv[0].Wp;
+    FC_REQUIRE(Wp <= 256, "fc_build: tensor-core modes need W <= 256 tokens (got %d); use FC_MATH_FP32", W);
+    const int B = pyr.B;
+    const TcLayout L = tc_layout(B, D, H, W);
+    if (!ws || ws_bytes < L.total) { set_error("fc_build: workspace %zu < %zu bytes", ws_bytes, L.total); return FC_EWORKSPACE; }
+    uint8_t* w8 = static_cast<uint8_t*>(ws);
+    // align the workspace base to 1 KB ourselves (torch allocations are 512-byte aligned)
+    const size_t shift = (1024 - (reinterpret_cast<uintptr_t>(w8) & 1023)) & 1023;
+    if (ws_bytes < L.total + shift) { set_error("fc_build: workspace %zu < %zu bytes (after alignment)", ws_bytes, L.total + shift); return FC_EWORKSPACE; }
+    w8 += shift;
+    const bool three = (math == FC_MATH_TC_3XBF16);
+    __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(w8 + L.a_hi);
+    __nv_bfloat16* a_lo = reinterpret_cast<__nv_bfloat16*>(w8 + L.a_lo);
+    __nv_bfloat16* b_hi = reinterpret_cast<__nv_bfloat16*>(w8 + L.b_hi);
+    __nv_bfloat16* b_lo = reinterpret_cast<__nv_bfloat16*>(w8 + L.b_lo);
+    const int N = pyr.N;
+    const long long NP = L.NP;
+
+    if (Wp != W) {   // pad rows of the target operand must be zero
+        FC_CUDA(cudaMemsetAsync(b_hi, 0, (size_t)B * NP * D * 2, s));
+        if (three) FC_CUDA(cudaMemsetAsync(b_lo, 0, (size_t)B * NP * D * 2, s));
+    }
+    dim3 pb(32, 8), pg((N + 31) / 32, (D + 63) / 64, B);
+    pack_bf16_kernel<<<pg, pb, 0, s>>>(f1, a_hi, three ? a_lo : nullptr, D, N, W, W, N);
+    pack_bf16_kernel<<<pg, pb, 0, s>>>(f2, b_hi, three ? b_lo : nullptr, D, N, W, Wp, (int)NP);
+    FC_LAUNCH_CHECK("pack_bf16_kernel");
+
+    TcParams P{};
+    P.vol0 = static_cast<float*>(pyramid) + pyr.lv[0].offset;
+    P.N = N; P.NP = (int)NP; P.H = H; P.Wp = Wp;
+    P.NT = (2 * Wp <= 256) ? 2 * Wp : Wp;
+    if (P.NT % 16 != 0) P.NT = round_up(P.NT, 16);     // single-row tile with Wp % 16 == 8: over-read 8 targets, masked at the store
+    P.n_tiles = (int)((NP + P.NT - 1) / P.NT);
+    P.m_tiles = (N + TC_BM - 1) / TC_BM;
+    P.sub1 = P.NT > TC_SUB ? P.NT - TC_SUB : 0;
+    P.three_pass = three ? 1 : 0;
+    P.scale = 1.0f / sqrtf((float)D);
+
+    CUtensorMap maps[6];
+    const int rows0 = P.NT < TC_SUB ? P.NT : TC_SUB;
+    const int rows1 = P.sub1 > 0 ? P.sub1 : 16;
+    if (int e = make_map(&maps[0], a_hi, (long long)B * N, D, TC_BM)) return e;
+    if (int e = make_map(&maps[1], three ? a_lo : a_hi, (long long)B * N, D, TC_BM)) return e;
+    if (int e = make_map(&maps[2], b_hi, (long long)B * NP, D, rows0)) return e;
+    if (int e = make_map(&maps[3], three ? b_lo : b_hi, (long long)B * NP, D, rows0)) return e;
+    if (int e = make_map(&maps[4], b_hi, (long long)B * NP, D, rows1)) return e;
+    if (int e = make_map(&maps[5], three ? b_lo : b_hi, (long long)B * NP, D, rows1)) return e;
+
+    int e;
+    switch (D / 64) {
+        case 1: e = launch_tc<1>(maps, P, B, s); break;
+        case 2: e = launch_tc<2>(maps, P, B, s); break;
+        case 3: e = launch_tc<3>(maps, P, B, s); break;
+        default: e = launch_tc<4>(maps, P, B, s); break;
+    }
+    if (e) return e;
+    return simt_pool_levels(static_cast<float*>(pyramid), pyr, s);
 }
 
 }  // namespace fc
