@@ -11,7 +11,10 @@ Arithmetic lives in libflowcorr.so (CUDA, sm_100a).  Differences to the referenc
 that a caller can observe are listed in DESIGN.md ("Behavioural notes").
 
 Modes (class attributes, or environment variables read at import):
-    CorrBlock.math       'fp32' | '3xbf16' | 'bf16'   (FLOWCORR_MATH;  default fp32-parity)
+    CorrBlock.math       'auto' | 'fp32' | '3xbf16' | 'bf16'   (FLOWCORR_MATH; default 'auto' =
+                          '3xbf16' tensor-core parity mode when the shape allows it
+                          (D % 64 == 0, D <= 256, W <= 256 tokens), else 'fp32' CUDA-core mode;
+                          both are this library's own kernels and both meet the 1e-4 contract)
     CorrBlock.volume     'f32'  | 'bf16'              (FLOWCORR_VOLUME)
     CorrBlock.coord_mode 'cuda' | 'cpu'               (FLOWCORR_COORD; which device's
                           rounding of utils.py:61-62 to reproduce; default 'cuda')
@@ -27,6 +30,12 @@ from . import _lib, ops
 _MATH = {"fp32": _lib.MATH_FP32, "3xbf16": _lib.MATH_TC_3XBF16, "bf16": _lib.MATH_TC_BF16}
 _VOL = {"f32": _lib.VOL_F32, "bf16": _lib.VOL_BF16}
 _COORD = {"cuda": _lib.COORD_CUDA, "cpu": _lib.COORD_CPU}
+
+
+def resolve_math(name: str, D: int, W: int) -> int:
+    if name == "auto":
+        name = "3xbf16" if (D % 64 == 0 and D <= 256 and (W + 7) // 8 * 8 <= 256) else "fp32"
+    return _MATH[name]
 
 
 def coords_grid(batch, ht, wd, device=None):
@@ -90,7 +99,7 @@ class _Lookup(torch.autograd.Function):
 
 
 class CorrBlock:
-    math = os.environ.get("FLOWCORR_MATH", "fp32")
+    math = os.environ.get("FLOWCORR_MATH", "auto")
     volume = os.environ.get("FLOWCORR_VOLUME", "f32")
     coord_mode = os.environ.get("FLOWCORR_COORD", "cuda")
 
@@ -106,7 +115,7 @@ class CorrBlock:
         st = self._state = _BlockState()
         st.B, _, st.H, st.W = fmap1.shape
         st.L, st.radius = num_levels, radius
-        st.math, st.coord = _MATH[self.math], _COORD[self.coord_mode]
+        st.math, st.coord = resolve_math(self.math, fmap1.shape[1], st.W), _COORD[self.coord_mode]
         self._vol_dtype = _VOL[self.volume]
         fmap1, fmap2 = fmap1.float(), fmap2.float()
         self._token = None
@@ -141,7 +150,8 @@ class CorrBlock:
     def corr(fmap1, fmap2):
         """corr.py:52-60: (B, H, W, 1, H, W) all-pairs volume (level 0 only)."""
         B, D, H, W = fmap1.shape
-        pyr = ops.build(fmap1.detach().float(), fmap2.detach().float(), 1, _MATH[CorrBlock.math], _lib.VOL_F32)
+        pyr = ops.build(fmap1.detach().float(), fmap2.detach().float(), 1, resolve_math(CorrBlock.math, D, W),
+                        _lib.VOL_F32)
         return ops.level_views(pyr, B, H, W, 1)[0].reshape(B, H, W, 1, H, W)
 
 

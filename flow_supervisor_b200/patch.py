@@ -14,6 +14,7 @@ from . import alt_cuda_corr as _alt
 from .corr import AlternateCorrBlock, CorrBlock
 
 _NAMES = {"CorrBlock": CorrBlock, "AlternateCorrBlock": AlternateCorrBlock}
+_ORIGINALS = []          # (module, attribute, original object) for unpatch_reference()
 
 
 def patch_reference(verbose: bool = False):
@@ -31,6 +32,7 @@ def patch_reference(verbose: bool = False):
                 continue
             origin = getattr(cur, "__module__", "") or ""
             if origin.split(".")[-1] in ("corr", "gma_corr"):
+                _ORIGINALS.append((mod, attr, cur))
                 setattr(mod, attr, repl)
                 patched.append((mod_name, attr))
         if getattr(mod, "alt_cuda_corr", None) is not None and mod_name.split(".")[-1] in ("corr", "gma_corr"):
@@ -39,3 +41,11 @@ def patch_reference(verbose: bool = False):
         for m, a in patched:
             print(f"[flowcorr] patched {m}.{a}")
     return patched
+
+
+def unpatch_reference():
+    """Undo patch_reference(): restore the reference's own classes (the alt_cuda_corr shim
+    stays registered; the reference treats that module as optional, corr.py:5-9)."""
+    while _ORIGINALS:
+        mod, attr, orig = _ORIGINALS.pop()
+        setattr(mod, attr, orig)

@@ -1,0 +1,109 @@
+"""CPU: host-side logic of the drop-in layer -- no-fallback behaviour, reference patching,
+batch sharding (single process and world_size-2 gloo)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import flow_supervisor_b200 as fsb
+from flow_supervisor_b200 import shard
+
+REF = "/root/reference/pytorch"
+
+
+def test_no_cpu_fallback():
+    f = torch.zeros(1, 8, 16, 16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fsb.CorrBlock(f, f)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fsb.AlternateCorrBlock(f, f)
+    from flow_supervisor_b200 import alt_cuda_corr
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):      # correlation.cpp:19
+        alt_cuda_corr.forward(f, f, torch.zeros(1, 1, 16, 16, 2), 4)
+
+
+def test_custom_ops_registered_with_fake_impls():
+    for name in ["build", "lookup", "lookup_bwd", "build_bwd", "ondemand_prepare", "ondemand_lookup",
+                 "altcorr_fwd", "altcorr_bwd"]:
+        assert hasattr(torch.ops.flowcorr, name)
+    # meta tracing needs neither CUDA nor the library
+    f = torch.empty(2, 256, 46, 62, device="meta")
+    pyr = torch.ops.flowcorr.build(f, f, 4, 0, 0)
+    assert pyr.numel() == fsb.ops.pyramid_numel(2, 46, 62, 4)
+    out = torch.ops.flowcorr.lookup(pyr, torch.empty(2, 2, 46, 62, device="meta"), 4, 4, 0)
+    assert tuple(out.shape) == (2, 324, 46, 62)
+
+
+def test_coords_grid_axis_order():
+    g = fsb.coords_grid(2, 3, 5)
+    assert tuple(g.shape) == (2, 2, 3, 5)
+    assert torch.equal(g[0, 0, 0], torch.arange(5.0)) and torch.equal(g[1, 1, :, 0], torch.arange(3.0))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="live reference only exists in the build container")
+def test_patch_reference_rebinds_every_import_site():
+    sys.path.insert(0, REF)
+    import core.corr, core.raft, core.l2l, core.gma_corr, core.gma_network, core.gma_l2l  # noqa: E401
+    patched = fsb.patch_reference()
+    try:
+        _check_patched(core, patched)
+    finally:
+        fsb.unpatch_reference()
+    assert core.raft.CorrBlock is core.corr.CorrBlock and core.corr.CorrBlock is not fsb.CorrBlock
+
+
+def _check_patched(core, patched):
+    for mod in (core.corr, core.raft, core.l2l, core.gma_corr, core.gma_network, core.gma_l2l):
+        assert mod.CorrBlock is fsb.CorrBlock, mod.__name__
+    for mod in (core.corr, core.raft, core.l2l):
+        assert mod.AlternateCorrBlock is fsb.AlternateCorrBlock, mod.__name__
+    assert sys.modules["alt_cuda_corr"].forward is not None
+    assert ("core.raft", "CorrBlock") in patched
+    # the patched model now refuses CPU inputs instead of silently using another path
+    import argparse
+    model = core.raft.RAFT(argparse.Namespace(small=False, mixed_precision=False, alternate_corr=False)).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.zeros(1, 3, 128, 128), torch.zeros(1, 3, 128, 128), iters=1, test_mode=True)
+
+
+def test_partition_covers_everything_once():
+    for n in (0, 1, 7, 8, 9, 64):
+        for w in (1, 2, 3, 8):
+            parts = shard.partition(n, w)
+            assert len(parts) == w and parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, n_items, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gen = torch.Generator().manual_seed(0)
+        a = torch.randn(n_items, 4, 6, 8, generator=gen)
+        b = torch.randn(n_items, 4, 6, 8, generator=gen)
+        calls = []
+
+        def fn(x, y):                       # stands in for a per-rank RAFT forward
+            calls.append(x.shape[0])
+            return (x * y).sum(dim=1, keepdim=True) + x.shape[0] * 0.0
+        full = shard.run_sharded(fn, a, b)
+        want = (a * b).sum(dim=1, keepdim=True)
+        ok = torch.equal(full, want) and calls == [shard.partition(n_items, world)[rank][1]
+                                                   - shard.partition(n_items, world)[rank][0]]
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_items", [8, 5, 1])
+def test_run_sharded_world2_gloo(n_items):
+    world, port = 2, 29500 + os.getpid() % 2000 + n_items
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, n_items, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Summarise ncu outputs into small text files for profiles/.
+
+    python tools/ncu_summary.py launches <launches.csv>           # per-kernel time shares
+    python tools/ncu_summary.py full <report.ncu-rep>             # key metrics per captured launch
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "smsp__inst_executed.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+        "launch__shared_mem_per_block_static"]
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr = rows[0]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        try:
+            agg.setdefault(r[ki], []).append(float(r[vi].replace(",", "")))
+        except ValueError:
+            pass
+    tot = sum(sum(v) for v in agg.values())
+    print(f"# {path}: {sum(len(v) for v in agg.values())} launches, {tot / 1e3:.1f} us total (cold-cache, serialised)")
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        print(f"{k[:90]:90s} n={len(v):4d} avg={sum(v) / len(v) / 1e3:9.1f} us  share={sum(v) / tot:6.1%}")
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        print("---", r[hdr.index("Kernel Name")][:100])
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"  {k:78s} {r[i]:>16s} {units[i]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
