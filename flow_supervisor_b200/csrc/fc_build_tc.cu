@@ -19,12 +19,13 @@
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 =
 // epilogue (TMEM lane quarter = warp_id % 4).
 #include <cuda.h>
+#include <cstdlib>
 
 #include "fc_common.cuh"
 
 namespace fc {
 
-int simt_pool_levels(float* pyramid, const Pyramid& pyr, cudaStream_t s);   // fc_simt.cu
+int simt_pool_levels(float* pyramid, const Pyramid& pyr, int first_level, cudaStream_t s);   // fc_simt.cu
 
 constexpr int TC_THREADS = 192;
 constexpr int TC_BM = 128;           // queries per CTA (UMMA M)
@@ -139,6 +140,10 @@ __global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 
 // ---------------------------------------------------------------- GEMM
 struct TcParams {
+    float* lvl[4];         // fused pyramid: level base pointers (level 0 == vol0)
+    int lvH[4], lvW[4], lvWp[4];
+    int n_fused;           // levels written by the epilogue (1 = level 0 only)
+    int W;                 // valid target columns of level 0
     float* vol0;           // level 0: (B*N, NP)
     int N, NP, H, Wp;      // queries per sample, padded targets per sample
     int NT;                // padded targets per tile (multiple of 16, <= 256)
@@ -259,35 +264,133 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         float* my = stg + quarter * 32 * TC_STG_PITCH;
         const long long row_base = (long long)b * P.N + m0 + quarter * 32;
         const int rows_valid = P.N - (m0 + quarter * 32);      // rows of this warp inside the sample
-        for (int t = 0; t < P.n_tiles; ++t) {
-            const int buf = t & 1;
-            mbar_wait(t_full + buf, (uint32_t)(t >> 1) & 1u);
-            tc_fence_after();
-            const int q0 = t * P.NT;                           // first padded target of the tile
-            const int ncols = min(P.NT, P.NP - q0);
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256 + c0), v);
-                tmem_ld_wait();
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+        // 32 values per thread (one query row each) -> [32 rows][ncols] block of a level:
+        // transposed through shared memory so each store instruction writes whole row segments
+        auto store_chunk = [&](float* base, long long pitch, long long off, int ncols, const float* v) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(my + lane * TC_STG_PITCH + 4 * j) =
-                        make_float4(v[4 * j] * P.scale, v[4 * j + 1] * P.scale, v[4 * j + 2] * P.scale, v[4 * j + 3] * P.scale);
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(my + lane * TC_STG_PITCH + 4 * j) =
+                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            const int c4 = lane & 7;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + (lane >> 3);
+                if (r < rows_valid && 4 * c4 < ncols)
+                    *reinterpret_cast<float4*>(base + (row_base + r) * pitch + off + 4 * c4) =
+                        *reinterpret_cast<const float4*>(my + r * TC_STG_PITCH + 4 * c4);
+            }
+            __syncwarp();
+        };
+
+        if (P.n_fused <= 1) {
+            for (int t = 0; t < P.n_tiles; ++t) {
+                const int buf = t & 1;
+                mbar_wait(t_full + buf, (uint32_t)(t >> 1) & 1u);
+                tc_fence_after();
+                const int q0 = t * P.NT;                       // first padded target of the tile
+                const int ncols = min(P.NT, P.NP - q0);
+                for (int c0 = 0; c0 < ncols; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(lane_addr + (uint32_t)(buf * 256 + c0), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= P.scale;
+                    store_chunk(P.vol0, P.NP, q0 + c0, ncols - c0, v);
+                }
+                tc_fence_before();
                 __syncwarp();
-                const int c4 = lane & 7;
+                if (lane == 0) mbar_arrive(t_empty + buf);
+            }
+        } else {
+            // Fused pyramid.  Tile t = target rows 2t (columns [0, Wp)) and 2t+1 (columns
+            // [Wp, 2Wp)) of THIS thread's query: every 2x2 pooling partner is thread-local.
+            // Levels 2 / 3 combine two / four consecutive tiles through the stashes s2 / s3.
+            // Summation order ((a + b) + c) + d, then * 0.25: bit-exact avg_pool2d of the
+            // level below (oracle/corr_spec.py::pool_pyramid).
+            const int Wp = P.Wp;
+            float s2[32], s3[16];
+            for (int t = 0; t < P.n_tiles; ++t) {
+                const int buf = t & 1;
+                mbar_wait(t_full + buf, (uint32_t)(t >> 1) & 1u);
+                tc_fence_after();
+                const bool row1 = 2 * t + 1 < P.H;
+                float l2[32];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = 4 * i + (lane >> 3);
-                    if (r < rows_valid && c0 + 4 * c4 < ncols) {
-                        const float4 x = *reinterpret_cast<const float4*>(my + r * TC_STG_PITCH + 4 * c4);
-                        *reinterpret_cast<float4*>(P.vol0 + (row_base + r) * P.NP + q0 + c0 + 4 * c4) = x;
+                for (int g = 0; g < 2; ++g) {                  // 64 level-0 columns -> 32 level-1 columns
+                    if (g * 64 < Wp) {
+                        float l1[32];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int c0 = g * 64 + h * 32;
+                            if (c0 < Wp) {
+                                float v0[32], v1[32];
+                                tmem_ld32(lane_addr + (uint32_t)(buf * 256 + c0), v0);
+                                tmem_ld32(lane_addr + (uint32_t)(buf * 256 + Wp + c0), v1);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) { v0[j] *= P.scale; v1[j] *= P.scale; }
+                                store_chunk(P.lvl[0], P.NP, (long long)(2 * t) * Wp + c0, Wp - c0, v0);
+                                if (row1) store_chunk(P.lvl[0], P.NP, (long long)(2 * t + 1) * Wp + c0, Wp - c0, v1);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const float a = __fadd_rn(__fadd_rn(__fadd_rn(v0[2 * j], v0[2 * j + 1]), v1[2 * j]), v1[2 * j + 1]);
+                                    l1[h * 16 + j] = (g * 32 + h * 16 + j < P.lvW[1]) ? a * 0.25f : 0.f;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) l1[h * 16 + j] = 0.f;
+                            }
+                        }
+                        if (t < P.lvH[1])
+                            store_chunk(P.lvl[1], (long long)P.lvH[1] * P.lvWp[1], (long long)t * P.lvWp[1] + g * 32,
+                                        P.lvWp[1] - g * 32, l1);
+                        if (P.n_fused > 2) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if ((t & 1) == 0) {
+                                    s2[g * 16 + j] = __fadd_rn(l1[2 * j], l1[2 * j + 1]);
+                                } else {
+                                    const float a = __fadd_rn(__fadd_rn(s2[g * 16 + j], l1[2 * j]), l1[2 * j + 1]);
+                                    l2[g * 16 + j] = (g * 16 + j < P.lvW[2]) ? a * 0.25f : 0.f;
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) l2[g * 16 + j] = 0.f;
                     }
                 }
+                // all TMEM reads of this tile are done: hand the accumulator back early
+                tc_fence_before();
                 __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty + buf);
+
+                if (P.n_fused > 2 && (t & 1)) {
+                    const int y2 = t >> 1;
+                    if (y2 < P.lvH[2])
+                        store_chunk(P.lvl[2], (long long)P.lvH[2] * P.lvWp[2], (long long)y2 * P.lvWp[2], P.lvWp[2], l2);
+                    if (P.n_fused > 3) {
+                        float l3[32];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if ((y2 & 1) == 0) {
+                                s3[j] = __fadd_rn(l2[2 * j], l2[2 * j + 1]);
+                                l3[j] = 0.f;
+                            } else {
+                                const float a = __fadd_rn(__fadd_rn(s3[j], l2[2 * j]), l2[2 * j + 1]);
+                                l3[j] = (j < P.lvW[3]) ? a * 0.25f : 0.f;
+                            }
+                            l3[16 + j] = 0.f;
+                        }
+                        const int y3 = t >> 2;
+                        if ((y2 & 1) && y3 < P.lvH[3])
+                            store_chunk(P.lvl[3], (long long)P.lvH[3] * P.lvWp[3], (long long)y3 * P.lvWp[3], P.lvWp[3], l3);
+                    }
+                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(t_empty + buf);
         }
     }
 
@@ -394,6 +497,14 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
 
     TcParams P{};
     P.vol0 = static_cast<float*>(pyramid) + pyr.lv[0].offset;
+    P.W = W;
+    // the epilogue produces the pyramid itself when a tile holds two whole target rows
+    const bool fuse = (2 * Wp <= 256) && pyr.L >= 2 && getenv("FLOWCORR_NO_FUSE") == nullptr;
+    P.n_fused = fuse ? (pyr.L < 4 ? pyr.L : 4) : 1;
+    for (int l = 0; l < 4 && l < pyr.L; ++l) {
+        P.lvl[l] = static_cast<float*>(pyramid) + pyr.lv[l].offset;
+        P.lvH[l] = pyr.lv[l].H; P.lvW[l] = pyr.lv[l].W; P.lvWp[l] = pyr.lv[l].Wp;
+    }
     P.N = N; P.NP = (int)NP; P.H = H; P.Wp = Wp;
     P.NT = (2 * Wp <= 256) ? 2 * Wp : Wp;
     if (P.NT % 16 != 0) P.NT = round_up(P.NT, 16);     // single-row tile with Wp % 16 == 8: over-read 8 targets, masked at the store
@@ -421,7 +532,7 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
         default: e = launch_tc<4>(maps, P, B, s); break;
     }
     if (e) return e;
-    return simt_pool_levels(static_cast<float*>(pyramid), pyr, s);
+    return simt_pool_levels(static_cast<float*>(pyramid), pyr, P.n_fused, s);
 }
 
 }  // namespace fc

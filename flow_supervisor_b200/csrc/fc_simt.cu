@@ -205,9 +205,10 @@ static inline unsigned grid_for(long long total, int threads) {
     return (unsigned)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
-int simt_pool_levels(float* pyramid, const Pyramid& pyr, cudaStream_t s) {
+// computes levels [first_level, L) from the level below each
+int simt_pool_levels(float* pyramid, const Pyramid& pyr, int first_level, cudaStream_t s) {
     const long long Q = (long long)pyr.B * pyr.N;
-    for (int l = 0; l + 1 < pyr.L; ++l) {
+    for (int l = (first_level < 1 ? 1 : first_level) - 1; l + 1 < pyr.L; ++l) {
         const Level &a = pyr.lv[l], &c = pyr.lv[l + 1];
         pool_level_kernel<<<grid_for(Q * c.H * c.Wp, 256), 256, 0, s>>>(
             pyramid + a.offset, pyramid + c.offset, Q, a.H, a.Wp, c.H, c.W, c.Wp);
@@ -225,7 +226,7 @@ int simt_build(const float* f1, const float* f2, float* pyramid, const Pyramid& 
     dim3 grid((P.NP + BN - 1) / BN, (P.N + BM - 1) / BM, pyr.B);
     simt_gemm_kernel<OP_FWD><<<grid, GEMM_THREADS, 0, s>>>(P);
     FC_LAUNCH_CHECK("simt_gemm_kernel<FWD>");
-    return simt_pool_levels(pyramid, pyr, s);
+    return simt_pool_levels(pyramid, pyr, 1, s);
 }
 
 int simt_fold(float* gpyr, const Pyramid& pyr, cudaStream_t s) {

@@ -71,3 +71,24 @@ def test_tc_lookup_end_to_end(fsb):
     assert float((out - ref).abs().max() / ref.abs().max()) < 2e-5
     out = build(fsb, f1, f2, "bf16")(c)
     assert float((out - ref).abs().max() / ref.abs().max()) < 1e-2
+
+
+@pytest.mark.parametrize("L", [1, 2, 3])
+def test_tc_fused_pyramid_fewer_levels(fsb, L):
+    B, D, H, W = 1, 128, 21, 50
+    gen = torch.Generator().manual_seed(47)
+    f1 = torch.randn(B, D, H, W, generator=gen).cuda()
+    f2 = torch.randn(B, D, H, W, generator=gen).cuda()
+    old = fsb.CorrBlock.math
+    fsb.CorrBlock.math = "3xbf16"
+    try:
+        blk = fsb.CorrBlock(f1, f2, num_levels=L, radius=3)
+    finally:
+        fsb.CorrBlock.math = old
+    lv = [v.cpu().numpy()[:, 0] for v in blk.corr_pyramid]
+    assert len(lv) == L
+    exact = corr_spec.all_pairs(f1.cpu().numpy(), f2.cpu().numpy(), exact=True)
+    assert float(np.abs(lv[0].reshape(exact.shape) - exact).max() / np.abs(exact).max()) < 2e-5
+    ref = corr_spec.pool_pyramid(lv[0], L)
+    for l in range(1, L):
+        assert np.array_equal(lv[l], ref[l]), l
