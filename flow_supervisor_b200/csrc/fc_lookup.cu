@@ -81,26 +81,32 @@ __device__ __forceinline__ void query_setup(const LookupParams& P, int level, in
 
 // Stage (forward) the footprints of the CTA's 32 queries: rows x 16-byte chunks,
 // zero-filling everything outside the (padded) map -- this IS the reference's
-// padding_mode='zeros'.
+// padding_mode='zeros'.  Warp w owns queries w, w+3, ...: lanes cover 8 rows x 4 chunks of
+// one query per step (a 64-byte run per row: 4 lanes), then rows 8..11 of two queries.
+__device__ __forceinline__ void stage_slot(const float* base, int Hl, int Wp, long long gq, int q,
+                                           int row, int chunk, const WinDesc& d, float* win) {
+    if (row < d.n_row[q] && chunk < d.n_chunk[q]) {
+        const int y = d.y_lo[q] + row;
+        const int x = d.x_s[q] + 4 * chunk;
+        float* dst = win + win_base(q) + row * WIN_PITCH + 4 * chunk;
+        if (y >= 0 && y < Hl && x >= 0 && x < Wp)
+            cp_async16(dst, base + (gq * Hl + y) * (long long)Wp + x);
+        else
+            *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 __device__ __forceinline__ void stage_windows(const LookupParams& P, int level, long long gq0,
                                               const WinDesc& d, float* win) {
     const int Hl = P.H[level], Wp = P.Wp[level];
     const float* base = P.pyr + P.off[level];
-    for (int idx = threadIdx.x; idx < QT * WIN_ROWS * 4; idx += LOOKUP_THREADS) {
-        int q = idx / (WIN_ROWS * 4);
-        int rem = idx - q * (WIN_ROWS * 4);
-        int row = rem >> 2, chunk = rem & 3;
-        if (row < d.n_row[q] && chunk < d.n_chunk[q]) {
-            int y = d.y_lo[q] + row;
-            int x = d.x_s[q] + 4 * chunk;
-            float* dst = win + win_base(q) + row * WIN_PITCH + 4 * chunk;
-            if (y >= 0 && y < Hl && x >= 0 && x < Wp) {
-                const float* src = base + ((gq0 + q) * Hl + y) * (long long)Wp + x;
-                cp_async16(dst, src);
-            } else {
-                *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = lane >> 2, chunk = lane & 3;
+    for (int q = warp; q < QT; q += LOOKUP_THREADS / 32)                   // rows 0..7
+        stage_slot(base, Hl, Wp, gq0 + q, q, row, chunk, d, win);
+    for (int q = warp; q < QT; q += 2 * (LOOKUP_THREADS / 32)) {          // rows 8..11, two queries
+        const int qq = q + (lane >> 4) * (LOOKUP_THREADS / 32);
+        if (qq < QT) stage_slot(base, Hl, Wp, gq0 + qq, qq, 8 + (row & 3), chunk, d, win);
     }
     cp_async_commit();
 }
@@ -144,6 +150,14 @@ lookup_fwd_kernel(const LookupParams P) {
     if (!live) return;
 
     const float* wq = win + win_base(lane);
+    // No floor flip among this query's y taps (the overwhelmingly common case): tap j reads
+    // window rows ry0+j and ry0+j+1, so one horizontally interpolated column of R+1 rows
+    // serves all R outputs of an x-offset (2 shared loads per row instead of 4 per output).
+    bool regular = near_;
+#pragma unroll
+    for (int j = 1; j < R; ++j) regular = regular && (y0[j] == y0[0] + j);
+    const int ry0 = min(max(y0[0] - ylo, 0), WIN_ROWS - 1 - R);
+    const bool want_mask = P.dbg_mask != nullptr;
 #pragma unroll
     for (int aa = 0; aa < A_PER_WARP; ++aa) {
         const int a = warp * A_PER_WARP + aa;
@@ -152,18 +166,33 @@ lookup_fwd_kernel(const LookupParams P) {
         axis_tap<CM>(cx, a - RADIUS, P.ax[level], x0, wx0, wx1);
         if (P.dbg_x0 != nullptr) P.dbg_x0[(gq * P.L + level) * R + a] = x0;
         const int rx = min(max(x0 - xs, 0), WIN_PITCH - 2);
+        float* oa = outq + (long long)(a * R) * P.N;
+        if (regular) {
+            const float* w = wq + ry0 * WIN_PITCH + rx;
+            float hprev = fmaf(wx1, w[1], wx0 * w[0]);
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-            float val = 0.f;
-            if (near_) {
-                const int ry = min(max(y0[j] - ylo, 0), WIN_ROWS - 2);
-                const float* w = wq + ry * WIN_PITCH + rx;
-                const float top = fmaf(wx1, w[1], wx0 * w[0]);
-                const float bot = fmaf(wx1, w[WIN_PITCH + 1], wx0 * w[WIN_PITCH]);
-                val = fmaf(wy1[j], bot, wy0[j] * top);
+            for (int j = 0; j < R; ++j) {
+                const float hnext = fmaf(wx1, w[(j + 1) * WIN_PITCH + 1], wx0 * w[(j + 1) * WIN_PITCH]);
+                oa[(long long)j * P.N] = fmaf(wy1[j], hnext, wy0[j] * hprev);
+                hprev = hnext;
             }
-            outq[(long long)(a * R + j) * P.N] = val;
-            if (P.dbg_mask != nullptr) {
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                float val = 0.f;
+                if (near_) {
+                    const int ry = min(max(y0[j] - ylo, 0), WIN_ROWS - 2);
+                    const float* w = wq + ry * WIN_PITCH + rx;
+                    const float top = fmaf(wx1, w[1], wx0 * w[0]);
+                    const float bot = fmaf(wx1, w[WIN_PITCH + 1], wx0 * w[WIN_PITCH]);
+                    val = fmaf(wy1[j], bot, wy0[j] * top);
+                }
+                oa[(long long)j * P.N] = val;
+            }
+        }
+        if (want_mask) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
                 const bool xa = (x0 >= 0 && x0 < Wl), xb = (x0 + 1 >= 0 && x0 + 1 < Wl);
                 const bool ya = (y0[j] >= 0 && y0[j] < Hl), yb = (y0[j] + 1 >= 0 && y0[j] + 1 < Hl);
                 uint8_t m = (uint8_t)((ya && xa) | ((ya && xb) << 1) | ((yb && xa) << 2) | ((yb && xb) << 3));
