@@ -128,7 +128,8 @@ class CorrBlock:
 
     @property
     def corr_pyramid(self):
-        """corr.py:16,24,27: list of (B*N, 1, Hl, Wl) levels (strided views, no copy)."""
+        """corr.py:16,24,27: list of (B*N, 1, Hl, Wl) levels (gathered copies; the hot path
+        never materialises them)."""
         st = self._state
         return ops.level_views(st.pyramid, st.B, st.H, st.W, st.L)
 

@@ -2,9 +2,10 @@
 // for sm_100a: TMA-fed tcgen05.mma with TMEM accumulators.
 //
 //   pack pre-pass : (B, D, N) fp32 NCHW  ->  K-major bf16 rows [row][D], hi = bf16(x) and
-//                   lo = bf16(x - hi).  fmap1 rows = queries p; fmap2 rows = PADDED targets
-//                   q' = y*Wp + x (pad rows are zero, so pad columns of the volume come out
-//                   as exact zeros and need no masking).
+//                   lo = bf16(x - hi).  fmap1 rows = queries p; fmap2 rows = PADDED targets in
+//                   patch order q' = tile_off(y, x) (fc_common.cuh; pad rows are zero), so a
+//                   GEMM output row IS a query's level-0 map in its final memory layout and
+//                   pad entries come out as exact zeros.
 //   GEMM          : one CTA per (sample, 128-query tile).  The query operand (hi and lo, all
 //                   of K) stays resident in shared memory; target tiles of NT = 2 rows x Wp
 //                   (or 1 row when 2*Wp > 256) stream through a 4-stage TMA ring in
@@ -107,10 +108,11 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
 }
 
 // ---------------------------------------------------------------- pack pre-pass
-// src (B, D, N) fp32 -> hi/lo [b*rows_per_sample + row(n)][D] bf16, row(n) = (n / W) * Wp + n % W
+// src (B, D, N) fp32 -> hi/lo [b*rows_per_sample + row(n)][D] bf16,
+// row(n) = n (tiled == 0) or tile_off(n / W, n % W, Wp) (tiled == 1: target operand)
 __global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
                                  __nv_bfloat16* __restrict__ lo, int D, int N, int W, int Wp,
-                                 int rows_per_sample) {
+                                 int rows_per_sample, int tiled) {
     __shared__ float tile[64][33];
     const int b = blockIdx.z, n0 = blockIdx.x * 32, d0 = blockIdx.y * 64;
     const int tx = threadIdx.x, ty = threadIdx.y;            // 32 x 8
@@ -126,7 +128,7 @@ __global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
         const int nl = ty + 8 * i, n = n0 + nl;
         const int d = d0 + 2 * tx;
         if (n < N && d < D) {
-            const int row = (n / W) * Wp + (n % W);
+            const int row = tiled ? tile_off(n / W, n % W, Wp) : n;
             const float x0 = tile[2 * tx][nl], x1 = tile[2 * tx + 1][nl];
             const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
             const long long o = ((long long)b * rows_per_sample + row) * D + d;
@@ -141,7 +143,7 @@ __global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 // ---------------------------------------------------------------- GEMM
 struct TcParams {
     float* lvl[4];         // fused pyramid: level base pointers (level 0 == vol0)
-    int lvH[4], lvW[4], lvWp[4];
+    int lvH[4], lvW[4], lvWp[4], lvHp[4];
     int n_fused;           // levels written by the epilogue (1 = level 0 only)
     int W;                 // valid target columns of level 0
     float* vol0;           // level 0: (B*N, NP)
@@ -305,48 +307,65 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 if (lane == 0) mbar_arrive(t_empty + buf);
             }
         } else {
-            // Fused pyramid.  Tile t = target rows 2t (columns [0, Wp)) and 2t+1 (columns
-            // [Wp, 2Wp)) of THIS thread's query: every 2x2 pooling partner is thread-local.
-            // Levels 2 / 3 combine two / four consecutive tiles through the stashes s2 / s3.
-            // Summation order ((a + b) + c) + d, then * 0.25: bit-exact avg_pool2d of the
-            // level below (oracle/corr_spec.py::pool_pyramid).
+            // Fused pyramid.  Tile t = row pair t of THIS thread's query map in patch order:
+            // 32 TMEM columns = 2 patches = [row 2t: x0..7][row 2t+1: x0..7][row 2t: x8..15][...],
+            // so every 2x2 pooling quad is thread-local and inside one tcgen05.ld.  Levels 2 / 3
+            // combine two / four consecutive tiles through the stashes s2 / s3.  Summation
+            // order ((a + b) + c) + d, then * 0.25: bit-exact avg_pool2d of the level below
+            // (oracle/corr_spec.py::pool_pyramid).  Pooled levels use the same patch layout:
+            // a row of 32 values = 4 runs of 8 floats, 16 floats apart.
+            auto store_strided = [&](float* base, long long msz, long long off, int ncols, const float* v) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(my + lane * TC_STG_PITCH + 4 * j) =
+                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                const int c4 = lane & 7;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 4 * i + (lane >> 3);
+                    if (r < rows_valid && 4 * c4 < ncols)
+                        *reinterpret_cast<float4*>(base + (row_base + r) * msz + off + (c4 >> 1) * 16 + (c4 & 1) * 4) =
+                            *reinterpret_cast<const float4*>(my + r * TC_STG_PITCH + 4 * c4);
+                }
+                __syncwarp();
+            };
             const int Wp = P.Wp;
+            const int W1 = P.lvW[1], W2 = P.lvW[2], W3 = P.lvW[3];
+            const long long ms1 = (long long)P.lvHp[1] * P.lvWp[1], ms2 = (long long)P.lvHp[2] * P.lvWp[2],
+                            ms3 = (long long)P.lvHp[3] * P.lvWp[3];
             float s2[32], s3[16];
             for (int t = 0; t < P.n_tiles; ++t) {
                 const int buf = t & 1;
                 mbar_wait(t_full + buf, (uint32_t)(t >> 1) & 1u);
                 tc_fence_after();
-                const bool row1 = 2 * t + 1 < P.H;
-                float l2[32];
+                float l1[32], l2[32];
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {                  // 64 level-0 columns -> 32 level-1 columns
-                    if (g * 64 < Wp) {
-                        float l1[32];
+                for (int c = 0; c < 8; ++c) {                  // 32 TMEM columns = 16 target columns x 2 rows
+                    if (c * 32 < 2 * Wp) {
+                        float v[32];
+                        tmem_ld32(lane_addr + (uint32_t)(buf * 256 + c * 32), v);
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int c0 = g * 64 + h * 32;
-                            if (c0 < Wp) {
-                                float v0[32], v1[32];
-                                tmem_ld32(lane_addr + (uint32_t)(buf * 256 + c0), v0);
-                                tmem_ld32(lane_addr + (uint32_t)(buf * 256 + Wp + c0), v1);
-                                tmem_ld_wait();
+                        for (int j = 0; j < 32; ++j) v[j] *= P.scale;
+                        store_chunk(P.lvl[0], P.NP, (long long)t * 2 * Wp + c * 32, 2 * Wp - c * 32, v);
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) { v0[j] *= P.scale; v1[j] *= P.scale; }
-                                store_chunk(P.lvl[0], P.NP, (long long)(2 * t) * Wp + c0, Wp - c0, v0);
-                                if (row1) store_chunk(P.lvl[0], P.NP, (long long)(2 * t + 1) * Wp + c0, Wp - c0, v1);
+                        for (int pp = 0; pp < 2; ++pp)
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const float a = __fadd_rn(__fadd_rn(__fadd_rn(v0[2 * j], v0[2 * j + 1]), v1[2 * j]), v1[2 * j + 1]);
-                                    l1[h * 16 + j] = (g * 32 + h * 16 + j < P.lvW[1]) ? a * 0.25f : 0.f;
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) l1[h * 16 + j] = 0.f;
+                            for (int j = 0; j < 4; ++j) {
+                                const float a = __fadd_rn(__fadd_rn(__fadd_rn(v[16 * pp + 2 * j], v[16 * pp + 2 * j + 1]),
+                                                                    v[16 * pp + 8 + 2 * j]), v[16 * pp + 8 + 2 * j + 1]);
+                                l1[(c & 3) * 8 + 4 * pp + j] = (8 * c + 4 * pp + j < W1) ? a * 0.25f : 0.f;
                             }
-                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) l1[(c & 3) * 8 + j] = 0.f;
+                    }
+                    if ((c & 3) == 3 && (c - 3) * 32 < 2 * Wp) {
+                        const int g = c >> 2;                  // level-1 columns [32g, 32g + 32)
                         if (t < P.lvH[1])
-                            store_chunk(P.lvl[1], (long long)P.lvH[1] * P.lvWp[1], (long long)t * P.lvWp[1] + g * 32,
-                                        P.lvWp[1] - g * 32, l1);
+                            store_strided(P.lvl[1], ms1, (long long)(t >> 1) * 2 * P.lvWp[1] + g * 64 + (t & 1) * 8,
+                                          P.lvWp[1] - g * 32, l1);
                         if (P.n_fused > 2) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
@@ -354,13 +373,13 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                                     s2[g * 16 + j] = __fadd_rn(l1[2 * j], l1[2 * j + 1]);
                                 } else {
                                     const float a = __fadd_rn(__fadd_rn(s2[g * 16 + j], l1[2 * j]), l1[2 * j + 1]);
-                                    l2[g * 16 + j] = (g * 16 + j < P.lvW[2]) ? a * 0.25f : 0.f;
+                                    l2[g * 16 + j] = (g * 16 + j < W2) ? a * 0.25f : 0.f;
                                 }
                             }
                         }
-                    } else {
+                    } else if ((c & 3) == 3) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) l2[g * 16 + j] = 0.f;
+                        for (int j = 0; j < 16; ++j) l2[(c >> 2) * 16 + j] = 0.f;
                     }
                 }
                 // all TMEM reads of this tile are done: hand the accumulator back early
@@ -371,7 +390,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 if (P.n_fused > 2 && (t & 1)) {
                     const int y2 = t >> 1;
                     if (y2 < P.lvH[2])
-                        store_chunk(P.lvl[2], (long long)P.lvH[2] * P.lvWp[2], (long long)y2 * P.lvWp[2], P.lvWp[2], l2);
+                        store_strided(P.lvl[2], ms2, (long long)(y2 >> 1) * 2 * P.lvWp[2] + (y2 & 1) * 8, P.lvWp[2], l2);
                     if (P.n_fused > 3) {
                         float l3[32];
 #pragma unroll
@@ -381,13 +400,13 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                                 l3[j] = 0.f;
                             } else {
                                 const float a = __fadd_rn(__fadd_rn(s3[j], l2[2 * j]), l2[2 * j + 1]);
-                                l3[j] = (j < P.lvW[3]) ? a * 0.25f : 0.f;
+                                l3[j] = (j < W3) ? a * 0.25f : 0.f;
                             }
                             l3[16 + j] = 0.f;
                         }
                         const int y3 = t >> 2;
                         if ((y2 & 1) && y3 < P.lvH[3])
-                            store_chunk(P.lvl[3], (long long)P.lvH[3] * P.lvWp[3], (long long)y3 * P.lvWp[3], P.lvWp[3], l3);
+                            store_strided(P.lvl[3], ms3, (long long)(y3 >> 1) * 2 * P.lvWp[3] + (y3 & 1) * 8, P.lvWp[3], l3);
                     }
                 }
             }
@@ -438,7 +457,7 @@ struct TcLayout { size_t a_hi, a_lo, b_hi, b_lo, total; long long NP; };
 
 static TcLayout tc_layout(int B, int D, int H, int W) {
     TcLayout L;
-    const long long N = (long long)H * W, NP = (long long)H * round_up(W, 8);
+    const long long N = (long long)H * W, NP = (long long)round_up(H, 2) * round_up(W, 8);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
     L.a_hi = take((size_t)B * N * D * 2);
@@ -486,13 +505,13 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     const int N = pyr.N;
     const long long NP = L.NP;
 
-    if (Wp != W) {   // pad rows of the target operand must be zero
+    if (Wp != W || pyr.lv[0].Hp != H) {   // pad rows of the target operand must be zero
         FC_CUDA(cudaMemsetAsync(b_hi, 0, (size_t)B * NP * D * 2, s));
         if (three) FC_CUDA(cudaMemsetAsync(b_lo, 0, (size_t)B * NP * D * 2, s));
     }
     dim3 pb(32, 8), pg((N + 31) / 32, (D + 63) / 64, B);
-    pack_bf16_kernel<<<pg, pb, 0, s>>>(f1, a_hi, three ? a_lo : nullptr, D, N, W, W, N);
-    pack_bf16_kernel<<<pg, pb, 0, s>>>(f2, b_hi, three ? b_lo : nullptr, D, N, W, Wp, (int)NP);
+    pack_bf16_kernel<<<pg, pb, 0, s>>>(f1, a_hi, three ? a_lo : nullptr, D, N, W, W, N, 0);
+    pack_bf16_kernel<<<pg, pb, 0, s>>>(f2, b_hi, three ? b_lo : nullptr, D, N, W, Wp, (int)NP, 1);
     FC_LAUNCH_CHECK("pack_bf16_kernel");
 
     TcParams P{};
@@ -503,7 +522,7 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     P.n_fused = fuse ? (pyr.L < 4 ? pyr.L : 4) : 1;
     for (int l = 0; l < 4 && l < pyr.L; ++l) {
         P.lvl[l] = static_cast<float*>(pyramid) + pyr.lv[l].offset;
-        P.lvH[l] = pyr.lv[l].H; P.lvW[l] = pyr.lv[l].W; P.lvWp[l] = pyr.lv[l].Wp;
+        P.lvH[l] = pyr.lv[l].H; P.lvW[l] = pyr.lv[l].W; P.lvWp[l] = pyr.lv[l].Wp; P.lvHp[l] = pyr.lv[l].Hp;
     }
     P.N = N; P.NP = (int)NP; P.H = H; P.Wp = Wp;
     P.NT = (2 * Wp <= 256) ? 2 * Wp : Wp;

@@ -36,9 +36,21 @@ int cuda_fail(cudaError_t e, const char* what);
 
 // ---------------------------------------------------------------- pyramid geometry
 struct Level {
-    int H, W, Wp;          // rows, valid columns, row pitch (elements)
+    int H, W, Wp, Hp;      // rows, valid columns, row pitch (multiple of 8), padded rows (even)
     long long offset;      // ELEMENT offset of the level inside the pyramid buffer
 };
+
+// Patch layout of one query's map: 64-byte patches of 2 rows x 8 columns, patches of a
+// row pair stored left to right (DRAM granule = 64 B: a (2r+2)^2 window touches ~25% fewer
+// granules than with row-major rows).  Element (y, x) of a map with row pitch Wp:
+__host__ __device__ __forceinline__ int tile_off(int y, int x, int Wp) {
+    return (y >> 1) * (2 * Wp) + ((x >> 3) << 4) + ((y & 1) << 3) + (x & 7);
+}
+__host__ __device__ __forceinline__ void tile_inv(int off, int Wp, int& y, int& x) {
+    const int pr = off / (2 * Wp), r = off - pr * 2 * Wp;
+    y = 2 * pr + ((r >> 3) & 1);
+    x = ((r >> 4) << 3) + (r & 7);
+}
 
 struct Pyramid {
     int L;
@@ -56,9 +68,9 @@ inline bool make_pyramid(Pyramid& P, int B, int H, int W, int L) {
     for (int l = 0; l < L; ++l) {
         int Hl = H >> l, Wl = W >> l;
         if (Hl < 1 || Wl < 1) return false;
-        P.lv[l].H = Hl; P.lv[l].W = Wl; P.lv[l].Wp = round_up(Wl, 8);
+        P.lv[l].H = Hl; P.lv[l].W = Wl; P.lv[l].Wp = round_up(Wl, 8); P.lv[l].Hp = round_up(Hl, 2);
         P.lv[l].offset = off;
-        off += (long long)B * P.N * Hl * P.lv[l].Wp;
+        off += (long long)B * P.N * P.lv[l].Hp * P.lv[l].Wp;
     }
     P.total = off;
     return true;

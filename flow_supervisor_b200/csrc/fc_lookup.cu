@@ -21,10 +21,11 @@ struct LookupParams {
     const float* coords;    // (B, 2, H, W)
     float* io;              // forward: out (B, K, H, W); backward: grad_out (read)
     float* gpyr;            // backward only: gradient pyramid (atomically accumulated)
-    long long Q;            // B * N
+    int Q;                  // B * N (< 2^31)
     int N, L, K;
     long long off[FC_MAX_LEVELS];
     int H[FC_MAX_LEVELS], W[FC_MAX_LEVELS], Wp[FC_MAX_LEVELS];
+    int msize[FC_MAX_LEVELS];   // elements per query map (Hp * Wp)
     AxisConst ax[FC_MAX_LEVELS], ay[FC_MAX_LEVELS];
     float inv_scale[FC_MAX_LEVELS];
     int32_t* dbg_x0;
@@ -44,20 +45,24 @@ struct WinDesc {            // per-query footprint descriptor (shared memory)
     int x_s[QT];            // first footprint column rounded down to a multiple of 4
     int n_row[QT];          // rows to stage   (0 = nothing: dead or far query)
     int n_chunk[QT];        // 16-byte chunks per row to stage
+    long long q_off[QT];    // element offset of the query's map inside the level
 };
 
 template <int RADIUS, int CM>
 __device__ __forceinline__ void query_setup(const LookupParams& P, int level, int lane,
-                                            long long gq, bool live,
+                                            int gq0, bool live, int& b, int& p,
                                             float& cx, float& cy, bool& near_,
                                             WinDesc& d, bool write_desc) {
     constexpr int R = 2 * RADIUS + 1;
+    // 32 consecutive flattened queries: one 32-bit division per thread, then a wrap
+    b = gq0 / P.N;
+    p = gq0 - b * P.N + lane;
+    while (p >= P.N) { p -= P.N; ++b; }
     cx = 0.f; cy = 0.f;
     if (live) {
-        long long b = gq / P.N;
-        long long p = gq - b * P.N;
-        cx = __fmul_rn(__ldg(P.coords + (b * 2 + 0) * P.N + p), P.inv_scale[level]);
-        cy = __fmul_rn(__ldg(P.coords + (b * 2 + 1) * P.N + p), P.inv_scale[level]);
+        const float* c = P.coords + (long long)b * 2 * P.N + p;
+        cx = __fmul_rn(__ldg(c), P.inv_scale[level]);
+        cy = __fmul_rn(__ldg(c + P.N), P.inv_scale[level]);
     }
     // beyond 2^20 every tap is out of bounds for any map this library accepts and the
     // +-1 flip bound used to size the window no longer holds; NaN compares false.
@@ -76,6 +81,7 @@ __device__ __forceinline__ void query_setup(const LookupParams& P, int level, in
             nchunk = min(((xh + 1 - xs) >> 2) + 1, WIN_PITCH / 4);
         }
         d.y_lo[lane] = ylo; d.x_s[lane] = xs; d.n_row[lane] = nrow; d.n_chunk[lane] = nchunk;
+        d.q_off[lane] = (long long)(gq0 + lane) * P.msize[level];
     }
 }
 
@@ -83,30 +89,30 @@ __device__ __forceinline__ void query_setup(const LookupParams& P, int level, in
 // zero-filling everything outside the (padded) map -- this IS the reference's
 // padding_mode='zeros'.  Warp w owns queries w, w+3, ...: lanes cover 8 rows x 4 chunks of
 // one query per step (a 64-byte run per row: 4 lanes), then rows 8..11 of two queries.
-__device__ __forceinline__ void stage_slot(const float* base, int Hl, int Wp, long long gq, int q,
+__device__ __forceinline__ void stage_slot(const float* base, int Hl, int Wp, int q,
                                            int row, int chunk, const WinDesc& d, float* win) {
     if (row < d.n_row[q] && chunk < d.n_chunk[q]) {
         const int y = d.y_lo[q] + row;
         const int x = d.x_s[q] + 4 * chunk;
         float* dst = win + win_base(q) + row * WIN_PITCH + 4 * chunk;
-        if (y >= 0 && y < Hl && x >= 0 && x < Wp)
-            cp_async16(dst, base + (gq * Hl + y) * (long long)Wp + x);
+        if ((unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wp)
+            cp_async16(dst, base + d.q_off[q] + tile_off(y, x, Wp));
         else
             *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
-__device__ __forceinline__ void stage_windows(const LookupParams& P, int level, long long gq0,
+__device__ __forceinline__ void stage_windows(const LookupParams& P, int level,
                                               const WinDesc& d, float* win) {
     const int Hl = P.H[level], Wp = P.Wp[level];
     const float* base = P.pyr + P.off[level];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = lane >> 2, chunk = lane & 3;
     for (int q = warp; q < QT; q += LOOKUP_THREADS / 32)                   // rows 0..7
-        stage_slot(base, Hl, Wp, gq0 + q, q, row, chunk, d, win);
+        stage_slot(base, Hl, Wp, q, row, chunk, d, win);
     for (int q = warp; q < QT; q += 2 * (LOOKUP_THREADS / 32)) {          // rows 8..11, two queries
         const int qq = q + (lane >> 4) * (LOOKUP_THREADS / 32);
-        if (qq < QT) stage_slot(base, Hl, Wp, gq0 + qq, qq, 8 + (row & 3), chunk, d, win);
+        if (qq < QT) stage_slot(base, Hl, Wp, qq, 8 + (row & 3), chunk, d, win);
     }
     cp_async_commit();
 }
@@ -120,14 +126,14 @@ lookup_fwd_kernel(const LookupParams P) {
 
     const int level = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long gq0 = (long long)blockIdx.x * QT;
-    const long long gq = gq0 + lane;
+    const int gq0 = blockIdx.x * QT;
+    const int gq = gq0 + lane;
     const bool live = gq < P.Q;
 
-    float cx, cy; bool near_;
-    query_setup<RADIUS, CM>(P, level, lane, gq, live, cx, cy, near_, desc, warp == 0);
+    float cx, cy; bool near_; int b, p;
+    query_setup<RADIUS, CM>(P, level, lane, gq0, live, b, p, cx, cy, near_, desc, warp == 0);
     __syncthreads();
-    stage_windows(P, level, gq0, desc, win);
+    stage_windows(P, level, desc, win);
 
     // tap arithmetic overlaps the copies in flight
     const int Hl = P.H[level], Wl = P.W[level];
@@ -136,13 +142,11 @@ lookup_fwd_kernel(const LookupParams P) {
     for (int j = 0; j < R; ++j) axis_tap<CM>(cy, j - RADIUS, P.ay[level], y0[j], wy0[j], wy1[j]);
     const int ylo = desc.y_lo[lane], xs = desc.x_s[lane];
 
-    long long b = 0, p = 0;
-    if (live) { b = gq / P.N; p = gq - b * P.N; }
-    float* outq = P.io + (b * P.K + (long long)level * R * R) * P.N + p;
+    float* outq = P.io + ((long long)b * P.K + level * R * R) * P.N + p;
 
     if (P.dbg_y0 != nullptr && live && warp == 0) {
 #pragma unroll
-        for (int j = 0; j < R; ++j) P.dbg_y0[(gq * P.L + level) * R + j] = y0[j];
+        for (int j = 0; j < R; ++j) P.dbg_y0[((long long)gq * P.L + level) * R + j] = y0[j];
     }
 
     cp_async_wait<0>();
@@ -164,7 +168,7 @@ lookup_fwd_kernel(const LookupParams P) {
         if (a >= R) break;
         int x0; float wx0, wx1;
         axis_tap<CM>(cx, a - RADIUS, P.ax[level], x0, wx0, wx1);
-        if (P.dbg_x0 != nullptr) P.dbg_x0[(gq * P.L + level) * R + a] = x0;
+        if (P.dbg_x0 != nullptr) P.dbg_x0[((long long)gq * P.L + level) * R + a] = x0;
         const int rx = min(max(x0 - xs, 0), WIN_PITCH - 2);
         float* oa = outq + (long long)(a * R) * P.N;
         if (regular) {
@@ -173,7 +177,8 @@ lookup_fwd_kernel(const LookupParams P) {
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 const float hnext = fmaf(wx1, w[(j + 1) * WIN_PITCH + 1], wx0 * w[(j + 1) * WIN_PITCH]);
-                oa[(long long)j * P.N] = fmaf(wy1[j], hnext, wy0[j] * hprev);
+                *oa = fmaf(wy1[j], hnext, wy0[j] * hprev);
+                oa += P.N;
                 hprev = hnext;
             }
         } else {
@@ -187,7 +192,8 @@ lookup_fwd_kernel(const LookupParams P) {
                     const float bot = fmaf(wx1, w[WIN_PITCH + 1], wx0 * w[WIN_PITCH]);
                     val = fmaf(wy1[j], bot, wy0[j] * top);
                 }
-                oa[(long long)j * P.N] = val;
+                *oa = val;
+                oa += P.N;
             }
         }
         if (want_mask) {
@@ -197,7 +203,7 @@ lookup_fwd_kernel(const LookupParams P) {
                 const bool ya = (y0[j] >= 0 && y0[j] < Hl), yb = (y0[j] + 1 >= 0 && y0[j] + 1 < Hl);
                 uint8_t m = (uint8_t)((ya && xa) | ((ya && xb) << 1) | ((yb && xa) << 2) | ((yb && xb) << 3));
                 if (!near_) m = 0;
-                P.dbg_mask[((gq * P.L + level) * R + a) * R + j] = m;
+                P.dbg_mask[(((long long)gq * P.L + level) * R + a) * R + j] = m;
             }
         }
     }
@@ -221,12 +227,12 @@ lookup_bwd_kernel(const LookupParams P) {
 
     const int level = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long gq0 = (long long)blockIdx.x * QT;
-    const long long gq = gq0 + lane;
+    const int gq0 = blockIdx.x * QT;
+    const int gq = gq0 + lane;
     const bool live = gq < P.Q;
 
-    float cx, cy; bool near_;
-    query_setup<RADIUS, CM>(P, level, lane, gq, live, cx, cy, near_, desc, warp == 0);
+    float cx, cy; bool near_; int b, p;
+    query_setup<RADIUS, CM>(P, level, lane, gq0, live, b, p, cx, cy, near_, desc, warp == 0);
     for (int i = threadIdx.x; i < QT * WIN_STRIDE / 4; i += LOOKUP_THREADS)
         reinterpret_cast<float4*>(win)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
@@ -236,8 +242,7 @@ lookup_bwd_kernel(const LookupParams P) {
 #pragma unroll
         for (int j = 0; j < R; ++j) axis_tap<CM>(cy, j - RADIUS, P.ay[level], y0[j], wy0[j], wy1[j]);
         const int ylo = desc.y_lo[lane], xs = desc.x_s[lane];
-        long long b = gq / P.N, p = gq - b * P.N;
-        const float* gq_ptr = P.io + (b * P.K + (long long)level * R * R) * P.N + p;
+        const float* gq_ptr = P.io + ((long long)b * P.K + level * R * R) * P.N + p;
         float* wq = win + win_base(lane);
 #pragma unroll
         for (int aa = 0; aa < A_PER_WARP; ++aa) {
@@ -278,7 +283,7 @@ lookup_bwd_kernel(const LookupParams P) {
                 if (x + 2 >= Wl) v.z = 0.f;
                 if (x + 3 >= Wl) v.w = 0.f;
                 if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
-                    red_add_v4(base + ((gq0 + q) * Hl + y) * (long long)Wp + x, v);
+                    red_add_v4(base + desc.q_off[q] + tile_off(y, x, Wp), v);
             }
         }
     }
@@ -286,13 +291,14 @@ lookup_bwd_kernel(const LookupParams P) {
 
 // ---------------------------------------------------------------- host side
 static int fill_params(LookupParams& P, const Pyramid& pyr, int radius) {
-    P.Q = (long long)pyr.B * pyr.N;
+    P.Q = pyr.B * pyr.N;
     P.N = pyr.N; P.L = pyr.L;
     const int R = 2 * radius + 1;
     P.K = pyr.L * R * R;
     for (int l = 0; l < pyr.L; ++l) {
         P.off[l] = pyr.lv[l].offset;
         P.H[l] = pyr.lv[l].H; P.W[l] = pyr.lv[l].W; P.Wp[l] = pyr.lv[l].Wp;
+        P.msize[l] = pyr.lv[l].Hp * pyr.lv[l].Wp;
         P.ax[l] = make_axis(pyr.lv[l].W);
         P.ay[l] = make_axis(pyr.lv[l].H);
         P.inv_scale[l] = 1.0f / (float)(1 << l);
@@ -316,6 +322,7 @@ static void launch_bwd(const LookupParams& P, int coord_mode, dim3 grid, cudaStr
 }
 
 static int check_common(const Pyramid& pyr, int radius, int coord_mode) {
+    FC_REQUIRE((long long)pyr.B * pyr.N < (1LL << 31) - QT, "B*H*W = %lld queries exceed 2^31", (long long)pyr.B * pyr.N);
     FC_REQUIRE(radius >= 1 && radius <= FC_MAX_RADIUS, "radius %d unsupported (1..%d)", radius, FC_MAX_RADIUS);
     FC_REQUIRE(coord_mode == FC_COORD_CUDA || coord_mode == FC_COORD_CPU, "bad coord_mode %d", coord_mode);
     for (int l = 0; l < pyr.L; ++l)

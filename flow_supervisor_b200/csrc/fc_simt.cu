@@ -8,8 +8,9 @@
 //   OP_FWD : vol0[b,p,q'] = sum_d f1[b,d,p] * f2pad[b,d,q'] / sqrt(D)
 //   OP_DF1 : dF1[b,d,p]   = sum_q' f2pad[b,d,q'] * G0[b,p,q'] / sqrt(D)
 //   OP_DF2 : dF2[b,d,q]   = sum_p  f1[b,d,p]    * G0[b,p,q'(q)] / sqrt(D)
-// where q' = y*Wp + x runs over the PADDED target index space (pad columns read as 0
-// and are written as 0, so the pyramid's pad invariant holds by construction).
+// where q' = tile_off(y, x) runs over the PADDED, patch-ordered target index space of a
+// level-0 map (fc_common.cuh): pad rows/columns read as 0 and are written as 0, so the
+// pyramid's pad invariant holds by construction and q' IS the memory offset.
 #include "fc_common.cuh"
 
 namespace fc {
@@ -21,16 +22,17 @@ enum { OP_FWD = 0, OP_DF1 = 1, OP_DF2 = 2 };
 struct GemmParams {
     const float* f1;     // (B, D, N)
     const float* f2;     // (B, D, N)
-    float* vol;          // level 0 of the (gradient) pyramid: (B*N, H, Wp)
+    float* vol;          // level 0 of the (gradient) pyramid: (B*N, NP)
     float* dout;         // dF1 or dF2 (B, D, N)
-    int D, N, H, W, Wp, NP;   // NP = H * Wp
+    int D, N, H, W, Wp, NP;   // NP = Hp * Wp
     float sqrt_d;
 };
 
 // padded target index -> real target index, or -1 on a pad column
-__device__ __forceinline__ int unpad(int qp, int W, int Wp) {
-    int y = qp / Wp, x = qp - y * Wp;
-    return x < W ? y * W + x : -1;
+__device__ __forceinline__ int unpad(int qp, int H, int W, int Wp) {
+    int y, x;
+    tile_inv(qp, Wp, y, x);
+    return (x < W && y < H) ? y * W + x : -1;
 }
 
 template <int OP>
@@ -63,12 +65,12 @@ simt_gemm_kernel(const GemmParams P) {
                 const int k = e >> 7, m = e & 127;
                 const int kk = k0 + k, mm = m0 + m, nn = n0 + m;
                 ra[i] = (kk < K && mm < M) ? __ldg(f1 + (long long)kk * P.N + mm) : 0.f;
-                int src = (kk < K && nn < Nn) ? unpad(nn, P.W, P.Wp) : -1;
+                int src = (kk < K && nn < Nn) ? unpad(nn, P.H, P.W, P.Wp) : -1;
                 rb[i] = src >= 0 ? __ldg(f2 + (long long)kk * P.N + src) : 0.f;
             } else if (OP == OP_DF1) {
                 const int m = e >> 4, k = e & 15;
                 const int kk = k0 + k, mm = m0 + m, nn = n0 + m;
-                int src = (kk < K && mm < M) ? unpad(kk, P.W, P.Wp) : -1;
+                int src = (kk < K && mm < M) ? unpad(kk, P.H, P.W, P.Wp) : -1;
                 ra[i] = src >= 0 ? __ldg(f2 + (long long)mm * P.N + src) : 0.f;
                 rb[i] = (kk < K && nn < Nn) ? __ldg(G + (long long)nn * P.NP + kk) : 0.f;
             } else {
@@ -146,7 +148,7 @@ simt_gemm_kernel(const GemmParams P) {
                     if (OP == OP_DF1) {
                         dst[n + j] = vv[j];
                     } else {
-                        int q = unpad(n + j, P.W, P.Wp);
+                        int q = unpad(n + j, P.H, P.W, P.Wp);
                         if (q >= 0) dst[q] = vv[j];
                     }
                 }
@@ -160,19 +162,19 @@ simt_gemm_kernel(const GemmParams P) {
 // (a + b + c + d) * 0.25 in this order reproduces ATen's avg_pool2d bit for bit
 // (oracle/corr_spec.py::pool_pyramid).
 __global__ void pool_level_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                  long long Q, int Hs, int Wps, int Hd, int Wd, int Wpd) {
-    const long long total = Q * Hd * Wpd;
+                                  long long Q, int Hps, int Wps, int Hd, int Wd, int Hpd, int Wpd) {
+    const int msrc = Hps * Wps, mdst = Hpd * Wpd;
+    const long long total = Q * mdst;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(i % Wpd);
-        const long long t = i / Wpd;
-        const int y = (int)(t % Hd);
-        const long long q = t / Hd;
+        const long long q = i / mdst;
+        int y, x;
+        tile_inv((int)(i - q * mdst), Wpd, y, x);
         float v = 0.f;
-        if (x < Wd) {
-            const float* s = src + (q * Hs + 2 * y) * (long long)Wps + 2 * x;
+        if (x < Wd && y < Hd) {
+            const float* s = src + q * msrc + tile_off(2 * y, 2 * x, Wps);   // rows 2y, 2y+1 share a patch
             const float2 r0 = *reinterpret_cast<const float2*>(s);
-            const float2 r1 = *reinterpret_cast<const float2*>(s + Wps);
+            const float2 r1 = *reinterpret_cast<const float2*>(s + 8);
             v = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(r0.x, r0.y), r1.x), r1.y), 0.25f);
         }
         dst[i] = v;
@@ -181,7 +183,8 @@ __global__ void pool_level_kernel(const float* __restrict__ src, float* __restri
 
 // avg_pool2d backward, in place: every parent gives a quarter to its 4 children.
 __global__ void fold_level_kernel(const float* __restrict__ parent, float* __restrict__ child,
-                                  long long Q, int Hc, int Wpc, int Hp, int Wp_, int Wpp) {
+                                  long long Q, int Hpc, int Wpc, int Hp, int Wp_, int Hpp, int Wpp) {
+    const int mpar = Hpp * Wpp, mch = Hpc * Wpc;
     const long long total = Q * Hp * Wp_;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -189,13 +192,13 @@ __global__ void fold_level_kernel(const float* __restrict__ parent, float* __res
         const long long t = i / Wp_;
         const int y = (int)(t % Hp);
         const long long q = t / Hp;
-        const float g = 0.25f * parent[(q * Hp + y) * (long long)Wpp + x];
-        float* c = child + (q * Hc + 2 * y) * (long long)Wpc + 2 * x;
+        const float g = 0.25f * parent[q * mpar + tile_off(y, x, Wpp)];
+        float* c = child + q * mch + tile_off(2 * y, 2 * x, Wpc);
         float2 r0 = *reinterpret_cast<float2*>(c);
-        float2 r1 = *reinterpret_cast<float2*>(c + Wpc);
+        float2 r1 = *reinterpret_cast<float2*>(c + 8);
         r0.x += g; r0.y += g; r1.x += g; r1.y += g;
         *reinterpret_cast<float2*>(c) = r0;
-        *reinterpret_cast<float2*>(c + Wpc) = r1;
+        *reinterpret_cast<float2*>(c + 8) = r1;
     }
 }
 
@@ -210,8 +213,8 @@ int simt_pool_levels(float* pyramid, const Pyramid& pyr, int first_level, cudaSt
     const long long Q = (long long)pyr.B * pyr.N;
     for (int l = (first_level < 1 ? 1 : first_level) - 1; l + 1 < pyr.L; ++l) {
         const Level &a = pyr.lv[l], &c = pyr.lv[l + 1];
-        pool_level_kernel<<<grid_for(Q * c.H * c.Wp, 256), 256, 0, s>>>(
-            pyramid + a.offset, pyramid + c.offset, Q, a.H, a.Wp, c.H, c.W, c.Wp);
+        pool_level_kernel<<<grid_for(Q * c.Hp * c.Wp, 256), 256, 0, s>>>(
+            pyramid + a.offset, pyramid + c.offset, Q, a.Hp, a.Wp, c.H, c.W, c.Hp, c.Wp);
         FC_LAUNCH_CHECK("pool_level_kernel");
     }
     return FC_OK;
@@ -221,7 +224,7 @@ int simt_build(const float* f1, const float* f2, float* pyramid, const Pyramid& 
                int D, int H, int W, cudaStream_t s) {
     GemmParams P{};
     P.f1 = f1; P.f2 = f2; P.vol = pyramid + pyr.lv[0].offset; P.dout = nullptr;
-    P.D = D; P.N = pyr.N; P.H = H; P.W = W; P.Wp = pyr.lv[0].Wp; P.NP = H * P.Wp;
+    P.D = D; P.N = pyr.N; P.H = H; P.W = W; P.Wp = pyr.lv[0].Wp; P.NP = pyr.lv[0].Hp * P.Wp;
     P.sqrt_d = sqrtf((float)D);
     dim3 grid((P.NP + BN - 1) / BN, (P.N + BM - 1) / BM, pyr.B);
     simt_gemm_kernel<OP_FWD><<<grid, GEMM_THREADS, 0, s>>>(P);
@@ -234,7 +237,7 @@ int simt_fold(float* gpyr, const Pyramid& pyr, cudaStream_t s) {
     for (int l = pyr.L - 1; l >= 1; --l) {
         const Level &p = pyr.lv[l], &c = pyr.lv[l - 1];
         fold_level_kernel<<<grid_for(Q * p.H * p.W, 256), 256, 0, s>>>(
-            gpyr + p.offset, gpyr + c.offset, Q, c.H, c.Wp, p.H, p.W, p.Wp);
+            gpyr + p.offset, gpyr + c.offset, Q, c.Hp, c.Wp, p.H, p.W, p.Hp, p.Wp);
         FC_LAUNCH_CHECK("fold_level_kernel");
     }
     return FC_OK;
@@ -244,7 +247,7 @@ int simt_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, flo
                    const Pyramid& pyr, int D, int H, int W, cudaStream_t s) {
     GemmParams P{};
     P.f1 = f1; P.f2 = f2; P.vol = gpyr + pyr.lv[0].offset;
-    P.D = D; P.N = pyr.N; P.H = H; P.W = W; P.Wp = pyr.lv[0].Wp; P.NP = H * P.Wp;
+    P.D = D; P.N = pyr.N; P.H = H; P.W = W; P.Wp = pyr.lv[0].Wp; P.NP = pyr.lv[0].Hp * P.Wp;
     P.sqrt_d = sqrtf((float)D);
     if (d1) {
         P.dout = d1;

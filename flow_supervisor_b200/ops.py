@@ -25,19 +25,31 @@ def geometry(H: int, W: int, L: int):
     return [(H >> l, W >> l, ((W >> l) + 7) // 8 * 8) for l in range(L)]
 
 
+def _hp(h: int) -> int:
+    return (h + 1) // 2 * 2
+
+
 def pyramid_numel(B: int, H: int, W: int, L: int) -> int:
-    return sum(B * H * W * h * wp for h, _, wp in geometry(H, W, L))
+    return sum(B * H * W * _hp(h) * wp for h, _, wp in geometry(H, W, L))
+
+
+def level_padded(pyramid: Tensor, B: int, H: int, W: int, L: int) -> List[Tensor]:
+    """Every level as a dense (B*N, Hp, Wp) tensor INCLUDING pad rows/columns, un-patched
+    from the library's 2x8 patch layout (include/flowcorr.h).  Copies."""
+    out, off, Q = [], 0, B * H * W
+    for h, w, wp in geometry(H, W, L):
+        hp = _hp(h)
+        n = Q * hp * wp
+        t = pyramid[off:off + n].view(Q, hp // 2, wp // 8, 2, 8).permute(0, 1, 3, 2, 4)
+        out.append(t.reshape(Q, hp, wp))
+        off += n
+    return out
 
 
 def level_views(pyramid: Tensor, B: int, H: int, W: int, L: int) -> List[Tensor]:
-    """The reference's ``corr_pyramid`` list ((B*N, 1, Hl, Wl), corr.py:14-27) as strided
-    views into the flat pyramid buffer (pad columns sliced away)."""
-    views, off, Q = [], 0, B * H * W
-    for h, w, wp in geometry(H, W, L):
-        n = Q * h * wp
-        views.append(pyramid[off:off + n].view(Q, 1, h, wp)[..., :w])
-        off += n
-    return views
+    """The reference's ``corr_pyramid`` list ((B*N, 1, Hl, Wl), corr.py:14-27), gathered out
+    of the patch layout (copies; nothing on the hot path reads them)."""
+    return [t[:, None, :h, :w] for t, (h, w, _) in zip(level_padded(pyramid, B, H, W, L), geometry(H, W, L))]
 
 
 def _need_cuda(*tensors: Tensor) -> None:

@@ -20,10 +20,12 @@
  *
  * Correlation pyramid layout (internal to this library; the reference keeps a list
  * of (B*N, 1, Hl, Wl) tensors, corr.py:14-27, which nothing outside corr.py reads):
- *   one buffer, level l at byte offset level_offset[l], holding
- *       vol_l[b*N + p][y][x]   for p < N = H*W queries, y < Hl, x < Wp_l
- *   with Hl = H >> l, Wl = W >> l (floor, like avg_pool2d) and the row pitch
- *   Wp_l = round_up(Wl, 8) elements.  Pad columns x in [Wl, Wp_l) hold zeros.
+ *   one buffer, level l at byte offset level_offset[l], holding for every query
+ *   b*N + p (p < N = H*W) a map of Hp_l x Wp_l elements, Hl = H >> l, Wl = W >> l (floor,
+ *   like avg_pool2d), Wp_l = round_up(Wl, 8), Hp_l = round_up(Hl, 2), stored in 64-byte
+ *   patches of 2 rows x 8 columns (the DRAM access granule), patches of a row pair left
+ *   to right:  offset(y, x) = (y/2)*(2*Wp_l) + (x/8)*16 + (y%2)*8 + x%8.
+ *   Pad columns of level 0 hold zeros; other pads are never read.
  *   Element type: fp32 (FC_VOL_F32) or bf16 (FC_VOL_BF16).
  */
 #ifndef FLOWCORR_H_

@@ -49,15 +49,9 @@ def test_tc_volume_matches_exact(fsb, shape, math, tol):
     ref = corr_spec.pool_pyramid(lv[0], 4)
     for l in range(1, 4):
         assert np.array_equal(lv[l], ref[l]), l
-    # pad columns hold exact zeros
-    st = blk._state
-    off = 0
-    for l, (h, w, wp) in enumerate(fsb.ops.geometry(H, W, 4)):
-        n = B * H * W * h * wp
-        if wp > w:
-            pads = st.pyramid[off:off + n].view(-1, wp)[:, w:]
-            assert not pads.any(), l
-        off += n
+    # pad columns / pad rows of level 0 hold exact zeros (pooled-level pads are never read)
+    lvl0 = fsb.ops.level_padded(blk._state.pyramid, B, H, W, 4)[0]
+    assert not lvl0[:, H:, :].any() and not lvl0[:, :, W:].any()
 
 
 def test_tc_lookup_end_to_end(fsb):
