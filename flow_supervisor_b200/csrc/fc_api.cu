@@ -4,7 +4,7 @@
 #include <cstdio>
 #include <cmath>
 
-#include "fc_common.cuh"
+#include "fc_tma.cuh"
 
 namespace fc {
 
@@ -32,6 +32,18 @@ int simt_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, flo
 size_t tc_build_workspace_bytes(int B, int D, int H, int W, int L, int math);
 int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr, int D, int H, int W,
              int vol_dtype, int math, void* ws, size_t ws_bytes, cudaStream_t s);
+
+EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -19,14 +19,14 @@
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 =
 // epilogue (TMEM lane quarter = warp_id % 4).
-#include <cuda.h>
 #include <cstdlib>
 
-#include "fc_common.cuh"
+#include "fc_tma.cuh"
 
 namespace fc {
 
 int simt_pool_levels(float* pyramid, const Pyramid& pyr, int first_level, cudaStream_t s);   // fc_simt.cu
+int simt_zero_pad_rows(float* pyramid, const Pyramid& pyr, int first, int last, cudaStream_t s);
 
 constexpr int TC_THREADS = 192;
 constexpr int TC_BM = 128;           // queries per CTA (UMMA M)
@@ -39,34 +39,6 @@ constexpr int TC_STG_PITCH = 36;                          // floats; staging row
 constexpr int TC_STG_BYTES = 4 * 32 * TC_STG_PITCH * 4;   // 18 KB
 
 // ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -186,7 +158,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         mbar_init(a_full, 1);
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        mbar_fence_init();
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
@@ -422,25 +394,9 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 }
 
 // ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = []() -> EncodeTiledFn {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-            qres != cudaDriverEntryPointSuccess)
-            return nullptr;
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-
 // 2-D bf16 row-major [rows][cols] tensor, box {64 cols, box_rows}, 128-byte swizzle
 static int make_map(CUtensorMap* map, const void* base, long long rows, int cols, int box_rows) {
-    EncodeTiledFn enc = encode_fn();
+    EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FC_ECUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
@@ -551,6 +507,9 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
         default: e = launch_tc<4>(maps, P, B, s); break;
     }
     if (e) return e;
+    // levels the epilogue wrote: their pad rows are not visited by the tile loop
+    if (P.n_fused > 1)
+        if (int e2 = simt_zero_pad_rows(static_cast<float*>(pyramid), pyr, 1, P.n_fused - 1, s)) return e2;
     return simt_pool_levels(static_cast<float*>(pyramid), pyr, P.n_fused, s);
 }
 

@@ -1,37 +1,19 @@
-// Pyramid lookup, forward and backward (CorrBlock.__call__, corr.py:29-50, and its
-// autograd).  HBM-bound gather/scatter: one CTA = 32 consecutive queries x one
+// Pyramid lookup BACKWARD (autograd of CorrBlock.__call__, corr.py:29-50; the forward
+// lives in fc_lookup_fwd.cu).  HBM-bound scatter: one CTA = 32 consecutive queries x one
 // pyramid level.  The (2r+2)^2 footprint of every query (plus one guard row/column
 // on each side for floor flips of the normalise/un-normalise round trip) is staged
 // into a skewed shared-memory window with 16-byte cp.async row chunks; interpolation
 // then reads the window with lane <-> query so the (B, K, H, W) output stores are
 // 128-byte coalesced.
-#include "fc_common.cuh"
+#include "fc_lookup.cuh"
 
 namespace fc {
 
-constexpr int QT = 32;            // queries per CTA (one per lane)
 constexpr int WIN_ROWS = 12;      // (2r+2) + 2 guard rows, r <= 4
 constexpr int WIN_PITCH = 16;     // floats per window row: 3 alignment + 12 + 1 spare
 constexpr int WIN_STRIDE = 224;   // floats per query window incl. skew room (== 0 mod 32)
 constexpr int LOOKUP_THREADS = 96;
 constexpr int A_PER_WARP = 3;     // x-offsets handled by one warp
-
-struct LookupParams {
-    const float* pyr;
-    const float* coords;    // (B, 2, H, W)
-    float* io;              // forward: out (B, K, H, W); backward: grad_out (read)
-    float* gpyr;            // backward only: gradient pyramid (atomically accumulated)
-    int Q;                  // B * N (< 2^31)
-    int N, L, K;
-    long long off[FC_MAX_LEVELS];
-    int H[FC_MAX_LEVELS], W[FC_MAX_LEVELS], Wp[FC_MAX_LEVELS];
-    int msize[FC_MAX_LEVELS];   // elements per query map (Hp * Wp)
-    AxisConst ax[FC_MAX_LEVELS], ay[FC_MAX_LEVELS];
-    float inv_scale[FC_MAX_LEVELS];
-    int32_t* dbg_x0;
-    int32_t* dbg_y0;
-    uint8_t* dbg_mask;
-};
 
 // Bank skew: lanes reading the same (row, column-within-chunk) of their own windows
 // land on 32 different banks when the per-query alignment offsets cycle mod 4 (the
@@ -82,130 +64,6 @@ __device__ __forceinline__ void query_setup(const LookupParams& P, int level, in
         }
         d.y_lo[lane] = ylo; d.x_s[lane] = xs; d.n_row[lane] = nrow; d.n_chunk[lane] = nchunk;
         d.q_off[lane] = (long long)(gq0 + lane) * P.msize[level];
-    }
-}
-
-// Stage (forward) the footprints of the CTA's 32 queries: rows x 16-byte chunks,
-// zero-filling everything outside the (padded) map -- this IS the reference's
-// padding_mode='zeros'.  Warp w owns queries w, w+3, ...: lanes cover 8 rows x 4 chunks of
-// one query per step (a 64-byte run per row: 4 lanes), then rows 8..11 of two queries.
-__device__ __forceinline__ void stage_slot(const float* base, int Hl, int Wp, int q,
-                                           int row, int chunk, const WinDesc& d, float* win) {
-    if (row < d.n_row[q] && chunk < d.n_chunk[q]) {
-        const int y = d.y_lo[q] + row;
-        const int x = d.x_s[q] + 4 * chunk;
-        float* dst = win + win_base(q) + row * WIN_PITCH + 4 * chunk;
-        if ((unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wp)
-            cp_async16(dst, base + d.q_off[q] + tile_off(y, x, Wp));
-        else
-            *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-}
-
-__device__ __forceinline__ void stage_windows(const LookupParams& P, int level,
-                                              const WinDesc& d, float* win) {
-    const int Hl = P.H[level], Wp = P.Wp[level];
-    const float* base = P.pyr + P.off[level];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row = lane >> 2, chunk = lane & 3;
-    for (int q = warp; q < QT; q += LOOKUP_THREADS / 32)                   // rows 0..7
-        stage_slot(base, Hl, Wp, q, row, chunk, d, win);
-    for (int q = warp; q < QT; q += 2 * (LOOKUP_THREADS / 32)) {          // rows 8..11, two queries
-        const int qq = q + (lane >> 4) * (LOOKUP_THREADS / 32);
-        if (qq < QT) stage_slot(base, Hl, Wp, qq, 8 + (row & 3), chunk, d, win);
-    }
-    cp_async_commit();
-}
-
-template <int RADIUS, int CM>
-__global__ void __launch_bounds__(LOOKUP_THREADS)
-lookup_fwd_kernel(const LookupParams P) {
-    constexpr int R = 2 * RADIUS + 1;
-    __shared__ __align__(16) float win[QT * WIN_STRIDE];
-    __shared__ WinDesc desc;
-
-    const int level = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gq0 = blockIdx.x * QT;
-    const int gq = gq0 + lane;
-    const bool live = gq < P.Q;
-
-    float cx, cy; bool near_; int b, p;
-    query_setup<RADIUS, CM>(P, level, lane, gq0, live, b, p, cx, cy, near_, desc, warp == 0);
-    __syncthreads();
-    stage_windows(P, level, desc, win);
-
-    // tap arithmetic overlaps the copies in flight
-    const int Hl = P.H[level], Wl = P.W[level];
-    int y0[R]; float wy0[R], wy1[R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) axis_tap<CM>(cy, j - RADIUS, P.ay[level], y0[j], wy0[j], wy1[j]);
-    const int ylo = desc.y_lo[lane], xs = desc.x_s[lane];
-
-    float* outq = P.io + ((long long)b * P.K + level * R * R) * P.N + p;
-
-    if (P.dbg_y0 != nullptr && live && warp == 0) {
-#pragma unroll
-        for (int j = 0; j < R; ++j) P.dbg_y0[((long long)gq * P.L + level) * R + j] = y0[j];
-    }
-
-    cp_async_wait<0>();
-    __syncthreads();
-    if (!live) return;
-
-    const float* wq = win + win_base(lane);
-    // No floor flip among this query's y taps (the overwhelmingly common case): tap j reads
-    // window rows ry0+j and ry0+j+1, so one horizontally interpolated column of R+1 rows
-    // serves all R outputs of an x-offset (2 shared loads per row instead of 4 per output).
-    bool regular = near_;
-#pragma unroll
-    for (int j = 1; j < R; ++j) regular = regular && (y0[j] == y0[0] + j);
-    const int ry0 = min(max(y0[0] - ylo, 0), WIN_ROWS - 1 - R);
-    const bool want_mask = P.dbg_mask != nullptr;
-#pragma unroll
-    for (int aa = 0; aa < A_PER_WARP; ++aa) {
-        const int a = warp * A_PER_WARP + aa;
-        if (a >= R) break;
-        int x0; float wx0, wx1;
-        axis_tap<CM>(cx, a - RADIUS, P.ax[level], x0, wx0, wx1);
-        if (P.dbg_x0 != nullptr) P.dbg_x0[((long long)gq * P.L + level) * R + a] = x0;
-        const int rx = min(max(x0 - xs, 0), WIN_PITCH - 2);
-        float* oa = outq + (long long)(a * R) * P.N;
-        if (regular) {
-            const float* w = wq + ry0 * WIN_PITCH + rx;
-            float hprev = fmaf(wx1, w[1], wx0 * w[0]);
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const float hnext = fmaf(wx1, w[(j + 1) * WIN_PITCH + 1], wx0 * w[(j + 1) * WIN_PITCH]);
-                *oa = fmaf(wy1[j], hnext, wy0[j] * hprev);
-                oa += P.N;
-                hprev = hnext;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                float val = 0.f;
-                if (near_) {
-                    const int ry = min(max(y0[j] - ylo, 0), WIN_ROWS - 2);
-                    const float* w = wq + ry * WIN_PITCH + rx;
-                    const float top = fmaf(wx1, w[1], wx0 * w[0]);
-                    const float bot = fmaf(wx1, w[WIN_PITCH + 1], wx0 * w[WIN_PITCH]);
-                    val = fmaf(wy1[j], bot, wy0[j] * top);
-                }
-                *oa = val;
-                oa += P.N;
-            }
-        }
-        if (want_mask) {
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const bool xa = (x0 >= 0 && x0 < Wl), xb = (x0 + 1 >= 0 && x0 + 1 < Wl);
-                const bool ya = (y0[j] >= 0 && y0[j] < Hl), yb = (y0[j] + 1 >= 0 && y0[j] + 1 < Hl);
-                uint8_t m = (uint8_t)((ya && xa) | ((ya && xb) << 1) | ((yb && xa) << 2) | ((yb && xb) << 3));
-                if (!near_) m = 0;
-                P.dbg_mask[(((long long)gq * P.L + level) * R + a) * R + j] = m;
-            }
-        }
     }
 }
 
@@ -290,29 +148,6 @@ lookup_bwd_kernel(const LookupParams P) {
 }
 
 // ---------------------------------------------------------------- host side
-static int fill_params(LookupParams& P, const Pyramid& pyr, int radius) {
-    P.Q = pyr.B * pyr.N;
-    P.N = pyr.N; P.L = pyr.L;
-    const int R = 2 * radius + 1;
-    P.K = pyr.L * R * R;
-    for (int l = 0; l < pyr.L; ++l) {
-        P.off[l] = pyr.lv[l].offset;
-        P.H[l] = pyr.lv[l].H; P.W[l] = pyr.lv[l].W; P.Wp[l] = pyr.lv[l].Wp;
-        P.msize[l] = pyr.lv[l].Hp * pyr.lv[l].Wp;
-        P.ax[l] = make_axis(pyr.lv[l].W);
-        P.ay[l] = make_axis(pyr.lv[l].H);
-        P.inv_scale[l] = 1.0f / (float)(1 << l);
-    }
-    return 0;
-}
-
-template <int RADIUS>
-static void launch_fwd(const LookupParams& P, int coord_mode, dim3 grid, cudaStream_t s) {
-    if (coord_mode == FC_COORD_CUDA)
-        lookup_fwd_kernel<RADIUS, FC_COORD_CUDA><<<grid, LOOKUP_THREADS, 0, s>>>(P);
-    else
-        lookup_fwd_kernel<RADIUS, FC_COORD_CPU><<<grid, LOOKUP_THREADS, 0, s>>>(P);
-}
 template <int RADIUS>
 static void launch_bwd(const LookupParams& P, int coord_mode, dim3 grid, cudaStream_t s) {
     if (coord_mode == FC_COORD_CUDA)
@@ -321,47 +156,9 @@ static void launch_bwd(const LookupParams& P, int coord_mode, dim3 grid, cudaStr
         lookup_bwd_kernel<RADIUS, FC_COORD_CPU><<<grid, LOOKUP_THREADS, 0, s>>>(P);
 }
 
-static int check_common(const Pyramid& pyr, int radius, int coord_mode) {
-    FC_REQUIRE((long long)pyr.B * pyr.N < (1LL << 31) - QT, "B*H*W = %lld queries exceed 2^31", (long long)pyr.B * pyr.N);
-    FC_REQUIRE(radius >= 1 && radius <= FC_MAX_RADIUS, "radius %d unsupported (1..%d)", radius, FC_MAX_RADIUS);
-    FC_REQUIRE(coord_mode == FC_COORD_CUDA || coord_mode == FC_COORD_CPU, "bad coord_mode %d", coord_mode);
-    for (int l = 0; l < pyr.L; ++l)
-        FC_REQUIRE(pyr.lv[l].H >= 2 && pyr.lv[l].W >= 2,
-                   "pyramid level %d is %dx%d: a unit dimension makes the reference divide by zero "
-                   "(utils.py:61-62); inputs must be at least %d px on a side",
-                   l, pyr.lv[l].H, pyr.lv[l].W, 16 << (pyr.L - 1));
-    return 0;
-}
-
 }  // namespace fc
 
 using namespace fc;
-
-extern "C" int fc_lookup_fwd(const void* pyramid, const float* coords, float* out,
-                             int B, int H, int W, int num_levels, int radius,
-                             int vol_dtype, int coord_mode,
-                             int32_t* dbg_x0, int32_t* dbg_y0, uint8_t* dbg_mask, void* stream) {
-    FC_REQUIRE(pyramid && coords && out, "fc_lookup_fwd: null pointer");
-    FC_REQUIRE(vol_dtype == FC_VOL_F32, "fc_lookup_fwd: vol_dtype %d not supported yet", vol_dtype);
-    Pyramid pyr;
-    FC_REQUIRE(make_pyramid(pyr, B, H, W, num_levels), "fc_lookup_fwd: bad geometry B=%d H=%d W=%d L=%d", B, H, W, num_levels);
-    if (int e = check_common(pyr, radius, coord_mode)) return e;
-    LookupParams P{};
-    fill_params(P, pyr, radius);
-    P.pyr = static_cast<const float*>(pyramid);
-    P.coords = coords; P.io = out; P.gpyr = nullptr;
-    P.dbg_x0 = dbg_x0; P.dbg_y0 = dbg_y0; P.dbg_mask = dbg_mask;
-    dim3 grid((unsigned)((P.Q + QT - 1) / QT), (unsigned)pyr.L);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    switch (radius) {
-        case 1: launch_fwd<1>(P, coord_mode, grid, s); break;
-        case 2: launch_fwd<2>(P, coord_mode, grid, s); break;
-        case 3: launch_fwd<3>(P, coord_mode, grid, s); break;
-        default: launch_fwd<4>(P, coord_mode, grid, s); break;
-    }
-    FC_LAUNCH_CHECK("lookup_fwd_kernel");
-    return FC_OK;
-}
 
 extern "C" int fc_lookup_bwd(const float* grad_out, const float* coords, float* grad_pyramid,
                              int B, int H, int W, int num_levels, int radius,
@@ -369,7 +166,7 @@ extern "C" int fc_lookup_bwd(const float* grad_out, const float* coords, float* 
     FC_REQUIRE(grad_out && coords && grad_pyramid, "fc_lookup_bwd: null pointer");
     Pyramid pyr;
     FC_REQUIRE(make_pyramid(pyr, B, H, W, num_levels), "fc_lookup_bwd: bad geometry B=%d H=%d W=%d L=%d", B, H, W, num_levels);
-    if (int e = check_common(pyr, radius, coord_mode)) return e;
+    if (int e = check_lookup_common(pyr, radius, coord_mode)) return e;
     LookupParams P{};
     fill_params(P, pyr, radius);
     P.pyr = nullptr; P.coords = coords;

@@ -1,0 +1,54 @@
+// Shared between the lookup forward (fc_lookup_fwd.cu) and backward (fc_lookup.cu).
+#pragma once
+
+#include "fc_common.cuh"
+
+namespace fc {
+
+constexpr int QT = 32;            // queries per tile (one per lane)
+
+struct LookupParams {
+    const float* pyr;
+    const float* coords;    // (B, 2, H, W)
+    float* io;              // forward: out (B, K, H, W); backward: grad_out (read)
+    float* gpyr;            // backward only: gradient pyramid (atomically accumulated)
+    int Q;                  // B * N (< 2^31)
+    int N, L, K;
+    long long off[FC_MAX_LEVELS];
+    int H[FC_MAX_LEVELS], W[FC_MAX_LEVELS], Wp[FC_MAX_LEVELS];
+    int msize[FC_MAX_LEVELS];   // elements per query map (Hp * Wp)
+    AxisConst ax[FC_MAX_LEVELS], ay[FC_MAX_LEVELS];
+    float inv_scale[FC_MAX_LEVELS];
+    int32_t* dbg_x0;
+    int32_t* dbg_y0;
+    uint8_t* dbg_mask;
+};
+
+inline void fill_params(LookupParams& P, const Pyramid& pyr, int radius) {
+    P.Q = pyr.B * pyr.N;
+    P.N = pyr.N; P.L = pyr.L;
+    const int R = 2 * radius + 1;
+    P.K = pyr.L * R * R;
+    for (int l = 0; l < pyr.L; ++l) {
+        P.off[l] = pyr.lv[l].offset;
+        P.H[l] = pyr.lv[l].H; P.W[l] = pyr.lv[l].W; P.Wp[l] = pyr.lv[l].Wp;
+        P.msize[l] = pyr.lv[l].Hp * pyr.lv[l].Wp;
+        P.ax[l] = make_axis(pyr.lv[l].W);
+        P.ay[l] = make_axis(pyr.lv[l].H);
+        P.inv_scale[l] = 1.0f / (float)(1 << l);
+    }
+}
+
+inline int check_lookup_common(const Pyramid& pyr, int radius, int coord_mode) {
+    FC_REQUIRE((long long)pyr.B * pyr.N < (1LL << 31) - QT, "B*H*W = %lld queries exceed 2^31", (long long)pyr.B * pyr.N);
+    FC_REQUIRE(radius >= 1 && radius <= FC_MAX_RADIUS, "radius %d unsupported (1..%d)", radius, FC_MAX_RADIUS);
+    FC_REQUIRE(coord_mode == FC_COORD_CUDA || coord_mode == FC_COORD_CPU, "bad coord_mode %d", coord_mode);
+    for (int l = 0; l < pyr.L; ++l)
+        FC_REQUIRE(pyr.lv[l].H >= 2 && pyr.lv[l].W >= 2,
+                   "pyramid level %d is %dx%d: a unit dimension makes the reference divide by zero "
+                   "(utils.py:61-62); inputs must be at least %d px on a side",
+                   l, pyr.lv[l].H, pyr.lv[l].W, 16 << (pyr.L - 1));
+    return 0;
+}
+
+}  // namespace fc

@@ -1,0 +1,414 @@
+// Pyramid lookup FORWARD (CorrBlock.__call__, corr.py:29-50 + utils.py:57-65 + ATen
+// grid_sample(bilinear, zeros, align_corners=True)): the per-GRU-iteration HBM-bound gather.
+//
+// Persistent CTAs (one per SM) walk over tiles = (32 consecutive queries) x (one pyramid level).
+// A query's footprint is ONE TMA tensor load: the level is described to the TMA unit as a
+// 3-D tensor [query][row pair][2*Wp floats] over the 2x8-patch layout (include/flowcorr.h),
+// and a box of {2|3 patches, 5|6 row pairs, 1 query} at signed coordinates lands the
+// (2r+2)^2 footprint (+1 guard row/column for floor flips of the normalise/un-normalise
+// round trip) in shared memory.  Everything outside the padded map is zero-filled by the
+// TMA unit itself -- that IS the reference's padding_mode='zeros'; pad rows/columns inside
+// the map hold zeros by the pyramid invariant.  Four box shapes per level keep the DRAM
+// traffic at the 64-byte patches the footprint really touches.
+//
+// A 6-stage mbarrier ring decouples three producer warps (tile k -> producer k % 3: coordinate
+// prefetch, footprint arithmetic, one TMA issue per lane) from three consumer groups of
+// three warps (tile k -> group k % 3).  Interpolation: lane <-> query, warp <-> three
+// x-offsets, so every store of the (B, K, H, W) output is a coalesced
+// 128-byte row; one horizontally interpolated column of R+1 rows serves all R outputs of an
+// x-offset.  The integer part (fc::axis_tap) is bit-exact to the reference's op sequence.
+#include <mutex>
+
+#include "fc_lookup.cuh"
+#include "fc_tma.cuh"
+
+namespace fc {
+
+constexpr int LF_PTEAMS = 3;                                  // producer teams (tile k -> team k % 3)
+constexpr int LF_PSPLIT = 1;                                  // warps per team: each issues 32 / PSPLIT of a tile's loads
+constexpr int LF_PRODUCERS = LF_PTEAMS * LF_PSPLIT;           // warps issuing TMA loads
+constexpr int LF_GROUPS = 3;                                  // consumer groups (tile k -> group k % 3)
+constexpr int LF_GWARPS = 3;                                  // warps per group (x-offset thirds)
+constexpr int LF_THREADS = 32 * (LF_PRODUCERS + LF_GROUPS * LF_GWARPS);   // 352
+constexpr int LF_STAGES = 6;
+// a ring stage must always be filled by the same producer and drained by the same group:
+// an mbarrier parity wait may run at most one phase ahead of the barrier
+static_assert(LF_STAGES % LF_PTEAMS == 0 && LF_STAGES % LF_GROUPS == 0, "stage ownership");
+constexpr int LF_WIN_FLOATS = 6 * 3 * 16;                     // 6 row pairs x 3 patches x 16 floats
+constexpr int LF_WIN_BYTES = LF_WIN_FLOATS * 4;               // 1152
+constexpr int LF_STAGE_BYTES = QT * LF_WIN_BYTES;             // 36 864 B per stage
+
+struct LookupMaps {
+    CUtensorMap m[FC_MAX_LEVELS][4];      // [level][(6 row pairs ? 2 : 0) + (3 patches ? 1 : 0)]
+};
+
+struct alignas(16) QueryDesc {           // producer -> consumers, per stage and lane
+    int ybase;                            // first window row    (2 * first row pair; may be negative)
+    int xbase;                            // first window column (8 * first patch;    may be negative)
+    int pitch;                            // BYTES per window row pair (128 or 192)
+    int valid;                            // 0: dead or far query -> all outputs are exact zeros
+};
+
+struct LfShared {
+    uint64_t full[LF_STAGES];
+    uint64_t empty[LF_STAGES];
+    QueryDesc desc[LF_STAGES][QT];
+};
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+struct LfQuery { int level, gq; bool live, near_; float cx, cy; };
+
+template <int RADIUS, int CM>
+__device__ __forceinline__ LfQuery lf_load_query(const LookupParams& P, int tile, int lane) {
+    LfQuery q;
+    q.level = tile % P.L;
+    q.gq = (tile / P.L) * QT + lane;
+    q.live = q.gq < P.Q;
+    q.cx = 0.f; q.cy = 0.f;
+    if (q.live) {
+        const int b = q.gq / P.N, p = q.gq - b * P.N;
+        const float* c = P.coords + (long long)b * 2 * P.N + p;
+        q.cx = __ldg(c);                                             // raw: scaled by lf_finish_query,
+        q.cy = __ldg(c + P.N);                                       // so a prefetch does not stall on the load
+    }
+    q.near_ = false;
+    return q;
+}
+
+__device__ __forceinline__ void lf_finish_query(const LookupParams& P, LfQuery& q) {
+    q.cx = __fmul_rn(q.cx, P.inv_scale[q.level]);
+    q.cy = __fmul_rn(q.cy, P.inv_scale[q.level]);
+    // beyond 2^20 every tap is out of bounds for any map this library accepts and the
+    // +-1 flip bound used to size the window no longer holds; NaN compares false.
+    q.near_ = q.live && (fabsf(q.cx) < 1048576.f) && (fabsf(q.cy) < 1048576.f);
+}
+
+// Producer: one warp issues the 32 footprint loads of a tile into ring stage `stage`.
+template <int RADIUS, int CM>
+__device__ __forceinline__ void lf_produce(const LookupParams& P, const LookupMaps& M, LfShared& sh,
+                                           uint32_t win, const LfQuery& q, int stage, int lane, int member) {
+    constexpr int R = 2 * RADIUS + 1;
+    QueryDesc d{0, 0, 128, 0};
+    uint32_t bytes = 0;
+    const bool mine = (lane / (32 / LF_PSPLIT)) == member;          // this warp's share of the tile's queries
+    if (q.near_ && mine) {
+        const int level = q.level;
+        int xl, xh, yl, yh; float t0, t1;
+        axis_tap<CM>(q.cx, -RADIUS, P.ax[level], xl, t0, t1);
+        axis_tap<CM>(q.cx, R - 1 - RADIUS, P.ax[level], xh, t0, t1);
+        axis_tap<CM>(q.cy, -RADIUS, P.ay[level], yl, t0, t1);
+        axis_tap<CM>(q.cy, R - 1 - RADIUS, P.ay[level], yh, t0, t1);
+        const int rp0 = yl >> 1, pc0 = xl >> 3;                       // arithmetic shifts: floor
+        const int n_rp = ((yh + 1) >> 1) - rp0 + 1;                   // <= 6 (taps are monotone, span <= R)
+        const int n_pc = ((xh + 1) >> 3) - pc0 + 1;                   // <= 3
+        const int sel = (n_rp > 5 ? 2 : 0) + (n_pc > 2 ? 1 : 0);
+        const int box_rp = n_rp > 5 ? 6 : 5, box_pc = n_pc > 2 ? 3 : 2;
+        d.ybase = 2 * rp0; d.xbase = 8 * pc0; d.pitch = 64 * box_pc; d.valid = 1;
+        bytes = (uint32_t)(box_rp * box_pc * 64);
+        tma_load_3d(win + stage * LF_STAGE_BYTES + lane * LF_WIN_BYTES, &M.m[level][sel],
+                    smem_u32(&sh.full[stage]), 16 * pc0, rp0, q.gq);
+    }
+    if (mine) sh.desc[stage][lane] = d;
+    const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+    __syncwarp();
+    if (lane == 0) mbar_expect_tx(&sh.full[stage], total);
+}
+
+// Consumer: warp `w` of a group interpolates x-offsets [w*APW, w*APW + APW) of the tile.
+template <int RADIUS, int CM, bool DBG>
+__device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, uint32_t win, const LfQuery& q,
+                                           int stage, uint32_t parity, int lane, int w) {
+    constexpr int R = 2 * RADIUS + 1;
+    constexpr int APW = (R + LF_GWARPS - 1) / LF_GWARPS;             // x-offsets per warp
+    const int level = q.level, gq = q.gq;
+
+    // tap arithmetic overlaps the loads in flight
+    int y0[R]; float wy0[R], wy1[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) axis_tap<CM>(q.cy, j - RADIUS, P.ay[level], y0[j], wy0[j], wy1[j]);
+    int x0[APW]; float wx0[APW], wx1[APW];
+#pragma unroll
+    for (int aa = 0; aa < APW; ++aa) {
+        const int a = min(w * APW + aa, R - 1);
+        axis_tap<CM>(q.cx, a - RADIUS, P.ax[level], x0[aa], wx0[aa], wx1[aa]);
+    }
+    bool regular = true;
+#pragma unroll
+    for (int j = 1; j < R; ++j) regular = regular && (y0[j] == y0[0] + j);
+#pragma unroll
+    for (int aa = 1; aa < APW; ++aa) regular = regular && (x0[aa] == x0[0] + aa);
+
+    const int b = q.live ? gq / P.N : 0, p = gq - b * P.N;
+    float* outq = P.io + ((long long)b * P.K + level * R * R + w * APW * R) * P.N + p;
+    const long long sa = (long long)R * P.N;                         // stride between x-offsets
+
+    mbar_wait(&sh.full[stage], parity);
+    const QueryDesc d = sh.desc[stage][lane];
+
+    if (q.live) {
+        const uint32_t wq = win + stage * LF_STAGE_BYTES + lane * LF_WIN_BYTES;
+        const int pitch = d.pitch;
+        if (!d.valid) {
+#pragma unroll
+            for (int aa = 0; aa < APW; ++aa)
+                if (w * APW + aa < R) {
+#pragma unroll
+                    for (int j = 0; j < R; ++j) outq[aa * sa + (long long)j * P.N] = 0.f;
+                }
+        } else if (regular) {
+            // byte addresses of window columns x0[0] .. x0[0]+APW (a patch jump every 8 columns)
+            uint32_t col[APW + 1];
+#pragma unroll
+            for (int i = 0; i <= APW; ++i) {
+                const int xr = min(max(x0[0] + i - d.xbase, 0), 23);
+                col[i] = wq + 4u * (uint32_t)(xr + (xr & ~7));
+            }
+            // footprint row n = y0[0] - ybase + r sits at (n >> 1) * pitch + (n & 1) * 32 bytes
+            const int n0 = min(max(y0[0] - d.ybase, 0), 1);
+            uint32_t rofs = 32u * n0;
+            uint32_t step = n0 ? (uint32_t)pitch - 32u : 32u;         // n even -> +32, n odd -> +pitch-32
+            float hprev[APW];
+            {
+                float v[APW + 1];
+#pragma unroll
+                for (int i = 0; i <= APW; ++i) v[i] = lds_f32(col[i] + rofs);
+#pragma unroll
+                for (int aa = 0; aa < APW; ++aa) hprev[aa] = fmaf(wx1[aa], v[aa + 1], wx0[aa] * v[aa]);
+            }
+            float* oj = outq;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                rofs += step;
+                step = (uint32_t)pitch - step;
+                float v[APW + 1];
+#pragma unroll
+                for (int i = 0; i <= APW; ++i) v[i] = lds_f32(col[i] + rofs);
+#pragma unroll
+                for (int aa = 0; aa < APW; ++aa) {
+                    const float hnext = fmaf(wx1[aa], v[aa + 1], wx0[aa] * v[aa]);
+                    if (w * APW + aa < R) oj[aa * sa] = fmaf(wy1[j], hnext, wy0[j] * hprev[aa]);
+                    hprev[aa] = hnext;
+                }
+                oj += P.N;
+            }
+        } else {
+            // floor flips among the taps (lattice coordinates): every tap addressed on its own
+#pragma unroll
+            for (int aa = 0; aa < APW; ++aa) {
+                if (w * APW + aa >= R) break;
+                const int xa = min(max(x0[aa] - d.xbase, 0), 22), xb = xa + 1;
+                const uint32_t ca = wq + 4u * (uint32_t)(xa + (xa & ~7)), cb = wq + 4u * (uint32_t)(xb + (xb & ~7));
+                float* oa = outq + aa * sa;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int ya = min(max(y0[j] - d.ybase, 0), 10), yb = ya + 1;
+                    const uint32_t ra = (uint32_t)((ya >> 1) * pitch + (ya & 1) * 32);
+                    const uint32_t rb = (uint32_t)((yb >> 1) * pitch + (yb & 1) * 32);
+                    const float top = fmaf(wx1[aa], lds_f32(cb + ra), wx0[aa] * lds_f32(ca + ra));
+                    const float bot = fmaf(wx1[aa], lds_f32(cb + rb), wx0[aa] * lds_f32(ca + rb));
+                    *oa = fmaf(wy1[j], bot, wy0[j] * top);
+                    oa += P.N;
+                }
+            }
+        }
+        if (DBG) {
+            const int Hl = P.H[level], Wl = P.W[level];
+            if (P.dbg_y0 != nullptr && w == 0) {
+#pragma unroll
+                for (int j = 0; j < R; ++j) P.dbg_y0[((long long)gq * P.L + level) * R + j] = y0[j];
+            }
+#pragma unroll
+            for (int aa = 0; aa < APW; ++aa) {
+                const int a = w * APW + aa;
+                if (a >= R) break;
+                if (P.dbg_x0 != nullptr) P.dbg_x0[((long long)gq * P.L + level) * R + a] = x0[aa];
+                if (P.dbg_mask != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        const bool xa = (x0[aa] >= 0 && x0[aa] < Wl), xb = (x0[aa] + 1 >= 0 && x0[aa] + 1 < Wl);
+                        const bool ya = (y0[j] >= 0 && y0[j] < Hl), yb = (y0[j] + 1 >= 0 && y0[j] + 1 < Hl);
+                        uint8_t m = (uint8_t)((ya && xa) | ((ya && xb) << 1) | ((yb && xa) << 2) | ((yb && xb) << 3));
+                        if (!q.near_) m = 0;
+                        P.dbg_mask[(((long long)gq * P.L + level) * R + a) * R + j] = m;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sh.empty[stage]);
+}
+
+template <int RADIUS, int CM, bool DBG>
+__global__ void __launch_bounds__(LF_THREADS, 1)
+lookup_fwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, int n_tiles) {
+    extern __shared__ __align__(1024) uint8_t lf_smem[];
+    const uint32_t win = smem_u32(lf_smem);                          // [stage][query][6 x 3 x 16 floats]
+    LfShared& sh = *reinterpret_cast<LfShared*>(lf_smem + LF_STAGES * LF_STAGE_BYTES);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < LF_STAGES; ++i) { mbar_init(&sh.full[i], LF_PSPLIT); mbar_init(&sh.empty[i], LF_GWARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // tiles of this CTA: blockIdx.x, + gridDim.x, ...   (k-th local tile lives in stage k % LF_STAGES)
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int n_local = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+
+    if (warp < LF_PRODUCERS) {
+        const int team = warp / LF_PSPLIT, member = warp - team * LF_PSPLIT;
+        int k = team;
+        if (k < n_local) {
+            LfQuery q = lf_load_query<RADIUS, CM>(P, first + k * stride, lane);
+            while (true) {
+                const int kn = k + LF_PTEAMS;
+                LfQuery qn = q;
+                if (kn < n_local) qn = lf_load_query<RADIUS, CM>(P, first + kn * stride, lane);   // prefetch coords
+                const int s = k % LF_STAGES;
+                if (k >= LF_STAGES) mbar_wait(&sh.empty[s], ((uint32_t)(k / LF_STAGES) & 1u) ^ 1u);
+                lf_finish_query(P, q);
+                lf_produce<RADIUS, CM>(P, M, sh, win, q, s, lane, member);
+                if (kn >= n_local) break;
+                k = kn; q = qn;
+            }
+        }
+    } else {
+        const int cw = warp - LF_PRODUCERS, g = cw / LF_GWARPS, w = cw - g * LF_GWARPS;
+        int k = g;
+        if (k < n_local) {
+            LfQuery q = lf_load_query<RADIUS, CM>(P, first + k * stride, lane);
+            while (true) {
+                const int kn = k + LF_GROUPS;
+                LfQuery qn = q;
+                if (kn < n_local) qn = lf_load_query<RADIUS, CM>(P, first + kn * stride, lane);   // prefetch coords
+                lf_finish_query(P, q);
+                lf_consume<RADIUS, CM, DBG>(P, sh, win, q, k % LF_STAGES, (uint32_t)(k / LF_STAGES) & 1u, lane, w);
+                if (kn >= n_local) break;
+                k = kn; q = qn;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- host side
+// Tensor maps are a pure function of (pyramid pointer, geometry): memoised so that the
+// per-iteration call does not pay 4 * L driver encodes.
+struct MapKey {
+    const void* ptr; int B, H, W, L;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && B == o.B && H == o.H && W == o.W && L == o.L; }
+};
+static std::mutex g_map_mutex;
+static constexpr int MAP_CACHE = 16;
+static MapKey g_map_keys[MAP_CACHE];
+static LookupMaps g_map_vals[MAP_CACHE];
+static int g_map_next = 0, g_map_used = 0;
+
+static int encode_level_maps(LookupMaps& M, const float* pyramid, const Pyramid& pyr) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FC_ECUDA; }
+    const long long Q = (long long)pyr.B * pyr.N;
+    for (int l = 0; l < pyr.L; ++l) {
+        const Level& lv = pyr.lv[l];
+        cuuint64_t dims[3] = {(cuuint64_t)(2 * lv.Wp), (cuuint64_t)(lv.Hp / 2), (cuuint64_t)Q};
+        cuuint64_t strides[2] = {(cuuint64_t)(2 * lv.Wp) * 4, (cuuint64_t)lv.Hp * lv.Wp * 4};
+        cuuint32_t estr[3] = {1, 1, 1};
+        for (int sel = 0; sel < 4; ++sel) {
+            cuuint32_t box[3] = {(cuuint32_t)((sel & 1) ? 48 : 32), (cuuint32_t)((sel & 2) ? 6 : 5), 1};
+            CUresult r = enc(&M.m[l][sel], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                             const_cast<float*>(pyramid + lv.offset), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                set_error("cuTensorMapEncodeTiled failed (%d) for level %d (%dx%d, pitch %d)", (int)r, l, lv.H, lv.W, lv.Wp);
+                return FC_ECUDA;
+            }
+        }
+    }
+    return FC_OK;
+}
+
+static int get_level_maps(LookupMaps& M, const float* pyramid, const Pyramid& pyr, int H, int W) {
+    const MapKey key{pyramid, pyr.B, H, W, pyr.L};
+    {
+        std::lock_guard<std::mutex> g(g_map_mutex);
+        for (int i = 0; i < g_map_used; ++i)
+            if (g_map_keys[i] == key) { M = g_map_vals[i]; return FC_OK; }
+    }
+    if (int e = encode_level_maps(M, pyramid, pyr)) return e;
+    std::lock_guard<std::mutex> g(g_map_mutex);
+    g_map_keys[g_map_next] = key; g_map_vals[g_map_next] = M;
+    g_map_next = (g_map_next + 1) % MAP_CACHE;
+    if (g_map_used < MAP_CACHE) ++g_map_used;
+    return FC_OK;
+}
+
+template <int RADIUS, int CM, bool DBG>
+static int launch_fwd3(const LookupMaps& M, const LookupParams& P, int n_tiles, int n_sm, cudaStream_t s) {
+    const size_t smem = (size_t)LF_STAGES * LF_STAGE_BYTES + sizeof(LfShared);
+    FC_CUDA(cudaFuncSetAttribute(lookup_fwd_kernel<RADIUS, CM, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    lookup_fwd_kernel<RADIUS, CM, DBG><<<grid, LF_THREADS, smem, s>>>(M, P, n_tiles);
+    FC_LAUNCH_CHECK("lookup_fwd_kernel");
+    return FC_OK;
+}
+template <int RADIUS>
+static int launch_fwd2(const LookupMaps& M, const LookupParams& P, int n_tiles, int n_sm, int coord_mode, bool dbg, cudaStream_t s) {
+    if (coord_mode == FC_COORD_CUDA)
+        return dbg ? launch_fwd3<RADIUS, FC_COORD_CUDA, true>(M, P, n_tiles, n_sm, s)
+                   : launch_fwd3<RADIUS, FC_COORD_CUDA, false>(M, P, n_tiles, n_sm, s);
+    return dbg ? launch_fwd3<RADIUS, FC_COORD_CPU, true>(M, P, n_tiles, n_sm, s)
+               : launch_fwd3<RADIUS, FC_COORD_CPU, false>(M, P, n_tiles, n_sm, s);
+}
+
+static int sm_count(int& n_sm) {
+    static thread_local int cached_dev = -1, cached_sm = 0;
+    int dev = 0;
+    FC_CUDA(cudaGetDevice(&dev));
+    if (dev != cached_dev) {
+        FC_CUDA(cudaDeviceGetAttribute(&cached_sm, cudaDevAttrMultiProcessorCount, dev));
+        cached_dev = dev;
+    }
+    n_sm = cached_sm;
+    return FC_OK;
+}
+
+}  // namespace fc
+
+using namespace fc;
+
+extern "C" int fc_lookup_fwd(const void* pyramid, const float* coords, float* out,
+                             int B, int H, int W, int num_levels, int radius,
+                             int vol_dtype, int coord_mode,
+                             int32_t* dbg_x0, int32_t* dbg_y0, uint8_t* dbg_mask, void* stream) {
+    FC_REQUIRE(pyramid && coords && out, "fc_lookup_fwd: null pointer");
+    FC_REQUIRE(vol_dtype == FC_VOL_F32, "fc_lookup_fwd: vol_dtype %d not supported yet", vol_dtype);
+    Pyramid pyr;
+    FC_REQUIRE(make_pyramid(pyr, B, H, W, num_levels), "fc_lookup_fwd: bad geometry B=%d H=%d W=%d L=%d", B, H, W, num_levels);
+    if (int e = check_lookup_common(pyr, radius, coord_mode)) return e;
+    FC_REQUIRE((reinterpret_cast<uintptr_t>(pyramid) & 15u) == 0, "fc_lookup_fwd: pyramid must be 16-byte aligned");
+    LookupParams P{};
+    fill_params(P, pyr, radius);
+    P.pyr = static_cast<const float*>(pyramid);
+    P.coords = coords; P.io = out; P.gpyr = nullptr;
+    P.dbg_x0 = dbg_x0; P.dbg_y0 = dbg_y0; P.dbg_mask = dbg_mask;
+    LookupMaps M;
+    if (int e = get_level_maps(M, P.pyr, pyr, H, W)) return e;
+    int n_sm = 0;
+    if (int e = sm_count(n_sm)) return e;
+    const int n_tiles = ((P.Q + QT - 1) / QT) * pyr.L;
+    const bool dbg = dbg_x0 || dbg_y0 || dbg_mask;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (radius) {
+        case 1: return launch_fwd2<1>(M, P, n_tiles, n_sm, coord_mode, dbg, s);
+        case 2: return launch_fwd2<2>(M, P, n_tiles, n_sm, coord_mode, dbg, s);
+        case 3: return launch_fwd2<3>(M, P, n_tiles, n_sm, coord_mode, dbg, s);
+        default: return launch_fwd2<4>(M, P, n_tiles, n_sm, coord_mode, dbg, s);
+    }
+}

@@ -208,6 +208,30 @@ static inline unsigned grid_for(long long total, int threads) {
     return (unsigned)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
+// Pad row (y = H when H is odd) of every query map of levels [first, last]: the lookup's TMA
+// boxes read whole row pairs, so the row must hold zeros (the pyramid invariant).
+__global__ void zero_pad_row_kernel(float* __restrict__ lvl, long long Q, int H, int Wp, int msize) {
+    const int per = Wp / 4;                                    // float4 per pad row
+    const long long total = Q * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long q = i / per;
+        const int x = (int)(i - q * per) * 4;
+        *reinterpret_cast<float4*>(lvl + q * msize + tile_off(H, x, Wp)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+int simt_zero_pad_rows(float* pyramid, const Pyramid& pyr, int first, int last, cudaStream_t s) {
+    const long long Q = (long long)pyr.B * pyr.N;
+    for (int l = first; l <= last && l < pyr.L; ++l) {
+        const Level& a = pyr.lv[l];
+        if (a.Hp == a.H) continue;
+        zero_pad_row_kernel<<<grid_for(Q * (a.Wp / 4), 256), 256, 0, s>>>(pyramid + a.offset, Q, a.H, a.Wp, a.Hp * a.Wp);
+        FC_LAUNCH_CHECK("zero_pad_row_kernel");
+    }
+    return FC_OK;
+}
+
 // computes levels [first_level, L) from the level below each
 int simt_pool_levels(float* pyramid, const Pyramid& pyr, int first_level, cudaStream_t s) {
     const long long Q = (long long)pyr.B * pyr.N;
