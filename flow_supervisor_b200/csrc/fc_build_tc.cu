@@ -31,12 +31,12 @@ int simt_zero_pad_rows(float* pyramid, const Pyramid& pyr, int first, int last, 
 constexpr int TC_THREADS = 192;
 constexpr int TC_BM = 128;           // queries per CTA (UMMA M)
 constexpr int TC_BK = 64;            // bf16 elements per 128-byte swizzle row
-constexpr int TC_SUB = 128;          // target rows per ring stage
+constexpr int TC_BKS = 32;           // k elements per target-operand ring stage (64-byte swizzle rows)
 constexpr int TC_STAGES = 4;
-constexpr int TC_STAGE_BYTES = TC_SUB * TC_BK * 2;        // 16 KB
+constexpr int TC_STAGE_BYTES = 256 * TC_BKS * 2;          // 16 KB: up to 256 target rows x 32 k
 constexpr int TC_ABLK_BYTES = TC_BM * TC_BK * 2;          // 16 KB per k-block of the query tile
-constexpr int TC_STG_PITCH = 36;                          // floats; staging row pitch (16B aligned, conflict-free)
-constexpr int TC_STG_BYTES = 4 * 32 * TC_STG_PITCH * 4;   // 18 KB
+constexpr int TC_STG_FLOATS = 32 * 32;                    // one TMA-store box: [32 queries][32 floats] = 4 KB
+constexpr int TC_STG_BYTES = 4 * 2 * TC_STG_FLOATS * 4;   // 4 epilogue warps x 2 buffers = 32 KB
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -73,6 +73,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// same for 64-byte rows (SWIZZLE_64B): 8-row groups are 512 bytes apart, layout type 4
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
 // instruction descriptor, kind::f16: D=F32 (bit 4), A=B=BF16 (bits 7, 10), K-major both,
 // N>>3 at bit 17, M>>4 at bit 24
 __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
@@ -84,7 +88,7 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
 // row(n) = n (tiled == 0) or tile_off(n / W, n % W, Wp) (tiled == 1: target operand)
 __global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
                                  __nv_bfloat16* __restrict__ lo, int D, int N, int W, int Wp,
-                                 int rows_per_sample, int tiled) {
+                                 int rows_per_sample, int tiled, float prescale) {
     __shared__ float tile[64][33];
     const int b = blockIdx.z, n0 = blockIdx.x * 32, d0 = blockIdx.y * 64;
     const int tx = threadIdx.x, ty = threadIdx.y;            // 32 x 8
@@ -101,7 +105,7 @@ __global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
         const int d = d0 + 2 * tx;
         if (n < N && d < D) {
             const int row = tiled ? tile_off(n / W, n % W, Wp) : n;
-            const float x0 = tile[2 * tx][nl], x1 = tile[2 * tx + 1][nl];
+            const float x0 = tile[2 * tx][nl] * prescale, x1 = tile[2 * tx + 1][nl] * prescale;
             const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
             const long long o = ((long long)b * rows_per_sample + row) * D + d;
             *reinterpret_cast<__nv_bfloat162*>(hi + o) = __nv_bfloat162(h0, h1);
@@ -113,6 +117,10 @@ __global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 }
 
 // ---------------------------------------------------------------- GEMM
+struct TcStoreMaps {
+    CUtensorMap l0_c32, l0_c16;    // level 0 as {NP, N, B}: boxes of 32 queries x 32 / 16 columns
+};
+
 struct TcParams {
     float* lvl[4];         // fused pyramid: level base pointers (level 0 == vol0)
     int lvH[4], lvW[4], lvWp[4], lvHp[4];
@@ -123,7 +131,6 @@ struct TcParams {
     int NT;                // padded targets per tile (multiple of 16, <= 256)
     int n_tiles;           // ceil(NP / NT)
     int m_tiles;           // ceil(N / 128)
-    int sub1;              // rows of the second ring sub-stage (NT - 128, or 0)
     int three_pass;        // 1 = hi*hi + lo*hi + hi*lo, 0 = hi*hi
     float scale;           // 1 / sqrt(D)
 };
@@ -132,8 +139,7 @@ template <int KB>   // KB = D / 64 k-blocks
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                const __grid_constant__ CUtensorMap map_b_hi1, const __grid_constant__ CUtensorMap map_b_lo1,
-                const TcParams P) {
+                const __grid_constant__ TcStoreMaps SM, const TcParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve (all operand regions 1024-byte aligned for SWIZZLE_128B)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -152,7 +158,6 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y, m0 = blockIdx.x * TC_BM;
     const int n_parts = P.three_pass ? 2 : 1;
-    const int n_subs = P.sub1 > 0 ? 2 : 1;
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -177,29 +182,25 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 tma_load_2d(a_hi + kb * TC_ABLK_BYTES, &map_a_hi, a_full, kb * TC_BK, b * P.N + m0);
                 if (P.three_pass) tma_load_2d(a_lo + kb * TC_ABLK_BYTES, &map_a_lo, a_full, kb * TC_BK, b * P.N + m0);
             }
+            // target operand: stages of [NT rows][32 k], hi then lo of each k range
             int it = 0;
             for (int t = 0; t < P.n_tiles; ++t) {
                 const int row0 = b * P.NP + t * P.NT;
-                for (int kb = 0; kb < KB; ++kb)
-                    for (int part = 0; part < n_parts; ++part)
-                        for (int sub = 0; sub < n_subs; ++sub, ++it) {
-                            const int s = it % TC_STAGES;
-                            const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
-                            mbar_wait(b_empty + s, ph ^ 1u);
-                            const int rows = sub == 0 ? (P.NT < TC_SUB ? P.NT : TC_SUB) : P.sub1;
-                            mbar_expect_tx(b_full + s, (uint32_t)(rows * TC_BK * 2));
-                            const CUtensorMap* m = sub == 0 ? (part == 0 ? &map_b_hi : &map_b_lo)
-                                                            : (part == 0 ? &map_b_hi1 : &map_b_lo1);
-                            tma_load_2d(ring + s * TC_STAGE_BYTES, m, b_full + s, kb * TC_BK, row0 + sub * TC_SUB);
-                        }
+                for (int i = 0; i < KB * (TC_BK / TC_BKS); ++i)
+                    for (int part = 0; part < n_parts; ++part, ++it) {
+                        const int s = it % TC_STAGES;
+                        const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                        mbar_wait(b_empty + s, ph ^ 1u);
+                        mbar_expect_tx(b_full + s, (uint32_t)(P.NT * TC_BKS * 2));
+                        tma_load_2d(ring + s * TC_STAGE_BYTES, part == 0 ? &map_b_hi : &map_b_lo, b_full + s,
+                                    i * TC_BKS, row0);
+                    }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const int rows0 = P.NT < TC_SUB ? P.NT : TC_SUB;
-            const uint32_t idesc0 = umma_idesc_bf16(TC_BM, rows0);
-            const uint32_t idesc1 = umma_idesc_bf16(TC_BM, P.sub1 > 0 ? P.sub1 : 16);
+            const uint32_t idesc = umma_idesc_bf16(TC_BM, P.NT);
             mbar_wait(a_full, 0);
             tc_fence_after();
             int it = 0;
@@ -207,57 +208,85 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const int buf = t & 1;
                 mbar_wait(t_empty + buf, ((uint32_t)(t >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                for (int kb = 0; kb < KB; ++kb)
-                    for (int part = 0; part < n_parts; ++part)
-                        for (int sub = 0; sub < n_subs; ++sub, ++it) {
-                            const int s = it % TC_STAGES;
-                            mbar_wait(b_full + s, (uint32_t)(it / TC_STAGES) & 1u);
-                            tc_fence_after();
-                            const uint32_t d_addr = tmem_base + (uint32_t)(buf * 256 + sub * TC_SUB);
-                            const uint32_t idesc = sub == 0 ? idesc0 : idesc1;
-                            const uint32_t b_addr = smem_u32(ring + s * TC_STAGE_BYTES);
-                            const uint32_t ah_addr = smem_u32(a_hi + kb * TC_ABLK_BYTES);
-                            const uint32_t al_addr = smem_u32(a_lo + kb * TC_ABLK_BYTES);
+                const uint32_t d_addr = tmem_base + (uint32_t)(buf * 256);
+                for (int i = 0; i < KB * (TC_BK / TC_BKS); ++i)
+                    for (int part = 0; part < n_parts; ++part, ++it) {
+                        const int s = it % TC_STAGES;
+                        mbar_wait(b_full + s, (uint32_t)(it / TC_STAGES) & 1u);
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(ring + s * TC_STAGE_BYTES);
+                        // query operand: k-block i/2 of the resident SW128 tile, 64-byte half i%2
+                        const uint32_t a_off = (uint32_t)((i >> 1) * TC_ABLK_BYTES + (i & 1) * (TC_BKS * 2));
+                        const uint32_t ah_addr = smem_u32(a_hi) + a_off, al_addr = smem_u32(a_lo) + a_off;
 #pragma unroll
-                            for (int k = 0; k < TC_BK / 16; ++k) {
-                                const uint64_t bd = umma_desc_sw128(b_addr + k * 32);
-                                // part 0: B = hi -> A_hi*B_hi (+ A_lo*B_hi); part 1: B = lo -> A_hi*B_lo
-                                umma_bf16(d_addr, umma_desc_sw128(ah_addr + k * 32), bd, idesc,
-                                          (kb | part | k) != 0 ? 1u : 0u);
-                                if (part == 0 && P.three_pass)
-                                    umma_bf16(d_addr, umma_desc_sw128(al_addr + k * 32), bd, idesc, 1u);
-                            }
-                            umma_commit(b_empty + s);          // frees the ring slot when these MMAs retire
+                        for (int k = 0; k < TC_BKS / 16; ++k) {
+                            const uint64_t bd = umma_desc_sw64(b_addr + k * 32);
+                            // part 0: B = hi -> A_hi*B_hi (+ A_lo*B_hi); part 1: B = lo -> A_hi*B_lo
+                            umma_bf16(d_addr, umma_desc_sw128(ah_addr + k * 32), bd, idesc, (i | part | k) != 0 ? 1u : 0u);
+                            if (part == 0 && P.three_pass)
+                                umma_bf16(d_addr, umma_desc_sw128(al_addr + k * 32), bd, idesc, 1u);
                         }
+                        umma_commit(b_empty + s);              // frees the ring slot when these MMAs retire
+                    }
                 umma_commit(t_full + buf);                      // accumulator complete
             }
         }
     } else {
         // ================= epilogue =================
+        // TMEM -> registers -> (scale, 2x2 pooling) -> shared staging -> TMA tensor store.
+        // A thread owns one query row; 32 accumulator columns = 4 groups of 8 floats that are
+        // contiguous in the query's map (patch layout).  The staging box [group][query][8] is
+        // what the store maps describe, so one elected lane writes 32 queries x 128 bytes with a
+        // single instruction; rows beyond the sample and groups beyond the map are clipped by
+        // the TMA unit.
         const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32)
-        float* my = stg + quarter * 32 * TC_STG_PITCH;
-        const long long row_base = (long long)b * P.N + m0 + quarter * 32;
-        const int rows_valid = P.N - (m0 + quarter * 32);      // rows of this warp inside the sample
+        float* sbuf = stg + quarter * 2 * TC_STG_FLOATS;
+        const int row0 = m0 + quarter * 32;                    // first query row of this warp inside the sample
+        const int rows_valid = P.N - row0;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        uint32_t use = 0;
 
-        // 32 values per thread (one query row each) -> [32 rows][ncols] block of a level:
-        // transposed through shared memory so each store instruction writes whole row segments
-        auto store_chunk = [&](float* base, long long pitch, long long off, int ncols, const float* v) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(my + lane * TC_STG_PITCH + 4 * j) =
-                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        // level 0: this thread's columns [col, col + 32) (or 16 on the last chunk of a tile whose
+        // width is an odd multiple of 16) are 128 (64) contiguous bytes of its query's map.  Staging
+        // rows are swizzled like the store map (SWIZZLE_128B / SWIZZLE_64B) so that a quarter
+        // warp's 16-byte stores hit all 32 banks.
+        auto store_l0 = [&](const float* v, int col, int ncols) {
+            float* buf = sbuf + (use & 1u) * TC_STG_FLOATS;
+            if (lane == 0) tma_wait_group_read<1>();           // the store that last read this buffer is done
             __syncwarp();
-            const int c4 = lane & 7;
+            if (ncols >= 32) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = 4 * i + (lane >> 3);
-                if (r < rows_valid && 4 * c4 < ncols)
-                    *reinterpret_cast<float4*>(base + (row_base + r) * pitch + off + 4 * c4) =
-                        *reinterpret_cast<const float4*>(my + r * TC_STG_PITCH + 4 * c4);
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<float4*>(buf + lane * 32 + ((c ^ (lane & 7)) << 2)) =
+                        make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<float4*>(buf + lane * 16 + ((c ^ ((lane >> 1) & 3)) << 2)) =
+                        make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
             }
+            fence_proxy_async_smem();
             __syncwarp();
+            ++use;
+            if (lane == 0 && rows_valid > 0) {
+                tma_store_3d(ncols >= 32 ? &SM.l0_c32 : &SM.l0_c16, smem_u32(buf), col, row0, b);
+                tma_commit_group();
+            }
         };
+        // pooled levels (1/4, 1/16, 1/64 of the data): 32-byte runs straight from registers
+        auto store_small = [&](float* base, long long msz, long long off, int ncols, const float* v) {
+            if (rows_valid > lane) {
+                float* dst = base + ((long long)b * P.N + row0 + lane) * msz + off;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    if (8 * g < ncols)
+                        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst + g * 16),
+                                     "f"(v[8 * g]), "f"(v[8 * g + 1]), "f"(v[8 * g + 2]), "f"(v[8 * g + 3]),
+                                     "f"(v[8 * g + 4]), "f"(v[8 * g + 5]), "f"(v[8 * g + 6]), "f"(v[8 * g + 7])
+                                     : "memory");
+            }
+        };
+        const bool do_scale = P.scale != 1.0f;
 
         if (P.n_fused <= 1) {
             for (int t = 0; t < P.n_tiles; ++t) {
@@ -270,9 +299,11 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     float v[32];
                     tmem_ld32(lane_addr + (uint32_t)(buf * 256 + c0), v);
                     tmem_ld_wait();
+                    if (do_scale) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] *= P.scale;
-                    store_chunk(P.vol0, P.NP, q0 + c0, ncols - c0, v);
+                        for (int j = 0; j < 32; ++j) v[j] *= P.scale;
+                    }
+                    store_l0(v, q0 + c0, ncols - c0);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -284,28 +315,11 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             // so every 2x2 pooling quad is thread-local and inside one tcgen05.ld.  Levels 2 / 3
             // combine two / four consecutive tiles through the stashes s2 / s3.  Summation
             // order ((a + b) + c) + d, then * 0.25: bit-exact avg_pool2d of the level below
-            // (oracle/corr_spec.py::pool_pyramid).  Pooled levels use the same patch layout:
-            // a row of 32 values = 4 runs of 8 floats, 16 floats apart.
-            auto store_strided = [&](float* base, long long msz, long long off, int ncols, const float* v) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(my + lane * TC_STG_PITCH + 4 * j) =
-                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                __syncwarp();
-                const int c4 = lane & 7;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = 4 * i + (lane >> 3);
-                    if (r < rows_valid && 4 * c4 < ncols)
-                        *reinterpret_cast<float4*>(base + (row_base + r) * msz + off + (c4 >> 1) * 16 + (c4 & 1) * 4) =
-                            *reinterpret_cast<const float4*>(my + r * TC_STG_PITCH + 4 * c4);
-                }
-                __syncwarp();
-            };
+            // (oracle/corr_spec.py::pool_pyramid).
             const int Wp = P.Wp;
             const int W1 = P.lvW[1], W2 = P.lvW[2], W3 = P.lvW[3];
-            const long long ms1 = (long long)P.lvHp[1] * P.lvWp[1], ms2 = (long long)P.lvHp[2] * P.lvWp[2],
-                            ms3 = (long long)P.lvHp[3] * P.lvWp[3];
+            const long long ms1 = (long long)P.lvHp[1] * P.lvWp[1];
+            const long long ms2 = (long long)P.lvHp[2] * P.lvWp[2], ms3 = (long long)P.lvHp[3] * P.lvWp[3];
             float s2[32], s3[16];
             for (int t = 0; t < P.n_tiles; ++t) {
                 const int buf = t & 1;
@@ -318,9 +332,11 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         float v[32];
                         tmem_ld32(lane_addr + (uint32_t)(buf * 256 + c * 32), v);
                         tmem_ld_wait();
+                        if (do_scale) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= P.scale;
-                        store_chunk(P.lvl[0], P.NP, (long long)t * 2 * Wp + c * 32, 2 * Wp - c * 32, v);
+                            for (int j = 0; j < 32; ++j) v[j] *= P.scale;
+                        }
+                        store_l0(v, t * 2 * Wp + c * 32, 2 * Wp - c * 32);
 #pragma unroll
                         for (int pp = 0; pp < 2; ++pp)
 #pragma unroll
@@ -336,8 +352,8 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     if ((c & 3) == 3 && (c - 3) * 32 < 2 * Wp) {
                         const int g = c >> 2;                  // level-1 columns [32g, 32g + 32)
                         if (t < P.lvH[1])
-                            store_strided(P.lvl[1], ms1, (long long)(t >> 1) * 2 * P.lvWp[1] + g * 64 + (t & 1) * 8,
-                                          P.lvWp[1] - g * 32, l1);
+                            store_small(P.lvl[1], ms1, (long long)(t >> 1) * 2 * P.lvWp[1] + g * 64 + (t & 1) * 8,
+                                        P.lvWp[1] - g * 32, l1);
                         if (P.n_fused > 2) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
@@ -362,7 +378,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 if (P.n_fused > 2 && (t & 1)) {
                     const int y2 = t >> 1;
                     if (y2 < P.lvH[2])
-                        store_strided(P.lvl[2], ms2, (long long)(y2 >> 1) * 2 * P.lvWp[2] + (y2 & 1) * 8, P.lvWp[2], l2);
+                        store_small(P.lvl[2], ms2, (long long)(y2 >> 1) * 2 * P.lvWp[2] + (y2 & 1) * 8, P.lvWp[2], l2);
                     if (P.n_fused > 3) {
                         float l3[32];
 #pragma unroll
@@ -378,11 +394,13 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         }
                         const int y3 = t >> 2;
                         if ((y2 & 1) && y3 < P.lvH[3])
-                            store_strided(P.lvl[3], ms3, (long long)(y3 >> 1) * 2 * P.lvWp[3] + (y3 & 1) * 8, P.lvWp[3], l3);
+                            store_small(P.lvl[3], ms3, (long long)(y3 >> 1) * 2 * P.lvWp[3] + (y3 & 1) * 8, P.lvWp[3], l3);
                     }
                 }
             }
         }
+        if (lane == 0) tma_wait_group<0>();                    // staging is read and the stores have landed
+        __syncwarp();
     }
 
     tc_fence_before();
@@ -394,18 +412,33 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 }
 
 // ---------------------------------------------------------------- host side
-// 2-D bf16 row-major [rows][cols] tensor, box {64 cols, box_rows}, 128-byte swizzle
-static int make_map(CUtensorMap* map, const void* base, long long rows, int cols, int box_rows) {
+// 2-D bf16 row-major [rows][cols] tensor, box {box_cols, box_rows}; box_cols = 64 -> 128-byte
+// swizzle (query operand), 32 -> 64-byte swizzle (target operand stages)
+static int make_map(CUtensorMap* map, const void* base, long long rows, int cols, int box_rows, int box_cols) {
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FC_ECUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return FC_ECUDA; }
+    return FC_OK;
+}
+
+// fp32 tensor of `rank` dims (dim 0 contiguous): the epilogue's store boxes
+static int make_f32_map(CUtensorMap* map, float* base, int rank, const cuuint64_t* dims,
+                        const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FC_ECUDA; }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (store map, rank %d) failed (%d)", rank, (int)r); return FC_ECUDA; }
     return FC_OK;
 }
 
@@ -430,11 +463,11 @@ size_t tc_build_workspace_bytes(int B, int D, int H, int W, int, int) {
 }
 
 template <int KB>
-static int launch_tc(const CUtensorMap* maps, const TcParams& P, int B, cudaStream_t s) {
+static int launch_tc(const CUtensorMap* maps, const TcStoreMaps& SM, const TcParams& P, int B, cudaStream_t s) {
     const size_t smem = 1024 + 2 * KB * TC_ABLK_BYTES + TC_STAGES * TC_STAGE_BYTES + TC_STG_BYTES + 256;
     FC_CUDA(cudaFuncSetAttribute(tc_build_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(P.m_tiles, B);
-    tc_build_kernel<KB><<<grid, TC_THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], P);
+    tc_build_kernel<KB><<<grid, TC_THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], SM, P);
     FC_LAUNCH_CHECK("tc_build_kernel");
     return FC_OK;
 }
@@ -466,8 +499,12 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
         if (three) FC_CUDA(cudaMemsetAsync(b_lo, 0, (size_t)B * NP * D * 2, s));
     }
     dim3 pb(32, 8), pg((N + 31) / 32, (D + 63) / 64, B);
-    pack_bf16_kernel<<<pg, pb, 0, s>>>(f1, a_hi, three ? a_lo : nullptr, D, N, W, W, N, 0);
-    pack_bf16_kernel<<<pg, pb, 0, s>>>(f2, b_hi, three ? b_lo : nullptr, D, N, W, Wp, (int)NP, 1);
+    // 1/sqrt(D) is folded into the query operand when it is a power of two (D = 64, 256:
+    // exact, bit-identical to scaling the product); otherwise the epilogue multiplies
+    const float inv_sqrt_d = 1.0f / sqrtf((float)D);
+    const bool fold_scale = (D == 4 || D == 16 || D == 64 || D == 256);
+    pack_bf16_kernel<<<pg, pb, 0, s>>>(f1, a_hi, three ? a_lo : nullptr, D, N, W, W, N, 0, fold_scale ? inv_sqrt_d : 1.0f);
+    pack_bf16_kernel<<<pg, pb, 0, s>>>(f2, b_hi, three ? b_lo : nullptr, D, N, W, Wp, (int)NP, 1, 1.0f);
     FC_LAUNCH_CHECK("pack_bf16_kernel");
 
     TcParams P{};
@@ -485,26 +522,32 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     if (P.NT % 16 != 0) P.NT = round_up(P.NT, 16);     // single-row tile with Wp % 16 == 8: over-read 8 targets, masked at the store
     P.n_tiles = (int)((NP + P.NT - 1) / P.NT);
     P.m_tiles = (N + TC_BM - 1) / TC_BM;
-    P.sub1 = P.NT > TC_SUB ? P.NT - TC_SUB : 0;
     P.three_pass = three ? 1 : 0;
-    P.scale = 1.0f / sqrtf((float)D);
+    P.scale = fold_scale ? 1.0f : inv_sqrt_d;
 
-    CUtensorMap maps[6];
-    const int rows0 = P.NT < TC_SUB ? P.NT : TC_SUB;
-    const int rows1 = P.sub1 > 0 ? P.sub1 : 16;
-    if (int e = make_map(&maps[0], a_hi, (long long)B * N, D, TC_BM)) return e;
-    if (int e = make_map(&maps[1], three ? a_lo : a_hi, (long long)B * N, D, TC_BM)) return e;
-    if (int e = make_map(&maps[2], b_hi, (long long)B * NP, D, rows0)) return e;
-    if (int e = make_map(&maps[3], three ? b_lo : b_hi, (long long)B * NP, D, rows0)) return e;
-    if (int e = make_map(&maps[4], b_hi, (long long)B * NP, D, rows1)) return e;
-    if (int e = make_map(&maps[5], three ? b_lo : b_hi, (long long)B * NP, D, rows1)) return e;
+    CUtensorMap maps[4];
+    if (int e = make_map(&maps[0], a_hi, (long long)B * N, D, TC_BM, TC_BK)) return e;
+    if (int e = make_map(&maps[1], three ? a_lo : a_hi, (long long)B * N, D, TC_BM, TC_BK)) return e;
+    if (int e = make_map(&maps[2], b_hi, (long long)B * NP, D, P.NT, TC_BKS)) return e;
+    if (int e = make_map(&maps[3], three ? b_lo : b_hi, (long long)B * NP, D, P.NT, TC_BKS)) return e;
+
+    // store maps (see the epilogue)
+    TcStoreMaps SM;
+    {
+        float* l0 = static_cast<float*>(pyramid) + pyr.lv[0].offset;
+        cuuint64_t dims[3] = {(cuuint64_t)NP, (cuuint64_t)N, (cuuint64_t)B};
+        cuuint64_t str[2] = {(cuuint64_t)NP * 4, (cuuint64_t)N * NP * 4};
+        cuuint32_t box32[3] = {32, 32, 1}, box16[3] = {16, 32, 1};
+        if (int e = make_f32_map(&SM.l0_c32, l0, 3, dims, str, box32, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+        if (int e = make_f32_map(&SM.l0_c16, l0, 3, dims, str, box16, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    }
 
     int e;
     switch (D / 64) {
-        case 1: e = launch_tc<1>(maps, P, B, s); break;
-        case 2: e = launch_tc<2>(maps, P, B, s); break;
-        case 3: e = launch_tc<3>(maps, P, B, s); break;
-        default: e = launch_tc<4>(maps, P, B, s); break;
+        case 1: e = launch_tc<1>(maps, SM, P, B, s); break;
+        case 2: e = launch_tc<2>(maps, SM, P, B, s); break;
+        case 3: e = launch_tc<3>(maps, SM, P, B, s); break;
+        default: e = launch_tc<4>(maps, SM, P, B, s); break;
     }
     if (e) return e;
     // levels the epilogue wrote: their pad rows are not visited by the tile loop
