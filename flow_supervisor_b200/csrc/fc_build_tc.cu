@@ -31,9 +31,8 @@ int simt_zero_pad_rows(float* pyramid, const Pyramid& pyr, int first, int last, 
 constexpr int TC_THREADS = 192;
 constexpr int TC_BM = 128;           // queries per CTA (UMMA M)
 constexpr int TC_BK = 64;            // bf16 elements per 128-byte swizzle row
-constexpr int TC_BKS = 32;           // k elements per target-operand ring stage (64-byte swizzle rows)
 constexpr int TC_STAGES = 4;
-constexpr int TC_STAGE_BYTES = 256 * TC_BKS * 2;          // 16 KB: up to 256 target rows x 32 k
+constexpr int TC_STAGE_BYTES = 128 * TC_BK * 2;           // 16 KB: this CTA's half (<= 128 rows) of a target tile x 64 k
 constexpr int TC_ABLK_BYTES = TC_BM * TC_BK * 2;          // 16 KB per k-block of the query tile
 constexpr int TC_STG_FLOATS = 32 * 32;                    // one TMA-store box: [32 queries][32 floats] = 4 KB
 constexpr int TC_STG_BYTES = 4 * 2 * TC_STG_FLOATS * 4;   // 4 epilogue warps x 2 buffers = 32 KB
@@ -41,18 +40,47 @@ constexpr int TC_STG_BYTES = 4 * 2 * TC_STG_FLOATS * 4;   // 4 epilogue warps x 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem, 256 x N over the CTA pair] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]^T
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
         "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+// arrives (once the MMAs issued so far retire) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// TMA load into this CTA's shared memory whose bytes are accounted on the LEADER CTA's barrier
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared::cluster address (pair -> rank 0)
+__device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// arrive on the barrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    uint32_t addr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(addr) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(addr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -72,10 +100,6 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // start>>4 | LBO(1)<<16 | SBO(1024>>4)<<32 | version(1)<<46 | layout SWIZZLE_128B(2)<<61
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// same for 64-byte rows (SWIZZLE_64B): 8-row groups are 512 bytes apart, layout type 4
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
 }
 // instruction descriptor, kind::f16: D=F32 (bit 4), A=B=BF16 (bits 7, 10), K-major both,
 // N>>3 at bit 17, M>>4 at bit 24
@@ -131,12 +155,15 @@ struct TcParams {
     int NT;                // padded targets per tile (multiple of 16, <= 256)
     int n_tiles;           // ceil(NP / NT)
     int m_tiles;           // ceil(N / 128)
+    int mp;                // CTA pairs (256 query rows) per sample
+    int groups;            // groups of 4 consecutive target tiles per sample (the level-3 pooling period)
+    int units;             // B * mp * groups work units, split evenly over the resident CTA pairs
     int three_pass;        // 1 = hi*hi + lo*hi + hi*lo, 0 = hi*hi
     float scale;           // 1 / sqrt(D)
 };
 
 template <int KB>   // KB = D / 64 k-blocks
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                 const __grid_constant__ TcStoreMaps SM, const TcParams P) {
@@ -153,82 +180,121 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     uint64_t* b_empty = b_full + TC_STAGES;        // TC_STAGES
     uint64_t* t_full = b_empty + TC_STAGES;        // 2
     uint64_t* t_empty = t_full + 2;                // 2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    uint64_t* a_empty = t_empty + 2;               // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y, m0 = blockIdx.x * TC_BM;
     const int n_parts = P.three_pass ? 2 : 1;
+    // CTA pair: rank 0 (the leader) issues every MMA for both; each CTA owns 128 query rows and
+    // streams its half of every target tile.  Full barriers live in the leader; empty / tmem-full
+    // barriers are signalled in both CTAs by multicast commits.
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int half = P.NT / 2;                     // target rows of a tile held by each CTA
+
+    // Persistent schedule: work unit u = (sample, query pair-tile, group of 4 target tiles), units
+    // [u_begin, u_end) of this CTA pair are consecutive, so the resident query operand is
+    // reloaded only when (sample, pair-tile) changes.  All three roles walk the same sequence.
+    const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+    const int u_begin = (int)((long long)P.units * cluster_id / n_clusters);
+    const int u_end = (int)((long long)P.units * (cluster_id + 1) / n_clusters);
+    auto decode = [&](int u, int& b, int& m0, int& t0, int& t1) {
+        const int am = u / P.groups, g = u - am * P.groups;
+        b = am / P.mp;
+        m0 = ((am - b * P.mp) * 2 + (int)rank) * TC_BM;
+        t0 = 4 * g;
+        t1 = min(t0 + 4, P.n_tiles);
+    };
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }   // 4 epilogue warps x 2 CTAs
         mbar_fence_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer (both CTAs) =================
         if (lane == 0) {
-            mbar_expect_tx(a_full, (uint32_t)(n_parts * KB * TC_ABLK_BYTES));
-            for (int kb = 0; kb < KB; ++kb) {
-                tma_load_2d(a_hi + kb * TC_ABLK_BYTES, &map_a_hi, a_full, kb * TC_BK, b * P.N + m0);
-                if (P.three_pass) tma_load_2d(a_lo + kb * TC_ABLK_BYTES, &map_a_lo, a_full, kb * TC_BK, b * P.N + m0);
-            }
-            // target operand: stages of [NT rows][32 k], hi then lo of each k range
-            int it = 0;
-            for (int t = 0; t < P.n_tiles; ++t) {
-                const int row0 = b * P.NP + t * P.NT;
-                for (int i = 0; i < KB * (TC_BK / TC_BKS); ++i)
-                    for (int part = 0; part < n_parts; ++part, ++it) {
-                        const int s = it % TC_STAGES;
-                        const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
-                        mbar_wait(b_empty + s, ph ^ 1u);
-                        mbar_expect_tx(b_full + s, (uint32_t)(P.NT * TC_BKS * 2));
-                        tma_load_2d(ring + s * TC_STAGE_BYTES, part == 0 ? &map_b_hi : &map_b_lo, b_full + s,
-                                    i * TC_BKS, row0);
+            int it = 0, a_use = 0, cur_am = -1;
+            for (int u = u_begin; u < u_end; ++u) {
+                int b, m0, t0, t1;
+                decode(u, b, m0, t0, t1);
+                const int am = u / P.groups;
+                if (am != cur_am) {
+                    // query operand (resident): wait until the MMAs reading the old one have retired
+                    if (a_use > 0) mbar_wait(a_empty, (uint32_t)(a_use - 1) & 1u);
+                    if (leader) mbar_expect_tx(a_full, (uint32_t)(2 * n_parts * KB * TC_ABLK_BYTES));
+                    for (int kb = 0; kb < KB; ++kb) {
+                        tma2_load_2d(a_hi + kb * TC_ABLK_BYTES, &map_a_hi, a_full, kb * TC_BK, b * P.N + m0);
+                        if (P.three_pass) tma2_load_2d(a_lo + kb * TC_ABLK_BYTES, &map_a_lo, a_full, kb * TC_BK, b * P.N + m0);
                     }
+                    ++a_use; cur_am = am;
+                }
+                // target operand: stages of [NT/2 rows][64 k], hi then lo of each k-block
+                for (int t = t0; t < t1; ++t) {
+                    const int row0 = b * P.NP + t * P.NT + (int)rank * half;
+                    for (int kb = 0; kb < KB; ++kb)
+                        for (int part = 0; part < n_parts; ++part, ++it) {
+                            const int s = it % TC_STAGES;
+                            const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                            mbar_wait(b_empty + s, ph ^ 1u);
+                            if (leader) mbar_expect_tx(b_full + s, (uint32_t)(P.NT * TC_BK * 2));  // both halves
+                            tma2_load_2d(ring + s * TC_STAGE_BYTES, part == 0 ? &map_b_hi : &map_b_lo, b_full + s,
+                                         kb * TC_BK, row0);
+                        }
+                }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(TC_BM, P.NT);
-            mbar_wait(a_full, 0);
-            tc_fence_after();
-            int it = 0;
-            for (int t = 0; t < P.n_tiles; ++t) {
-                const int buf = t & 1;
-                mbar_wait(t_empty + buf, ((uint32_t)(t >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t d_addr = tmem_base + (uint32_t)(buf * 256);
-                for (int i = 0; i < KB * (TC_BK / TC_BKS); ++i)
-                    for (int part = 0; part < n_parts; ++part, ++it) {
-                        const int s = it % TC_STAGES;
-                        mbar_wait(b_full + s, (uint32_t)(it / TC_STAGES) & 1u);
-                        tc_fence_after();
-                        const uint32_t b_addr = smem_u32(ring + s * TC_STAGE_BYTES);
-                        // query operand: k-block i/2 of the resident SW128 tile, 64-byte half i%2
-                        const uint32_t a_off = (uint32_t)((i >> 1) * TC_ABLK_BYTES + (i & 1) * (TC_BKS * 2));
-                        const uint32_t ah_addr = smem_u32(a_hi) + a_off, al_addr = smem_u32(a_lo) + a_off;
+        // ================= MMA issuer (leader CTA only) =================
+        if (lane == 0 && leader) {
+            const uint32_t idesc = umma_idesc_bf16(2 * TC_BM, P.NT);
+            int it = 0, tc = 0, a_use = 0, cur_am = -1;
+            for (int u = u_begin; u < u_end; ++u) {
+                int b, m0, t0, t1;
+                decode(u, b, m0, t0, t1);
+                const int am = u / P.groups;
+                if (am != cur_am) {
+                    if (cur_am >= 0) umma2_commit(a_empty);    // old query operand is free once everything issued retires
+                    mbar_wait(a_full, (uint32_t)a_use & 1u);
+                    tc_fence_after();
+                    ++a_use; cur_am = am;
+                }
+                for (int t = t0; t < t1; ++t, ++tc) {
+                    const int buf = tc & 1;
+                    mbar_wait(t_empty + buf, ((uint32_t)(tc >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_addr = tmem_base + (uint32_t)(buf * 256);
+                    for (int kb = 0; kb < KB; ++kb)
+                        for (int part = 0; part < n_parts; ++part, ++it) {
+                            const int s = it % TC_STAGES;
+                            mbar_wait(b_full + s, (uint32_t)(it / TC_STAGES) & 1u);
+                            tc_fence_after();
+                            const uint32_t b_addr = smem_u32(ring + s * TC_STAGE_BYTES);
+                            const uint32_t ah_addr = smem_u32(a_hi + kb * TC_ABLK_BYTES);
+                            const uint32_t al_addr = smem_u32(a_lo + kb * TC_ABLK_BYTES);
 #pragma unroll
-                        for (int k = 0; k < TC_BKS / 16; ++k) {
-                            const uint64_t bd = umma_desc_sw64(b_addr + k * 32);
-                            // part 0: B = hi -> A_hi*B_hi (+ A_lo*B_hi); part 1: B = lo -> A_hi*B_lo
-                            umma_bf16(d_addr, umma_desc_sw128(ah_addr + k * 32), bd, idesc, (i | part | k) != 0 ? 1u : 0u);
-                            if (part == 0 && P.three_pass)
-                                umma_bf16(d_addr, umma_desc_sw128(al_addr + k * 32), bd, idesc, 1u);
+                            for (int k = 0; k < TC_BK / 16; ++k) {
+                                const uint64_t bd = umma_desc_sw128(b_addr + k * 32);
+                                // part 0: B = hi -> A_hi*B_hi (+ A_lo*B_hi); part 1: B = lo -> A_hi*B_lo
+                                umma2_bf16(d_addr, umma_desc_sw128(ah_addr + k * 32), bd, idesc, (kb | part | k) != 0 ? 1u : 0u);
+                                if (part == 0 && P.three_pass)
+                                    umma2_bf16(d_addr, umma_desc_sw128(al_addr + k * 32), bd, idesc, 1u);
+                            }
+                            umma2_commit(b_empty + s);         // frees the ring slot in both CTAs when these MMAs retire
                         }
-                        umma_commit(b_empty + s);              // frees the ring slot when these MMAs retire
-                    }
-                umma_commit(t_full + buf);                      // accumulator complete
+                    umma2_commit(t_full + buf);                // accumulator complete: both epilogues
+                }
             }
         }
     } else {
@@ -241,8 +307,8 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // the TMA unit.
         const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32)
         float* sbuf = stg + quarter * 2 * TC_STG_FLOATS;
-        const int row0 = m0 + quarter * 32;                    // first query row of this warp inside the sample
-        const int rows_valid = P.N - row0;
+        int b = 0, row0 = 0, rows_valid = 0;                   // sample, first query row of this warp inside it
+        int tc = 0;                                            // running tile count: accumulator buffer / phase
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         uint32_t use = 0;
 
@@ -289,9 +355,13 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const bool do_scale = P.scale != 1.0f;
 
         if (P.n_fused <= 1) {
-            for (int t = 0; t < P.n_tiles; ++t) {
-                const int buf = t & 1;
-                mbar_wait(t_full + buf, (uint32_t)(t >> 1) & 1u);
+            for (int u = u_begin; u < u_end; ++u) {
+              int m0, t0, t1;
+              decode(u, b, m0, t0, t1);
+              row0 = m0 + quarter * 32; rows_valid = P.N - row0;
+              for (int t = t0; t < t1; ++t, ++tc) {
+                const int buf = tc & 1;
+                mbar_wait(t_full + buf, (uint32_t)(tc >> 1) & 1u);
                 tc_fence_after();
                 const int q0 = t * P.NT;                       // first padded target of the tile
                 const int ncols = min(P.NT, P.NP - q0);
@@ -307,7 +377,8 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(t_empty + buf);
+                if (lane == 0) mbar_arrive_remote(t_empty + buf, 0);
+              }
             }
         } else {
             // Fused pyramid.  Tile t = row pair t of THIS thread's query map in patch order:
@@ -321,9 +392,13 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const long long ms1 = (long long)P.lvHp[1] * P.lvWp[1];
             const long long ms2 = (long long)P.lvHp[2] * P.lvWp[2], ms3 = (long long)P.lvHp[3] * P.lvWp[3];
             float s2[32], s3[16];
-            for (int t = 0; t < P.n_tiles; ++t) {
-                const int buf = t & 1;
-                mbar_wait(t_full + buf, (uint32_t)(t >> 1) & 1u);
+            for (int u = u_begin; u < u_end; ++u) {
+              int m0, t0, t1;
+              decode(u, b, m0, t0, t1);
+              row0 = m0 + quarter * 32; rows_valid = P.N - row0;
+              for (int t = t0; t < t1; ++t, ++tc) {
+                const int buf = tc & 1;
+                mbar_wait(t_full + buf, (uint32_t)(tc >> 1) & 1u);
                 tc_fence_after();
                 float l1[32], l2[32];
 #pragma unroll
@@ -373,7 +448,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 // all TMEM reads of this tile are done: hand the accumulator back early
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(t_empty + buf);
+                if (lane == 0) mbar_arrive_remote(t_empty + buf, 0);
 
                 if (P.n_fused > 2 && (t & 1)) {
                     const int y2 = t >> 1;
@@ -397,17 +472,19 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             store_small(P.lvl[3], ms3, (long long)(y3 >> 1) * 2 * P.lvWp[3] + (y3 & 1) * 8, P.lvWp[3], l3);
                     }
                 }
+              }
             }
         }
         if (lane == 0) tma_wait_group<0>();                    // staging is read and the stores have landed
         __syncwarp();
     }
 
+    // neither CTA may leave while its peer can still touch its barriers / tensor memory
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -466,7 +543,20 @@ template <int KB>
 static int launch_tc(const CUtensorMap* maps, const TcStoreMaps& SM, const TcParams& P, int B, cudaStream_t s) {
     const size_t smem = 1024 + 2 * KB * TC_ABLK_BYTES + TC_STAGES * TC_STAGE_BYTES + TC_STG_BYTES + 256;
     FC_CUDA(cudaFuncSetAttribute(tc_build_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(P.m_tiles, B);
+    // persistent: one CTA pair (cluster 2x1x1) per co-resident SM pair
+    int n_clusters = 0;
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        FC_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, tc_build_kernel<KB>, &cfg));
+    }
+    if (n_clusters < 1) { set_error("fc_build: no CTA pair of the tensor-core kernel fits on this device"); return FC_ECUDA; }
+    if (n_clusters > P.units) n_clusters = P.units;
+    dim3 grid(2 * n_clusters);
     tc_build_kernel<KB><<<grid, TC_THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], SM, P);
     FC_LAUNCH_CHECK("tc_build_kernel");
     return FC_OK;
@@ -522,14 +612,17 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     if (P.NT % 16 != 0) P.NT = round_up(P.NT, 16);     // single-row tile with Wp % 16 == 8: over-read 8 targets, masked at the store
     P.n_tiles = (int)((NP + P.NT - 1) / P.NT);
     P.m_tiles = (N + TC_BM - 1) / TC_BM;
+    P.mp = (P.m_tiles + 1) / 2;
+    P.groups = (P.n_tiles + 3) / 4;
+    P.units = B * P.mp * P.groups;
     P.three_pass = three ? 1 : 0;
     P.scale = fold_scale ? 1.0f : inv_sqrt_d;
 
     CUtensorMap maps[4];
     if (int e = make_map(&maps[0], a_hi, (long long)B * N, D, TC_BM, TC_BK)) return e;
     if (int e = make_map(&maps[1], three ? a_lo : a_hi, (long long)B * N, D, TC_BM, TC_BK)) return e;
-    if (int e = make_map(&maps[2], b_hi, (long long)B * NP, D, P.NT, TC_BKS)) return e;
-    if (int e = make_map(&maps[3], three ? b_lo : b_hi, (long long)B * NP, D, P.NT, TC_BKS)) return e;
+    if (int e = make_map(&maps[2], b_hi, (long long)B * NP, D, P.NT / 2, TC_BK)) return e;
+    if (int e = make_map(&maps[3], three ? b_lo : b_hi, (long long)B * NP, D, P.NT / 2, TC_BK)) return e;
 
     // store maps (see the epilogue)
     TcStoreMaps SM;
