@@ -93,49 +93,74 @@ def inbounds_footprint(coords, H, W):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed regions by a thread polling
+    NVML (~2 ms period; nvidia-smi takes longer to start than a whole timed region)."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.proc, self.path = index, None, None
-
-    def start(self):
+        import threading
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop, self._on = threading.Event(), threading.Event()
+        self._thread, self.err = None, None
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES if it is a plain list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except (ValueError, IndexError):
+                    phys = index
+            self._nv, self._h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        except Exception as e:                      # noqa: BLE001
+            self.err = f"nvml unavailable: {e}"
+
+    def _run(self):
+        nv, h = self._nv, self._h
+        while not self._stop.is_set():
+            if self._on.is_set():
+                try:
+                    mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    self.samples.append(mhz)
+                    for name, bit in self.BAD.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception as e:              # noqa: BLE001
+                    self.err = str(e)
+            time.sleep(0.002)
+
+    def resume(self):
+        self._on.set()
+
+    def pause(self):
+        self._on.clear()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            p = [x.strip() for x in line.split(",")]
-            if len(p) < 9:
-                continue
-            try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, p[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        os.unlink(self.path)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        sm = sorted(self.samples)
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+               "samples": len(sm), "reasons": sorted(self.reasons)}
+        if self.err and not sm:
+            out["reasons"] = [self.err]
+        return out
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read + dram__bytes_write per launch from the committed ncu capture
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py traffic) or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def peaks():
@@ -255,9 +280,10 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(local) if rank == 0 else None
+    lib = _lib.load()
+    if sampler: sampler.resume()
+    launches0 = lib.fc_kernel_launches()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
     t_start.record()
@@ -266,7 +292,8 @@ def main():
     t_end.record()
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.fc_kernel_launches() - launches0
+    if sampler: sampler.pause()
     elapsed_ms = t_start.elapsed_time(t_end)
     build_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
     look_ms = sum(e[t + 1].elapsed_time(e[t + 2]) for e in ev for t in range(iters)) / (args.steps * iters)
@@ -288,12 +315,14 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_e2e = max(3, min(args.steps, 10))
+    if sampler: sampler.resume()
     e0.record()
     for _ in range(n_e2e):
         step_e2e()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / n_e2e
+    clocks = sampler.stop() if sampler else None
 
     # ---- max over ranks
     t = torch.tensor([elapsed_ms, e2e_ms, build_ms, look_ms], device="cuda", dtype=torch.float64)
@@ -307,7 +336,7 @@ def main():
         value = world * B * args.steps / (elapsed_ms * 1e-3)
         lb = lookup_bytes(B, H, W, foot)
         look = {"kernel": "lookup_fwd_kernel", "bound": "hbm", "achieved": lb / (look_ms * 1e-3) / 1e9,
-                "peak": hbm, "unit": "GB/s", "traffic": None, "peak_source": peak_src,
+                "peak": hbm, "unit": "GB/s", "traffic": ncu_traffic("lookup_fwd_kernel"), "peak_source": peak_src,
                 "bytes_per_launch": lb, "bytes_nominal": lookup_bytes(B, H, W), "ms_per_launch": look_ms,
                 "share_of_step": iters * look_ms / ms_step}
         look["frac"] = look["achieved"] / hbm
@@ -316,7 +345,8 @@ def main():
         pyr_bytes, _ = _lib.pyramid_layout(B, H, W, LEVELS, _lib.VOL_F32)
         bld = {"kernel": "build (gemm + pyramid)", "bound": "tensor" if math_id else "fp32-simt",
                "achieved": flop / (build_ms * 1e-3) / 1e12, "peak": tf_sust, "unit": "TFLOP/s",
-               "traffic": None, "peak_source": peak_src, "flop_per_launch": flop,
+               "traffic": ncu_traffic("tc_build_kernel") if math_id else None, "peak_source": peak_src,
+               "flop_per_launch": flop, "flop_issued": flop * (3 if math_id == 1 else 1),
                "hbm_bytes_per_launch": pyr_bytes + 2 * B * DIM * N * 4,
                "hbm_gbs": (pyr_bytes + 2 * B * DIM * N * 4) / (build_ms * 1e-3) / 1e9,
                "ms_per_launch": build_ms, "share_of_step": build_ms / ms_step}
@@ -337,7 +367,7 @@ def main():
             "roofline": dominant, "roofline_other": other,
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps * (iters + (4 if math_id == 0 else 2)),
+            "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:

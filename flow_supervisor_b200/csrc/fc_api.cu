@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cmath>
+#include <atomic>
 
 #include "fc_tma.cuh"
 
@@ -16,6 +17,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error in %s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
@@ -54,6 +58,8 @@ using namespace fc;
 extern "C" int fc_abi_version(void) { return FC_ABI_VERSION; }
 
 extern "C" const char* fc_last_error(void) { return g_err; }
+
+extern "C" unsigned long long fc_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int fc_level_dims(int H, int W, int level, int* Hl, int* Wl, int* Wp) {
     FC_REQUIRE(H > 0 && W > 0 && level >= 0 && level < FC_MAX_LEVELS, "fc_level_dims: bad arguments");

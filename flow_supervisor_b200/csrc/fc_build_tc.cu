@@ -594,6 +594,7 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     const float inv_sqrt_d = 1.0f / sqrtf((float)D);
     const bool fold_scale = (D == 4 || D == 16 || D == 64 || D == 256);
     pack_bf16_kernel<<<pg, pb, 0, s>>>(f1, a_hi, three ? a_lo : nullptr, D, N, W, W, N, 0, fold_scale ? inv_sqrt_d : 1.0f);
+    FC_LAUNCH_CHECK("pack_bf16_kernel");
     pack_bf16_kernel<<<pg, pb, 0, s>>>(f2, b_hi, three ? b_lo : nullptr, D, N, W, Wp, (int)NP, 1, 1.0f);
     FC_LAUNCH_CHECK("pack_bf16_kernel");
 

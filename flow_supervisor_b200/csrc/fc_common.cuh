@@ -13,6 +13,7 @@ namespace fc {
 // ---------------------------------------------------------------- error plumbing
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void count_launch();          // fc_kernel_launches() instrumentation
 
 #define FC_REQUIRE(cond, ...)                 \
     do {                                      \
@@ -30,6 +31,7 @@ int cuda_fail(cudaError_t e, const char* what);
 
 #define FC_LAUNCH_CHECK(name)                                 \
     do {                                                      \
+        fc::count_launch();                                   \
         cudaError_t e__ = cudaPeekAtLastError();              \
         if (e__ != cudaSuccess) return fc::cuda_fail(e__, name); \
     } while (0)

@@ -65,6 +65,10 @@ extern "C" {
 int fc_abi_version(void);
 const char* fc_last_error(void);
 
+/* Number of CUDA kernels this library has launched in the calling process so far
+ * (monotonic; instrumentation for benchmarks: bench.py's gpu_launches). */
+unsigned long long fc_kernel_launches(void);
+
 /* Geometry of level `level` for an H x W (1/8-resolution) token grid.
  * Replaces: the implicit shapes of corr.py:24-27 (F.avg_pool2d(corr, 2, stride=2)). */
 int fc_level_dims(int H, int W, int level, int* Hl, int* Wl, int* Wp);

@@ -14,7 +14,7 @@ HEADER = os.path.join(ROOT, "include", "flowcorr.h")
 def header_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    decls = re.findall(r"\b(?:int|size_t|const char\s*\*)\s+(fc_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+    decls = re.findall(r"\b(?:int|size_t|unsigned long long|const char\s*\*)\s+(fc_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
     out = {}
     for name, args in decls:
         args = args.strip()

@@ -51,5 +51,27 @@ def full(path):
                 print(f"  {k:78s} {r[i]:>16s} {units[i]}")
 
 
+def traffic(path):
+    """Merge dram bytes per launch of every kernel captured in <report> into
+    profiles/ncu_traffic.json (read by bench.py for roofline.traffic)."""
+    import json, os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    db = json.load(open(dst)) if os.path.exists(dst) else {}
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0]
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(k)
+            tot += float(r[i].replace(",", "")) * scale[units[i]]
+        db[name] = {"dram_bytes_per_launch": tot, "gpu_time_us": float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")),
+                    "report": os.path.basename(path)}
+    json.dump(db, open(dst, "w"), indent=1, sort_keys=True)
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
