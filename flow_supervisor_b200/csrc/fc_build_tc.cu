@@ -108,34 +108,67 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
 }
 
 // ---------------------------------------------------------------- pack pre-pass
-// src (B, D, N) fp32 -> hi/lo [b*rows_per_sample + row(n)][D] bf16,
-// row(n) = n (tiled == 0) or tile_off(n / W, n % W, Wp) (tiled == 1: target operand)
-__global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
-                                 __nv_bfloat16* __restrict__ lo, int D, int N, int W, int Wp,
-                                 int rows_per_sample, int tiled, float prescale) {
-    __shared__ float tile[64][33];
-    const int b = blockIdx.z, n0 = blockIdx.x * 32, d0 = blockIdx.y * 64;
-    const int tx = threadIdx.x, ty = threadIdx.y;            // 32 x 8
-    const float* s = src + (long long)b * D * N;
+// One launch for both operands (blockIdx.z = 2*b + which):
+//   which 0: fmap1 (B, D, N) fp32 -> rows p = query,              hi/lo [b*N  + p ][D] bf16, scaled by `prescale`
+//   which 1: fmap2 (B, D, N) fp32 -> rows q' = PADDED target in patch order (tile_inv),
+//                                                                 hi/lo [b*NP + q'][D] bf16; pad rows are zeros
+// hi = bf16(x), lo = bf16(x - hi).
+struct PackParams {
+    const float* src[2];
+    __nv_bfloat16* hi[2];
+    __nv_bfloat16* lo[2];      // nullptr: single-pass bf16 mode
+    int D, N, NP, H, W, Wp;
+    float prescale;
+};
+
+__global__ void __launch_bounds__(256) pack_bf16_kernel(const PackParams P) {
+    // lane <-> token (coalesced 128-byte reads per channel), warp <-> 16 consecutive channels:
+    // every thread writes one full 32-byte sector of its row in hi and in lo
+    const int which = blockIdx.z & 1, b = blockIdx.z >> 1;
+    const int rows = which ? P.NP : P.N;                     // rows per sample of the packed operand
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + lane;
+    const int d0 = (blockIdx.y * 8 + warp) * 16;
+    const float* __restrict__ s = P.src[which] + (long long)b * P.D * P.N;
+    __nv_bfloat16* __restrict__ hi = P.hi[which];
+    __nv_bfloat16* __restrict__ lo = P.lo[which];
+    const float scale = which ? 1.0f : P.prescale;
+    if (n < P.N && d0 < P.D) {
+        float x[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int d = d0 + ty + 8 * i, n = n0 + tx;
-        tile[ty + 8 * i][tx] = (d < D && n < N) ? s[(long long)d * N + n] : 0.f;
+        for (int i = 0; i < 16; ++i) x[i] = __ldg(s + (long long)(d0 + i) * P.N + n) * scale;
+        uint32_t h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+            const __nv_bfloat162 hh(h0, h1);
+            const __nv_bfloat162 ll(__float2bfloat16_rn(x[2 * i] - __bfloat162float(h0)),
+                                    __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1)));
+            h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+            l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        const int row = which ? tile_off(n / P.W, n % P.W, P.Wp) : n;
+        const long long o = ((long long)b * rows + row) * P.D + d0;
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(hi + o), "r"(h[0]), "r"(h[1]),
+                     "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+        if (lo != nullptr)
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(lo + o), "r"(l[0]), "r"(l[1]),
+                         "r"(l[2]), "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]) : "memory");
     }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int nl = ty + 8 * i, n = n0 + nl;
-        const int d = d0 + 2 * tx;
-        if (n < N && d < D) {
-            const int row = tiled ? tile_off(n / W, n % W, Wp) : n;
-            const float x0 = tile[2 * tx][nl] * prescale, x1 = tile[2 * tx + 1][nl] * prescale;
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-            const long long o = ((long long)b * rows_per_sample + row) * D + d;
-            *reinterpret_cast<__nv_bfloat162*>(hi + o) = __nv_bfloat162(h0, h1);
-            if (lo != nullptr)
-                *reinterpret_cast<__nv_bfloat162*>(lo + o) = __nv_bfloat162(
-                    __float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+    // pad rows of the target operand (y >= H or x >= W in patch order) hold zeros; block x scans
+    // its share [x * span, (x + 1) * span) of the padded index space
+    if (which && P.NP > P.N && d0 < P.D) {
+        const int span = (P.NP + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int q_end = min((int)(blockIdx.x + 1) * span, P.NP);
+        for (int q = blockIdx.x * span + lane; q < q_end; q += 32) {
+            int y, x;
+            tile_inv(q, P.Wp, y, x);
+            if (y >= P.H || x >= P.W) {
+                const long long o = ((long long)b * rows + q) * P.D + d0;
+                asm volatile("st.global.v8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};\n" ::"l"(hi + o), "r"(0u) : "memory");
+                if (lo != nullptr)
+                    asm volatile("st.global.v8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};\n" ::"l"(lo + o), "r"(0u) : "memory");
+            }
         }
     }
 }
@@ -472,6 +505,20 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             store_small(P.lvl[3], ms3, (long long)(y3 >> 1) * 2 * P.lvWp[3] + (y3 & 1) * 8, P.lvWp[3], l3);
                     }
                 }
+                if (t == P.n_tiles - 1) {
+                    // pad row (y = Hl, Hl odd) of every pooled level: the lookup's TMA boxes read whole
+                    // row pairs, so it must hold zeros (the tile loop itself never produces it)
+                    float z[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) z[j] = 0.f;
+                    for (int l = 1; l < P.n_fused; ++l)
+                        if (P.lvHp[l] > P.lvH[l]) {
+                            const int y = P.lvH[l], wp = P.lvWp[l];
+                            for (int g = 0; g * 32 < wp; ++g)
+                                store_small(P.lvl[l], (long long)P.lvHp[l] * wp,
+                                            (long long)(y >> 1) * 2 * wp + g * 64 + (y & 1) * 8, wp - g * 32, z);
+                        }
+                }
               }
             }
         }
@@ -584,19 +631,22 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     const int N = pyr.N;
     const long long NP = L.NP;
 
-    if (Wp != W || pyr.lv[0].Hp != H) {   // pad rows of the target operand must be zero
-        FC_CUDA(cudaMemsetAsync(b_hi, 0, (size_t)B * NP * D * 2, s));
-        if (three) FC_CUDA(cudaMemsetAsync(b_lo, 0, (size_t)B * NP * D * 2, s));
-    }
-    dim3 pb(32, 8), pg((N + 31) / 32, (D + 63) / 64, B);
     // 1/sqrt(D) is folded into the query operand when it is a power of two (D = 64, 256:
     // exact, bit-identical to scaling the product); otherwise the epilogue multiplies
     const float inv_sqrt_d = 1.0f / sqrtf((float)D);
     const bool fold_scale = (D == 4 || D == 16 || D == 64 || D == 256);
-    pack_bf16_kernel<<<pg, pb, 0, s>>>(f1, a_hi, three ? a_lo : nullptr, D, N, W, W, N, 0, fold_scale ? inv_sqrt_d : 1.0f);
-    FC_LAUNCH_CHECK("pack_bf16_kernel");
-    pack_bf16_kernel<<<pg, pb, 0, s>>>(f2, b_hi, three ? b_lo : nullptr, D, N, W, Wp, (int)NP, 1, 1.0f);
-    FC_LAUNCH_CHECK("pack_bf16_kernel");
+    {
+        PackParams K{};
+        K.src[0] = f1; K.src[1] = f2;
+        K.hi[0] = a_hi; K.hi[1] = b_hi;
+        K.lo[0] = three ? a_lo : nullptr; K.lo[1] = three ? b_lo : nullptr;
+        K.D = D; K.N = N; K.NP = (int)NP; K.H = H; K.W = W; K.Wp = Wp;
+        K.prescale = fold_scale ? inv_sqrt_d : 1.0f;
+        // (D % 64 == 0 is required above, so channel chunks of 16 never straddle D)
+        dim3 pb(256), pg((unsigned)((N + 31) / 32), (unsigned)((D + 127) / 128), 2 * B);
+        pack_bf16_kernel<<<pg, pb, 0, s>>>(K);
+        FC_LAUNCH_CHECK("pack_bf16_kernel");
+    }
 
     TcParams P{};
     P.vol0 = static_cast<float*>(pyramid) + pyr.lv[0].offset;
@@ -644,9 +694,6 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
         default: e = launch_tc<4>(maps, SM, P, B, s); break;
     }
     if (e) return e;
-    // levels the epilogue wrote: their pad rows are not visited by the tile loop
-    if (P.n_fused > 1)
-        if (int e2 = simt_zero_pad_rows(static_cast<float*>(pyramid), pyr, 1, P.n_fused - 1, s)) return e2;
     return simt_pool_levels(static_cast<float*>(pyramid), pyr, P.n_fused, s);
 }
 

@@ -96,7 +96,10 @@ def test_training_step_gradients_through_the_gru(env):
         grads[name] = {k: p.grad.detach().clone() for k, p in model.fnet.named_parameters() if p.grad is not None}
     model.zero_grad(set_to_none=True)
     assert grads["ours"].keys() == grads["ref"].keys() and len(grads["ref"]) > 0
+    gmax = max(float(g.abs().max()) for g in grads["ref"].values())
     for k, gr in grads["ref"].items():
         go = grads["ours"][k]
-        denom = float(gr.abs().max()) + 1e-12
+        # biases in front of an instance norm have mathematically zero gradient (1e-8 noise):
+        # scale every comparison by at least 1e-3 of the largest gradient in the encoder
+        denom = max(float(gr.abs().max()), 1e-3 * gmax)
         assert float((go - gr).abs().max()) / denom <= 2e-3, (k, float((go - gr).abs().max()) / denom)
