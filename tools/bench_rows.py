@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""Per-row timings of SURVEY.md section 8 that bench.py's headline line does not carry:
+
+  a6  lookup backward (scatter-add) and build backward (fold + two GEMMs) at config 3
+      (368x768 crops, batch 6 -> 46x96 tokens; teacher frame 432x1024 -> 54x128)
+  a7  on-demand lookup (AlternateCorrBlock) at config 5 (1088x1920 -> 136x240, batch 2),
+      next to the reference's own CUDA kernel (oracle/_ref, when built) driven with the
+      reference's call pattern (corr.py:74-91)
+  a8/a9  alt_cuda_corr forward / backward, one level, same geometry, vs the compiled reference
+
+Each line states the algorithmic work, the measured time (CUDA events on the
+launching stream, warm, mean over reps) and the fraction of the bounding roofline
+(MEASURED_PEAKS.json).  Auxiliary measurement: one JSON line per row on stdout.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import flow_supervisor_b200 as fsb              # noqa: E402
+from flow_supervisor_b200 import _lib, ops      # noqa: E402
+
+L, R, D = 4, 4, 256
+K = L * (2 * R + 1) ** 2
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return p["hbm_gbs"], p["bf16_tflops_sustained"]
+    except Exception:
+        return 6650.0, 1400.0
+
+
+def timed(fn, reps, warm=3, setup=None):
+    for _ in range(warm):
+        if setup: setup()
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(reps):
+        if setup: setup()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
+def inbounds_footprint(c, H, W):
+    tot = 0.0
+    for l in range(L):
+        Hl, Wl = H >> l, W >> l
+        x0 = torch.floor(c[:, 0] / 2 ** l) - R
+        y0 = torch.floor(c[:, 1] / 2 ** l) - R
+        nx = (torch.clamp(x0 + 2 * R + 2, max=Wl) - torch.clamp(x0, min=0)).clamp(min=0)
+        ny = (torch.clamp(y0 + 2 * R + 2, max=Hl) - torch.clamp(y0, min=0)).clamp(min=0)
+        tot += float((nx * ny).mean())
+    return tot
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def row_backward(B, H, W, reps):
+    hbm, tf = peaks()
+    g = torch.Generator().manual_seed(0)
+    f1 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
+    f2 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
+    c = (fsb.coords_grid(B, H, W) + 5.0 * torch.randn(B, 2, H, W, generator=g)).cuda()
+    gout = torch.randn(B, K, H, W, generator=g).cuda()
+    N, Q = H * W, B * H * W
+    numel = ops.pyramid_numel(B, H, W, L)
+    gp = torch.zeros(numel, device="cuda")
+    foot = inbounds_footprint(c.cpu(), H, W)
+    ms = timed(lambda: ops.lookup_bwd(gout, c, gp, L, R, _lib.COORD_CUDA), reps)
+    byts = Q * (K * 4 + 2 * foot * 4 + 8)
+    emit(row="a6 lookup_bwd", geometry=f"B={B} {H}x{W}", ms=ms, bytes_algorithmic=byts,
+         gbs=byts / ms / 1e6, bound="hbm", peak=hbm, frac=byts / ms / 1e6 / hbm,
+         note="per launch: grad read + footprint read-modify-write (in-bounds discounted) + coords")
+    for math_name, math in (("fp32", _lib.MATH_FP32), ("3xbf16", _lib.MATH_TC_3XBF16)):
+        def setup():
+            gp.normal_()
+        try:
+            ms = timed(lambda: ops.build_bwd(gp, f1, f2, L, math), reps, setup=setup)
+        except RuntimeError as e:
+            emit(row="a6 build_bwd", math=math_name, error=str(e)); continue
+        flop = 2 * 2.0 * B * N * N * D
+        byts = numel * 4 + 4 * B * D * N * 4
+        emit(row="a6 build_bwd (fold + dF1 + dF2)", math=math_name, geometry=f"B={B} {H}x{W}", ms=ms,
+             gflop=flop / 1e9, tflops=flop / ms / 1e9, bytes_algorithmic=byts, gbs=byts / ms / 1e6,
+             bound="tensor", peak=tf, frac=flop / ms / 1e9 / tf,
+             hbm_floor_ms=byts / hbm / 1e6, tensor_floor_ms=flop / tf / 1e9)
+
+
+def row_ondemand(B, H, W, reps):
+    hbm, tf = peaks()
+    g = torch.Generator().manual_seed(1)
+    f1 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
+    f2 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
+    c = (fsb.coords_grid(B, H, W) + 8.0 * torch.randn(B, 2, H, W, generator=g)).cuda()
+    Q = B * H * W
+    ms_prep = timed(lambda: fsb.AlternateCorrBlock(f1, f2, L, R), reps)
+    blk = fsb.AlternateCorrBlock(f1, f2, L, R)
+    ms = timed(lambda: blk(c), reps)
+    flop = Q * L * (2 * R + 2) ** 2 * 2.0 * D
+    byts = Q * (D * 4 + K * 4 + 8) + sum(B * (H >> l) * (W >> l) * D * 4 for l in range(L))
+    line = dict(row="a7 ondemand_fwd (4 levels, one launch)", geometry=f"B={B} {H}x{W}", ms=ms, prepare_ms=ms_prep,
+                gflop=flop / 1e9, tflops=flop / ms / 1e9, bytes_algorithmic=byts, hbm_floor_ms=byts / hbm / 1e6,
+                query_lookups_per_s=Q / ms * 1e3)
+    try:
+        from oracle import ref_ext
+        if ref_ext.available():
+            rblk = ref_ext.RefAlternateCorrBlock(f1, f2, L, R)
+            want = rblk(c)
+            got = blk(c)
+            line["max_rel_diff_vs_reference_kernel"] = float((got - want).abs().max() / want.abs().max())
+            line["reference_kernel_ms"] = timed(lambda: rblk(c), max(2, reps // 3), warm=1)
+            line["speedup_vs_reference_kernel"] = line["reference_kernel_ms"] / ms
+            # single level, raw extension signature (rows a8 / a9)
+            from flow_supervisor_b200 import alt_cuda_corr as shim
+            mod = ref_ext.load()
+            n1, n2 = rblk.q_nhwc, rblk.t_nhwc[0]
+            cc = c.permute(0, 2, 3, 1).reshape(B, 1, H, W, 2).contiguous()
+            gg = torch.randn(B, 1, 81, H, W, generator=g).cuda()
+            a8 = timed(lambda: shim.forward(n1, n2, cc, R), reps)
+            a8r = timed(lambda: mod.forward(n1, n2, cc, R), max(2, reps // 3), warm=1)
+            a9 = timed(lambda: shim.backward(n1, n2, cc, gg, R), reps)
+            a9r = timed(lambda: mod.backward(n1, n2, cc, gg, R), max(2, reps // 3), warm=1)
+            emit(row="a8 altcorr_fwd (level 0)", geometry=f"B={B} {H}x{W}", ms=a8, reference_kernel_ms=a8r, speedup=a8r / a8)
+            emit(row="a9 altcorr_bwd (level 0)", geometry=f"B={B} {H}x{W}", ms=a9, reference_kernel_ms=a9r, speedup=a9r / a9)
+        else:
+            line["reference_kernel_ms"] = None
+    except Exception as e:                                    # noqa: BLE001
+        line["reference_kernel_error"] = repr(e)
+    emit(**line)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--rows", default="bwd,ondemand")
+    a = ap.parse_args()
+    if "bwd" in a.rows:
+        row_backward(6, 46, 96, a.reps)
+        row_backward(6, 54, 128, a.reps)
+    if "ondemand" in a.rows:
+        row_ondemand(2, 136, 240, a.reps)
