@@ -33,6 +33,7 @@ SIGNATURES = {
     "fc_build": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
     "fc_lookup_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "fc_lookup_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "fc_build_bwd_workspace_bytes": (_z, [_i, _i, _i, _i, _i, _i]),
     "fc_build_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
     "fc_ondemand_workspace_bytes": (_z, [_i, _i, _i, _i, _i]),
     "fc_ondemand_prepare": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _z, _p]),

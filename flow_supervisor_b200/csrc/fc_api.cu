@@ -37,6 +37,12 @@ size_t tc_build_workspace_bytes(int B, int D, int H, int W, int L, int math);
 int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr, int D, int H, int W,
              int vol_dtype, int math, void* ws, size_t ws_bytes, cudaStream_t s);
 
+// fc_bwd_tc.cu
+bool tc_bwd_supported(int D, int H, int W);
+size_t tc_bwd_workspace_bytes(int B, int D, int H, int W);
+int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float* d2, const Pyramid& pyr,
+                 int D, int H, int W, int math, void* ws, size_t ws_bytes, cudaStream_t s);
+
 EncodeTiledFn tensor_map_encoder() {
     static EncodeTiledFn fn = []() -> EncodeTiledFn {
         void* p = nullptr;
@@ -107,18 +113,28 @@ extern "C" int fc_build(const float* fmap1, const float* fmap2, void* pyramid,
     return tc_build(fmap1, fmap2, pyramid, pyr, D, H, W, vol_dtype, math, workspace, workspace_bytes, s);
 }
 
+extern "C" size_t fc_build_bwd_workspace_bytes(int B, int D, int H, int W, int num_levels, int math) {
+    (void)num_levels;
+    if (math == FC_MATH_FP32) return 0;
+    return tc_bwd_workspace_bytes(B, D, H, W);        // 0: this shape runs the fp32 CUDA-core contractions
+}
+
 extern "C" int fc_build_bwd(float* grad_pyramid, const float* fmap1, const float* fmap2,
                             float* dfmap1, float* dfmap2,
                             int B, int D, int H, int W, int num_levels, int math,
                             void* workspace, size_t workspace_bytes, void* stream) {
-    (void)workspace; (void)workspace_bytes;
     FC_REQUIRE(grad_pyramid && fmap1 && fmap2, "fc_build_bwd: null pointer");
+    FC_REQUIRE(aligned16(grad_pyramid) && aligned16(fmap1) && aligned16(fmap2) && aligned16(dfmap1) && aligned16(dfmap2),
+               "fc_build_bwd: pointers must be 16-byte aligned");
     Pyramid pyr;
     FC_REQUIRE(make_pyramid(pyr, B, H, W, num_levels), "fc_build_bwd: bad geometry B=%d H=%d W=%d L=%d", B, H, W, num_levels);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     FC_REQUIRE(math == FC_MATH_FP32 || math == FC_MATH_TC_3XBF16 || math == FC_MATH_TC_BF16,
                "fc_build_bwd: unknown math mode %d", math);
+    // tensor-core modes: fused fold + bf16 split in place, then two tcgen05 GEMMs; shapes the
+    // tensor-core kernel does not take (fc_build_bwd_workspace_bytes == 0) run the fp32 mode
+    if (math != FC_MATH_FP32 && tc_bwd_supported(D, H, W))
+        return tc_build_bwd(grad_pyramid, fmap1, fmap2, dfmap1, dfmap2, pyr, D, H, W, math, workspace, workspace_bytes, s);
     if (int e = simt_fold(grad_pyramid, pyr, s)) return e;
-    // gradient contractions currently always run in fp32 on the CUDA cores
     return simt_build_bwd(grad_pyramid, fmap1, fmap2, dfmap1, dfmap2, pyr, D, H, W, s);
 }

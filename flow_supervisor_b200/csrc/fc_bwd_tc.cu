@@ -1,0 +1,492 @@
+// Tensor-core backward of CorrBlock.__init__ (autograd of corr.py:21-27,52-60; driven by
+// pytorch/train.py:273,277) for sm_100a:
+//
+//   dC = fold(G) / sqrt(D);   dfmap1[b,:,p] = sum_q dC[b,p,q] fmap2[b,:,q];
+//                             dfmap2[b,:,q] = sum_p dC[b,p,q] fmap1[b,:,p]
+//
+//   fold + pack   : ONE pass over the gradient pyramid.  A CTA owns one query row: it folds the
+//                   coarse levels into level 0 on the fly (avg_pool2d backward: every parent
+//                   gives a quarter to its 4 children, coarsest level first -- same arithmetic
+//                   as fold_level_kernel) and rewrites the row IN PLACE as two bf16 planes
+//                   hi = bf16(g), lo = bf16(g - hi): bytes [0, 2 NP) and [2 NP, 4 NP) of the
+//                   row's 4 NP bytes.  No extra volume-sized buffer exists.
+//   feature pack  : fmap1 -> bf16 hi/lo [b][d][p], fmap2 -> bf16 hi/lo [b][d][q'] with q' the
+//                   padded patch-ordered target index (zeros on pads), both contraction-major.
+//   two GEMMs     : persistent CTA pairs, tcgen05.mma.cta_group::2 (M = 256 rows per pair,
+//                   N = D, fp32 accumulators in TMEM), 3-stage TMA ring, 3 MMAs per k-step in
+//                   FC_MATH_TC_3XBF16 (hi*hi + lo*hi + hi*lo), split-K over work units with
+//                   red.global.add.f32 into the zero-initialised outputs.
+//       dF1: rows = queries p,  k = q' : the G planes are K-major operands.
+//       dF2: rows = targets q', k = p  : the SAME G planes read as MN-major operands (the TMA
+//            box is 64 q' x 64 p, the UMMA descriptor says "M-contiguous") -- no transposed copy.
+//
+// Warp roles as in fc_build_tc.cu: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// issuer (leader CTA), warps 2-5 = epilogue.
+#include "fc_umma.cuh"
+
+namespace fc {
+
+constexpr int BW_THREADS = 192;
+constexpr int BW_BM = 128;                                  // rows per CTA (UMMA M = 256 per pair)
+constexpr int BW_BK = 64;                                   // bf16 per 128-byte swizzle row
+constexpr int BW_STAGES = 3;
+constexpr int BW_PART_BYTES = 128 * BW_BK * 2;              // 16 KB: one operand part (<= 128 rows x 64 k)
+constexpr int BW_STAGE_BYTES = 4 * BW_PART_BYTES;           // A_hi, A_lo, B_hi, B_lo
+constexpr int BW_MAX_CHUNKS = 8;                            // fold+pack: 8-element chunks per thread (NP <= 16384)
+
+enum { BW_DF1 = 0, BW_DF2 = 1 };
+
+// ---------------------------------------------------------------- PTX
+__device__ __forceinline__ void tma2_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// MN-major, SWIZZLE_128B operand (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in
+// 16-byte units): 64 M-contiguous bf16 per 128-byte row, 8 k-rows per 1 KB atom, atoms along k
+// SBO = 1 KB apart, the next 64 M elements LBO = 8 KB apart (a second 64 x 64 TMA box).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(p), "f"(v) : "memory");
+}
+
+// ---------------------------------------------------------------- fold + pack (in place)
+struct FoldParams {
+    float* lvl[FC_MAX_LEVELS];          // level base pointers of the gradient pyramid
+    int H[FC_MAX_LEVELS], W[FC_MAX_LEVELS], Wp[FC_MAX_LEVELS], msize[FC_MAX_LEVELS];
+    int L, NP, two_planes;
+};
+
+__global__ void __launch_bounds__(256) bwd_fold_pack_kernel(const FoldParams P) {
+    const long long row = blockIdx.x;
+    float* g0 = P.lvl[0] + row * P.NP;
+    const int n_chunks = P.NP >> 3, ppr = P.Wp[0] >> 3;      // 8-element chunks; patches per row pair
+    uint4 hi[BW_MAX_CHUNKS], lo[BW_MAX_CHUNKS];
+#pragma unroll
+    for (int i = 0; i < BW_MAX_CHUNKS; ++i) {
+        const int c = threadIdx.x + i * 256;
+        if (c >= n_chunks) break;
+        // chunk c = one patch row: patch c >> 1, row c & 1 inside it
+        const int patch = c >> 1;
+        const int y = 2 * (patch / ppr) + (c & 1), x0 = 8 * (patch % ppr);
+        const float4 a = *reinterpret_cast<const float4*>(g0 + 8 * c);
+        const float4 b = *reinterpret_cast<const float4*>(g0 + 8 * c + 4);
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // coarsest level first; v holds the (already folded) cells of level l over this chunk
+        for (int l = P.L - 1; l >= 1; --l) {
+            const int n = (8 >> l) > 0 ? (8 >> l) : 1;
+            const int yl = y >> l, xl = x0 >> l;
+            const float* src = P.lvl[l] + row * P.msize[l];
+            float w[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < n) {
+                    float cell = 0.f;
+                    if (yl < P.H[l] && xl + j < P.W[l])
+                        cell = __ldg(src + tile_off(yl, xl + j, P.Wp[l])) + 0.25f * v[j >> 1];
+                    w[j] = cell;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (j < n) ? w[j] : 0.f;
+        }
+        float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (P.L > 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] += 0.25f * v[j >> 1];
+        }
+        uint32_t h[4], lw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(g[2 * j]), h1 = __float2bfloat16_rn(g[2 * j + 1]);
+            const __nv_bfloat162 hh(h0, h1);
+            const __nv_bfloat162 ll(__float2bfloat16_rn(g[2 * j] - __bfloat162float(h0)),
+                                    __float2bfloat16_rn(g[2 * j + 1] - __bfloat162float(h1)));
+            h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            lw[j] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        hi[i] = make_uint4(h[0], h[1], h[2], h[3]);
+        lo[i] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+    __syncthreads();                                         // every fp32 value of the row has been read
+    uint4* out_hi = reinterpret_cast<uint4*>(g0);
+    uint4* out_lo = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(g0) + (size_t)P.NP * 2);
+#pragma unroll
+    for (int i = 0; i < BW_MAX_CHUNKS; ++i) {
+        const int c = threadIdx.x + i * 256;
+        if (c >= n_chunks) break;
+        out_hi[c] = hi[i];
+        if (P.two_planes) out_lo[c] = lo[i];
+    }
+}
+
+// ---------------------------------------------------------------- feature pack
+// blockIdx.z = 2 * b + which;  which 0: fmap1 -> [b][d][p] (row pitch N8), which 1: fmap2 ->
+// [b][d][q'] (row pitch NPk, zeros on pad targets).  Each thread writes 8 consecutive elements.
+struct BwdPackParams {
+    const float* src[2];
+    __nv_bfloat16* hi[2];
+    __nv_bfloat16* lo[2];
+    int D, N, N8, NP, NPk, H, W, Wp, two_planes;
+};
+
+__global__ void __launch_bounds__(256) bwd_pack_kernel(const BwdPackParams P) {
+    const int which = blockIdx.z & 1, b = blockIdx.z >> 1, d = blockIdx.y;
+    const int pitch = which ? P.NPk : P.N8;
+    const int c = blockIdx.x * 256 + threadIdx.x;            // chunk of 8 output elements
+    if (8 * c >= pitch) return;
+    const float* s = P.src[which] + ((long long)b * P.D + d) * P.N;
+    float x[8];
+    if (which == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (8 * c + j < P.N) ? __ldg(s + 8 * c + j) : 0.f;
+    } else {
+        int y, x0;
+        tile_inv(8 * c, P.Wp, y, x0);                        // a chunk is one patch row: same y, x0 .. x0 + 7
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (8 * c < P.NP && y < P.H && x0 + j < P.W) ? __ldg(s + y * P.W + x0 + j) : 0.f;
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * j]), h1 = __float2bfloat16_rn(x[2 * j + 1]);
+        const __nv_bfloat162 hh(h0, h1);
+        const __nv_bfloat162 ll(__float2bfloat16_rn(x[2 * j] - __bfloat162float(h0)),
+                                __float2bfloat16_rn(x[2 * j + 1] - __bfloat162float(h1)));
+        h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    const long long o = ((long long)b * P.D + d) * pitch + 8 * c;
+    *reinterpret_cast<uint4*>(P.hi[which] + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (P.two_planes) *reinterpret_cast<uint4*>(P.lo[which] + o) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---------------------------------------------------------------- GEMM
+struct BwdParams {
+    float* out;            // dfmap1 or dfmap2: (B, D, N) fp32, zero-initialised (split-K accumulates)
+    int D, N, NP, H, W, Wp;
+    int M;                 // rows of this GEMM: N (dF1) or NP (dF2)
+    int kb_total;          // ceil(K / 64), K = NP (dF1) or N (dF2)
+    int mp;                // pair-tiles (256 rows) per sample
+    int ksplit;            // work units per (sample, pair-tile)
+    int units;             // B * mp * ksplit
+    int three_pass;
+    float scale;           // 1 / sqrt(D)
+};
+
+template <int OP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BW_THREADS, 1)
+tc_bwd_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+              const BwdParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + BW_STAGES * BW_STAGE_BYTES);
+    uint64_t* full = bars;                          // BW_STAGES (leader's are used)
+    uint64_t* empty = full + BW_STAGES;             // BW_STAGES
+    uint64_t* t_full = empty + BW_STAGES;           // 2
+    uint64_t* t_empty = t_full + 2;                 // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_parts = P.three_pass ? 2 : 1;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int half_n = P.D / 2;                     // rows of the N-side operand held by each CTA
+
+    const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+    const int u_begin = (int)((long long)P.units * cluster_id / n_clusters);
+    const int u_end = (int)((long long)P.units * (cluster_id + 1) / n_clusters);
+    auto decode = [&](int u, int& b, int& m0, int& kb0, int& kb1) {
+        const int am = u / P.ksplit, ks = u - am * P.ksplit;
+        b = am / P.mp;
+        m0 = ((am - b * P.mp) * 2 + (int)rank) * BW_BM;
+        kb0 = (int)((long long)P.kb_total * ks / P.ksplit);
+        kb1 = (int)((long long)P.kb_total * (ks + 1) / P.ksplit);
+    };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < BW_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }   // 4 epilogue warps x 2 CTAs
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (lane == 0) {
+            const uint32_t stage_tx = (uint32_t)(2 * n_parts * (BW_PART_BYTES + half_n * BW_BK * 2));
+            int it = 0;
+            for (int u = u_begin; u < u_end; ++u) {
+                int b, m0, kb0, kb1;
+                decode(u, b, m0, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % BW_STAGES;
+                    mbar_wait(empty + s, ((uint32_t)(it / BW_STAGES) & 1u) ^ 1u);
+                    if (leader) mbar_expect_tx(full + s, stage_tx);
+                    uint8_t* st = ring + s * BW_STAGE_BYTES;
+                    for (int part = 0; part < n_parts; ++part) {
+                        const CUtensorMap* ma = part ? &map_a_lo : &map_a_hi;
+                        const CUtensorMap* mb = part ? &map_b_lo : &map_b_hi;
+                        uint8_t* a_dst = st + part * BW_PART_BYTES;
+                        if (OP == BW_DF1) {
+                            tma2_load_3d(a_dst, ma, full + s, kb * BW_BK, m0, b);               // [128 p][64 q']
+                        } else {
+                            tma2_load_3d(a_dst, ma, full + s, m0, kb * BW_BK, b);               // [64 p][64 q'] x 2
+                            tma2_load_3d(a_dst + BW_PART_BYTES / 2, ma, full + s, m0 + 64, kb * BW_BK, b);
+                        }
+                        tma2_load_2d(st + (2 + part) * BW_PART_BYTES, mb, full + s, kb * BW_BK,
+                                     b * P.D + (int)rank * half_n);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (lane == 0 && leader) {
+            const uint32_t idesc = umma_idesc_bf16(2 * BW_BM, P.D) | (OP == BW_DF2 ? (1u << 15) : 0u);
+            int it = 0, uc = 0;
+            for (int u = u_begin; u < u_end; ++u, ++uc) {
+                int b, m0, kb0, kb1;
+                decode(u, b, m0, kb0, kb1);
+                const int buf = uc & 1;
+                mbar_wait(t_empty + buf, ((uint32_t)(uc >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + (uint32_t)(buf * 256);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % BW_STAGES;
+                    mbar_wait(full + s, (uint32_t)(it / BW_STAGES) & 1u);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(ring + s * BW_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BW_BK / 16; ++k) {
+                        uint64_t ah, al;
+                        if (OP == BW_DF1) {
+                            ah = umma_desc_sw128(st + k * 32);
+                            al = umma_desc_sw128(st + BW_PART_BYTES + k * 32);
+                        } else {
+                            ah = umma_desc_mn_sw128(st + k * 2048);
+                            al = umma_desc_mn_sw128(st + BW_PART_BYTES + k * 2048);
+                        }
+                        const uint64_t bh = umma_desc_sw128(st + 2 * BW_PART_BYTES + k * 32);
+                        const uint64_t bl = umma_desc_sw128(st + 3 * BW_PART_BYTES + k * 32);
+                        umma2_bf16(d_addr, ah, bh, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                        if (P.three_pass) {
+                            umma2_bf16(d_addr, al, bh, idesc, 1u);
+                            umma2_bf16(d_addr, ah, bl, idesc, 1u);
+                        }
+                    }
+                    umma2_commit(empty + s);
+                }
+                umma2_commit(t_full + buf);
+            }
+        }
+    } else {
+        // ================= epilogue: TMEM -> scale -> red.add into (B, D, N) =================
+        const int quarter = warp & 3;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        int uc = 0;
+        for (int u = u_begin; u < u_end; ++u, ++uc) {
+            int b, m0, kb0, kb1;
+            decode(u, b, m0, kb0, kb1);
+            const int buf = uc & 1;
+            const int r = m0 + quarter * 32 + lane;            // row of this GEMM held by this thread
+            int col = -1;                                      // position inside the (.., N) output row
+            if (r < P.M) {
+                if (OP == BW_DF1) {
+                    col = r;
+                } else {
+                    int y, x;
+                    tile_inv(r, P.Wp, y, x);
+                    if (y < P.H && x < P.W) col = y * P.W + x;
+                }
+            }
+            float* dst = P.out + (long long)b * P.D * P.N + col;
+            mbar_wait(t_full + buf, (uint32_t)(uc >> 1) & 1u);
+            tc_fence_after();
+            for (int c0 = 0; c0 < P.D; c0 += 32) {
+                float v[32];
+                tmem_ld32(lane_addr + (uint32_t)(buf * 256 + c0), v);
+                tmem_ld_wait();
+                if (col >= 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) red_add_f32(dst + (long long)(c0 + j) * P.N, v[j] * P.scale);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(t_empty + buf, 0);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ---------------------------------------------------------------- host side
+static int encode_bf16(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                       const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FC_ECUDA; }
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (backward operand, rank %d) failed (%d)", rank, (int)r); return FC_ECUDA; }
+    return FC_OK;
+}
+
+struct BwdLayout { size_t f1_hi, f1_lo, f2_hi, f2_lo, total; int N8, NPk; };
+
+static BwdLayout bwd_layout(int B, int D, int N, int NP) {
+    BwdLayout L;
+    L.N8 = round_up(N, 8); L.NPk = round_up(NP, 8);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
+    L.f1_hi = take((size_t)B * D * L.N8 * 2);
+    L.f1_lo = take((size_t)B * D * L.N8 * 2);
+    L.f2_hi = take((size_t)B * D * L.NPk * 2);
+    L.f2_lo = take((size_t)B * D * L.NPk * 2);
+    L.total = off;
+    return L;
+}
+
+bool tc_bwd_supported(int D, int H, int W) {
+    const long long NP = (long long)round_up(H, 2) * round_up(W, 8);
+    return D % 64 == 0 && D <= 256 && NP <= 256LL * 8 * BW_MAX_CHUNKS;
+}
+
+size_t tc_bwd_workspace_bytes(int B, int D, int H, int W) {
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || !tc_bwd_supported(D, H, W)) return 0;
+    return bwd_layout(B, D, H * W, round_up(H, 2) * round_up(W, 8)).total + 1024;
+}
+
+static int pick_ksplit(int m_units, int kb_total, int n_clusters) {
+    int best = 1; long long best_cost = -1;
+    for (int s = 1; s <= 8 && s <= kb_total; ++s) {
+        const long long rounds = ((long long)m_units * s + n_clusters - 1) / n_clusters;
+        const long long cost = rounds * ((kb_total + s - 1) / s) + 2 * rounds;      // + per-unit epilogue/fill slack
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+    }
+    return best;
+}
+
+template <int OP>
+static int launch_bwd_gemm(const CUtensorMap* maps, BwdParams P, int B, cudaStream_t s) {
+    const size_t smem = 1024 + (size_t)BW_STAGES * BW_STAGE_BYTES + 256;
+    FC_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int n_clusters = 0;
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(BW_THREADS); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        FC_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, tc_bwd_kernel<OP>, &cfg));
+    }
+    if (n_clusters < 1) { set_error("fc_build_bwd: no CTA pair of the tensor-core kernel fits on this device"); return FC_ECUDA; }
+    P.ksplit = pick_ksplit(B * P.mp, P.kb_total, n_clusters);
+    P.units = B * P.mp * P.ksplit;
+    if (n_clusters > P.units) n_clusters = P.units;
+    tc_bwd_kernel<OP><<<dim3(2 * n_clusters), BW_THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], P);
+    FC_LAUNCH_CHECK("tc_bwd_kernel");
+    return FC_OK;
+}
+
+int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float* d2, const Pyramid& pyr,
+                 int D, int H, int W, int math, void* ws, size_t ws_bytes, cudaStream_t s) {
+    const int B = pyr.B, N = pyr.N, Wp = pyr.lv[0].Wp, NP = pyr.lv[0].Hp * Wp;
+    FC_REQUIRE(tc_bwd_supported(D, H, W), "fc_build_bwd: tensor-core modes need D %% 64 == 0, D <= 256 and a padded map of "
+               "at most %d targets (got D=%d, %d targets); use FC_MATH_FP32", 256 * 8 * BW_MAX_CHUNKS, D, NP);
+    const BwdLayout L = bwd_layout(B, D, N, NP);
+    uint8_t* w8 = static_cast<uint8_t*>(ws);
+    const size_t shift = w8 ? ((1024 - (reinterpret_cast<uintptr_t>(w8) & 1023)) & 1023) : 0;
+    if (!w8 || ws_bytes < L.total + shift) {
+        set_error("fc_build_bwd: workspace %zu < %zu bytes (fc_build_bwd_workspace_bytes)", ws_bytes, L.total + shift);
+        return FC_EWORKSPACE;
+    }
+    w8 += shift;
+    const int three = (math == FC_MATH_TC_3XBF16) ? 1 : 0;
+    float* g0 = gpyr + pyr.lv[0].offset;
+
+    {   // fold the pyramid into level 0 and split it into bf16 planes, in place
+        FoldParams F{};
+        F.L = pyr.L; F.NP = NP; F.two_planes = three;
+        for (int l = 0; l < pyr.L; ++l) {
+            F.lvl[l] = gpyr + pyr.lv[l].offset;
+            F.H[l] = pyr.lv[l].H; F.W[l] = pyr.lv[l].W; F.Wp[l] = pyr.lv[l].Wp; F.msize[l] = pyr.lv[l].Hp * pyr.lv[l].Wp;
+        }
+        bwd_fold_pack_kernel<<<dim3((unsigned)((long long)B * N)), 256, 0, s>>>(F);
+        FC_LAUNCH_CHECK("bwd_fold_pack_kernel");
+    }
+    __nv_bfloat16* f1_hi = reinterpret_cast<__nv_bfloat16*>(w8 + L.f1_hi);
+    __nv_bfloat16* f1_lo = reinterpret_cast<__nv_bfloat16*>(w8 + L.f1_lo);
+    __nv_bfloat16* f2_hi = reinterpret_cast<__nv_bfloat16*>(w8 + L.f2_hi);
+    __nv_bfloat16* f2_lo = reinterpret_cast<__nv_bfloat16*>(w8 + L.f2_lo);
+    {
+        BwdPackParams K{};
+        K.src[0] = f1; K.src[1] = f2;
+        K.hi[0] = f1_hi; K.lo[0] = f1_lo; K.hi[1] = f2_hi; K.lo[1] = f2_lo;
+        K.D = D; K.N = N; K.N8 = L.N8; K.NP = NP; K.NPk = L.NPk; K.H = H; K.W = W; K.Wp = Wp; K.two_planes = three;
+        const int chunks = (L.NPk > L.N8 ? L.NPk : L.N8) / 8;
+        bwd_pack_kernel<<<dim3((unsigned)((chunks + 255) / 256), (unsigned)D, (unsigned)(2 * B)), 256, 0, s>>>(K);
+        FC_LAUNCH_CHECK("bwd_pack_kernel");
+    }
+
+    // the G planes as a 3-D bf16 tensor {q' (contiguous), p, b}: row pitch 4 NP bytes
+    const uint8_t* g_hi = reinterpret_cast<const uint8_t*>(g0);
+    const uint8_t* g_lo = g_hi + (size_t)NP * 2;
+    const cuuint64_t gdims[3] = {(cuuint64_t)NP, (cuuint64_t)N, (cuuint64_t)B};
+    const cuuint64_t gstr[2] = {(cuuint64_t)NP * 4, (cuuint64_t)N * NP * 4};
+
+    BwdParams P{};
+    P.D = D; P.N = N; P.NP = NP; P.H = H; P.W = W; P.Wp = Wp;
+    P.three_pass = three; P.scale = 1.0f / sqrtf((float)D);
+    const cuuint32_t bbox[2] = {(cuuint32_t)BW_BK, (cuuint32_t)(D / 2)};
+    CUtensorMap maps[4];
+    if (d1) {
+        FC_CUDA(cudaMemsetAsync(d1, 0, (size_t)B * D * N * 4, s));
+        const cuuint32_t abox[3] = {(cuuint32_t)BW_BK, (cuuint32_t)BW_BM, 1};
+        if (int e = encode_bf16(&maps[0], g_hi, 3, gdims, gstr, abox)) return e;
+        if (int e = encode_bf16(&maps[1], three ? g_lo : g_hi, 3, gdims, gstr, abox)) return e;
+        const cuuint64_t bdims[2] = {(cuuint64_t)NP, (cuuint64_t)B * D};
+        const cuuint64_t bstr[1] = {(cuuint64_t)L.NPk * 2};
+        if (int e = encode_bf16(&maps[2], f2_hi, 2, bdims, bstr, bbox)) return e;
+        if (int e = encode_bf16(&maps[3], three ? f2_lo : f2_hi, 2, bdims, bstr, bbox)) return e;
+        P.out = d1; P.M = N; P.kb_total = (NP + BW_BK - 1) / BW_BK; P.mp = (N + 2 * BW_BM - 1) / (2 * BW_BM);
+        if (int e = launch_bwd_gemm<BW_DF1>(maps, P, B, s)) return e;
+    }
+    if (d2) {
+        FC_CUDA(cudaMemsetAsync(d2, 0, (size_t)B * D * N * 4, s));
+        const cuuint32_t abox[3] = {64, 64, 1};
+        if (int e = encode_bf16(&maps[0], g_hi, 3, gdims, gstr, abox)) return e;
+        if (int e = encode_bf16(&maps[1], three ? g_lo : g_hi, 3, gdims, gstr, abox)) return e;
+        const cuuint64_t bdims[2] = {(cuuint64_t)N, (cuuint64_t)B * D};
+        const cuuint64_t bstr[1] = {(cuuint64_t)L.N8 * 2};
+        if (int e = encode_bf16(&maps[2], f1_hi, 2, bdims, bstr, bbox)) return e;
+        if (int e = encode_bf16(&maps[3], three ? f1_lo : f1_hi, 2, bdims, bstr, bbox)) return e;
+        P.out = d2; P.M = NP; P.kb_total = (N + BW_BK - 1) / BW_BK; P.mp = (NP + 2 * BW_BM - 1) / (2 * BW_BM);
+        if (int e = launch_bwd_gemm<BW_DF2>(maps, P, B, s)) return e;
+    }
+    return FC_OK;
+}
+
+}  // namespace fc

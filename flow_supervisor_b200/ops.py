@@ -166,9 +166,11 @@ def build_bwd(grad_pyramid: Tensor, fmap1: Tensor, fmap2: Tensor, num_levels: in
     lib = _lib.load()
     with torch.cuda.device(f1.device):
         d1, d2 = torch.empty_like(f1), torch.empty_like(f2)
+        ws_bytes = lib.fc_build_bwd_workspace_bytes(B, D, H, W, num_levels, math)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=f1.device)
         _lib.check(lib.fc_build_bwd(grad_pyramid.data_ptr(), f1.data_ptr(), f2.data_ptr(), d1.data_ptr(),
-                                    d2.data_ptr(), B, D, H, W, num_levels, math, None, 0, _stream()),
-                   "fc_build_bwd")
+                                    d2.data_ptr(), B, D, H, W, num_levels, math, ws.data_ptr(), ws_bytes,
+                                    _stream()), "fc_build_bwd")
     return d1, d2
 
 

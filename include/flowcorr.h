@@ -78,7 +78,7 @@ int fc_level_dims(int H, int W, int level, int* Hl, int* Wl, int* Wp);
 size_t fc_pyramid_bytes(int B, int H, int W, int num_levels, int vol_dtype,
                         size_t* level_offsets /* [num_levels] or NULL */);
 
-/* Scratch needed by fc_build / fc_build_bwd for the given problem and math mode. */
+/* Scratch needed by fc_build for the given problem and math mode. */
 size_t fc_build_workspace_bytes(int B, int D, int H, int W, int num_levels, int math);
 
 /* CorrBlock.__init__  (corr.py:13-27; CorrBlock.corr corr.py:52-60; gma_corr.py:15-63)
@@ -113,6 +113,10 @@ int fc_lookup_fwd(const void* pyramid, const float* coords, float* out,
 int fc_lookup_bwd(const float* grad_out, const float* coords, float* grad_pyramid,
                   int B, int H, int W, int num_levels, int radius,
                   int coord_mode, void* stream);
+
+/* Scratch needed by fc_build_bwd (0 for FC_MATH_FP32 and for shapes the tensor-core
+ * backward does not take: those run the fp32 CUDA-core contractions). */
+size_t fc_build_bwd_workspace_bytes(int B, int D, int H, int W, int num_levels, int math);
 
 /* Backward of CorrBlock.__init__ (autograd of corr.py:21-27,52-60): folds the
  * gradient pyramid to level 0 (avg_pool2d backward; grad_pyramid is consumed /
