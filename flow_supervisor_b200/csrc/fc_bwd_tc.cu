@@ -32,7 +32,7 @@ constexpr int BW_BK = 64;                                   // bf16 per 128-byte
 constexpr int BW_STAGES = 3;
 constexpr int BW_PART_BYTES = 128 * BW_BK * 2;              // 16 KB: one operand part (<= 128 rows x 64 k)
 constexpr int BW_STAGE_BYTES = 4 * BW_PART_BYTES;           // A_hi, A_lo, B_hi, B_lo
-constexpr int BW_MAX_CHUNKS = 8;                            // fold+pack: 8-element chunks per thread (NP <= 16384)
+constexpr int BW_MAX_NP = 16384;                            // fold+pack stages a whole query row (all levels + both planes) in shared memory
 
 enum { BW_DF1 = 0, BW_DF2 = 1 };
 
@@ -56,53 +56,80 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
 }
 
 // ---------------------------------------------------------------- fold + pack (in place)
+// One CTA per query row.  The row's maps of every level arrive in shared memory as 1-D bulk
+// copies (one instruction each, no registers in flight), the fold + split runs out of shared
+// memory, and the two bf16 planes leave as ONE bulk store over the row's own level-0 bytes
+// (hi plane = bytes [0, 2 NP), lo plane = [2 NP, 4 NP)): in place is safe because the store
+// is issued after this CTA's loads have landed and no other CTA touches the row.
 struct FoldParams {
     float* lvl[FC_MAX_LEVELS];          // level base pointers of the gradient pyramid
     int H[FC_MAX_LEVELS], W[FC_MAX_LEVELS], Wp[FC_MAX_LEVELS], msize[FC_MAX_LEVELS];
-    int L, NP, two_planes;
+    int soff[FC_MAX_LEVELS];            // float offset of level l inside the shared staging area
+    int L, NP, two_planes, in_floats;   // in_floats = sum of msize
 };
 
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* gdst, uint32_t smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+
+template <int L>
 __global__ void __launch_bounds__(256) bwd_fold_pack_kernel(const FoldParams P) {
+    extern __shared__ __align__(128) uint8_t fp_smem[];
+    float* in = reinterpret_cast<float*>(fp_smem);                                   // [in_floats]
+    uint4* out_hi = reinterpret_cast<uint4*>(fp_smem + (size_t)P.in_floats * 4);      // NP bf16
+    uint4* out_lo = reinterpret_cast<uint4*>(fp_smem + (size_t)P.in_floats * 4 + (size_t)P.NP * 2);
+    __shared__ uint64_t bar;
     const long long row = blockIdx.x;
-    float* g0 = P.lvl[0] + row * P.NP;
-    const int n_chunks = P.NP >> 3, ppr = P.Wp[0] >> 3;      // 8-element chunks; patches per row pair
-    uint4 hi[BW_MAX_CHUNKS], lo[BW_MAX_CHUNKS];
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&bar, (uint32_t)P.in_floats * 4u);
 #pragma unroll
-    for (int i = 0; i < BW_MAX_CHUNKS; ++i) {
-        const int c = threadIdx.x + i * 256;
-        if (c >= n_chunks) break;
-        // chunk c = one patch row: patch c >> 1, row c & 1 inside it
-        const int patch = c >> 1;
-        const int y = 2 * (patch / ppr) + (c & 1), x0 = 8 * (patch % ppr);
-        const float4 a = *reinterpret_cast<const float4*>(g0 + 8 * c);
-        const float4 b = *reinterpret_cast<const float4*>(g0 + 8 * c + 4);
-        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        // coarsest level first; v holds the (already folded) cells of level l over this chunk
-        for (int l = P.L - 1; l >= 1; --l) {
-            const int n = (8 >> l) > 0 ? (8 >> l) : 1;
+        for (int l = 0; l < L; ++l)
+            bulk_load_1d(smem_u32(in + P.soff[l]), P.lvl[l] + row * P.msize[l], (uint32_t)P.msize[l] * 4u, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    const int n_patches = P.NP >> 4, ppr = P.Wp[0] >> 3;      // a patch = rows (y, y + 1) x 8 columns
+    for (int pt = threadIdx.x; pt < n_patches; pt += 256) {
+        const int y = 2 * (pt / ppr), x0 = 8 * (pt % ppr);
+        // v: the (already folded) cells of the level above over this patch, coarsest level first
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int l = L - 1; l >= 1; --l) {
+            const int n = (8 >> l) > 0 ? (8 >> l) : 1;        // cells of level l under 8 columns (rows y, y+1 share them)
             const int yl = y >> l, xl = x0 >> l;
-            const float* src = P.lvl[l] + row * P.msize[l];
-            float w[8];
+            float w[4] = {0.f, 0.f, 0.f, 0.f};
+            if (yl < P.H[l] && xl < P.W[l]) {
+                const float* src = in + P.soff[l] + tile_off(yl, xl, P.Wp[l]);
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
+                if (n == 4) { const float4 t = *reinterpret_cast<const float4*>(src); c[0] = t.x; c[1] = t.y; c[2] = t.z; c[3] = t.w; }
+                else if (n == 2) { const float2 t = *reinterpret_cast<const float2*>(src); c[0] = t.x; c[1] = t.y; }
+                else c[0] = *src;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j < n) {
-                    float cell = 0.f;
-                    if (yl < P.H[l] && xl + j < P.W[l])
-                        cell = __ldg(src + tile_off(yl, xl + j, P.Wp[l])) + 0.25f * v[j >> 1];
-                    w[j] = cell;
-                }
+                for (int j = 0; j < 4; ++j)
+                    if (j < n && xl + j < P.W[l]) w[j] = c[j] + 0.25f * v[j >> 1];
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = (j < n) ? w[j] : 0.f;
+            for (int j = 0; j < 4; ++j) v[j] = w[j];
         }
-        float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        if (P.L > 1) {
+        const float4* g4 = reinterpret_cast<const float4*>(in + 16 * pt);
+        float g[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] += 0.25f * v[j >> 1];
+        for (int i = 0; i < 4; ++i) { const float4 t = g4[i]; g[4 * i] = t.x; g[4 * i + 1] = t.y; g[4 * i + 2] = t.z; g[4 * i + 3] = t.w; }
+        if (L > 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] += 0.25f * v[(j & 7) >> 1];
         }
-        uint32_t h[4], lw[4];
+        uint32_t h[8], lw[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
             const __nv_bfloat16 h0 = __float2bfloat16_rn(g[2 * j]), h1 = __float2bfloat16_rn(g[2 * j + 1]);
             const __nv_bfloat162 hh(h0, h1);
             const __nv_bfloat162 ll(__float2bfloat16_rn(g[2 * j] - __bfloat162float(h0)),
@@ -110,18 +137,19 @@ __global__ void __launch_bounds__(256) bwd_fold_pack_kernel(const FoldParams P) 
             h[j] = *reinterpret_cast<const uint32_t*>(&hh);
             lw[j] = *reinterpret_cast<const uint32_t*>(&ll);
         }
-        hi[i] = make_uint4(h[0], h[1], h[2], h[3]);
-        lo[i] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        out_hi[2 * pt] = make_uint4(h[0], h[1], h[2], h[3]);
+        out_hi[2 * pt + 1] = make_uint4(h[4], h[5], h[6], h[7]);
+        if (P.two_planes) {
+            out_lo[2 * pt] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            out_lo[2 * pt + 1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+        }
     }
-    __syncthreads();                                         // every fp32 value of the row has been read
-    uint4* out_hi = reinterpret_cast<uint4*>(g0);
-    uint4* out_lo = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(g0) + (size_t)P.NP * 2);
-#pragma unroll
-    for (int i = 0; i < BW_MAX_CHUNKS; ++i) {
-        const int c = threadIdx.x + i * 256;
-        if (c >= n_chunks) break;
-        out_hi[c] = hi[i];
-        if (P.two_planes) out_lo[c] = lo[i];
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bulk_store_1d(P.lvl[0] + row * P.NP, smem_u32(out_hi), (uint32_t)P.NP * (P.two_planes ? 4u : 2u));
+        tma_commit_group();
+        tma_wait_group_read<0>();                              // shared memory may be released
     }
 }
 
@@ -370,7 +398,7 @@ static BwdLayout bwd_layout(int B, int D, int N, int NP) {
 
 bool tc_bwd_supported(int D, int H, int W) {
     const long long NP = (long long)round_up(H, 2) * round_up(W, 8);
-    return D % 64 == 0 && D <= 256 && NP <= 256LL * 8 * BW_MAX_CHUNKS;
+    return D % 64 == 0 && D <= 256 && NP <= BW_MAX_NP;
 }
 
 size_t tc_bwd_workspace_bytes(int B, int D, int H, int W) {
@@ -415,7 +443,7 @@ int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float
                  int D, int H, int W, int math, void* ws, size_t ws_bytes, cudaStream_t s) {
     const int B = pyr.B, N = pyr.N, Wp = pyr.lv[0].Wp, NP = pyr.lv[0].Hp * Wp;
     FC_REQUIRE(tc_bwd_supported(D, H, W), "fc_build_bwd: tensor-core modes need D %% 64 == 0, D <= 256 and a padded map of "
-               "at most %d targets (got D=%d, %d targets); use FC_MATH_FP32", 256 * 8 * BW_MAX_CHUNKS, D, NP);
+               "at most %d targets (got D=%d, %d targets); use FC_MATH_FP32", BW_MAX_NP, D, NP);
     const BwdLayout L = bwd_layout(B, D, N, NP);
     uint8_t* w8 = static_cast<uint8_t*>(ws);
     const size_t shift = w8 ? ((1024 - (reinterpret_cast<uintptr_t>(w8) & 1023)) & 1023) : 0;
@@ -430,11 +458,25 @@ int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float
     {   // fold the pyramid into level 0 and split it into bf16 planes, in place
         FoldParams F{};
         F.L = pyr.L; F.NP = NP; F.two_planes = three;
+        int so = 0;
         for (int l = 0; l < pyr.L; ++l) {
             F.lvl[l] = gpyr + pyr.lv[l].offset;
             F.H[l] = pyr.lv[l].H; F.W[l] = pyr.lv[l].W; F.Wp[l] = pyr.lv[l].Wp; F.msize[l] = pyr.lv[l].Hp * pyr.lv[l].Wp;
+            F.soff[l] = so; so += F.msize[l];
         }
-        bwd_fold_pack_kernel<<<dim3((unsigned)((long long)B * N)), 256, 0, s>>>(F);
+        F.in_floats = so;
+        const size_t smem = (size_t)so * 4 + (size_t)NP * 4;
+        const dim3 grid((unsigned)((long long)B * N));
+#define FC_FOLD_CASE(LV)                                                                                              \
+    case LV:                                                                                                          \
+        FC_CUDA(cudaFuncSetAttribute(bwd_fold_pack_kernel<LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        bwd_fold_pack_kernel<LV><<<grid, 256, smem, s>>>(F);                                                         \
+        break;
+        switch (pyr.L) {
+            FC_FOLD_CASE(1) FC_FOLD_CASE(2) FC_FOLD_CASE(3) FC_FOLD_CASE(4) FC_FOLD_CASE(5) FC_FOLD_CASE(6)
+            default: set_error("fc_build_bwd: %d levels", pyr.L); return FC_EINVAL;
+        }
+#undef FC_FOLD_CASE
         FC_LAUNCH_CHECK("bwd_fold_pack_kernel");
     }
     __nv_bfloat16* f1_hi = reinterpret_cast<__nv_bfloat16*>(w8 + L.f1_hi);

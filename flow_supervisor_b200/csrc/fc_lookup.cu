@@ -1,159 +1,209 @@
-// Pyramid lookup BACKWARD (autograd of CorrBlock.__call__, corr.py:29-50; the forward
-// lives in fc_lookup_fwd.cu).  HBM-bound scatter: one CTA = 32 consecutive queries x one
-// pyramid level.  The (2r+2)^2 footprint of every query (plus one guard row/column
-// on each side for floor flips of the normalise/un-normalise round trip) is staged
-// into a skewed shared-memory window with 16-byte cp.async row chunks; interpolation
-// then reads the window with lane <-> query so the (B, K, H, W) output stores are
-// 128-byte coalesced.
+// Pyramid lookup BACKWARD (autograd of CorrBlock.__call__, corr.py:29-50; the forward lives in
+// fc_lookup_fwd.cu).  HBM-bound scatter into the block's ONE gradient pyramid.
+//
+// Mirror image of the forward: persistent CTAs walk tiles = (32 consecutive queries) x (one
+// level).  A group of three warps (lane <-> query, warp <-> a third of the window columns)
+// builds every query's (2r+2)^2 gradient window in shared memory in GATHER form --
+//     W[i][j] = wy0[i] (wx0[j] g[j][i] + wx1[j-1] g[j-1][i]) + wy1[i-1] (wx0[j] g[j][i-1] + wx1[j-1] g[j-1][i-1])
+// with g[a][b] the output gradient of window tap (x-offset a, y-offset b) -- laid out exactly as
+// the TMA box of the forward ({2|3 patches, 5|6 row pairs} of the 2x8-patch layout), and ONE
+// `cp.reduce.async.bulk.tensor` per query adds the box into the gradient pyramid: the adds
+// happen in L2 at sector granularity, nothing goes through the SM's REDG path (the previous
+// kernel issued ~30 red.global.add.v4 per query-level and was bound by that issue rate), and
+// parts of the box outside the padded map are dropped by the TMA unit.  Taps on pad columns /
+// the pad row are masked here, so the pads of the gradient pyramid stay zero.
+// Every (query, level) map is touched by exactly one lane per launch; launches of one
+// CorrBlock are stream-ordered, so the only concurrency is inside L2's adder.
+//
+// Lattice coordinates (GRU iteration 0) can flip the floor of single taps
+// (fc::axis_tap): such queries take a per-tap path (warp 0 of the group, plain shared-memory
+// read-modify-write on the lane's private window).
 #include "fc_lookup.cuh"
 
 namespace fc {
 
-constexpr int WIN_ROWS = 12;      // (2r+2) + 2 guard rows, r <= 4
-constexpr int WIN_PITCH = 16;     // floats per window row: 3 alignment + 12 + 1 spare
-constexpr int WIN_STRIDE = 224;   // floats per query window incl. skew room (== 0 mod 32)
-constexpr int LOOKUP_THREADS = 96;
-constexpr int A_PER_WARP = 3;     // x-offsets handled by one warp
+constexpr int LB_GROUPS = 3;                                  // independent warp groups per CTA
+constexpr int LB_GWARPS = 3;                                  // warps per group (window column thirds)
+constexpr int LB_THREADS = 32 * LB_GROUPS * LB_GWARPS;        // 288
+constexpr int LB_STAGES = 2;                                  // window buffers per group
+constexpr int LB_WIN_BYTES = 6 * 3 * 64;                      // 6 row pairs x 3 patches x 64 B = 1152
+constexpr int LB_STAGE_BYTES = QT * LB_WIN_BYTES;             // 36 864
 
-// Bank skew: lanes reading the same (row, column-within-chunk) of their own windows
-// land on 32 different banks when the per-query alignment offsets cycle mod 4 (the
-// smooth-flow case): 4 banks from x0 mod 4, x4 from (q>>2)&3, x2 from (q>>4)&1.
-__device__ __forceinline__ int win_base(int q) {
-    return q * WIN_STRIDE + 4 * ((q >> 2) & 3) + 16 * ((q >> 4) & 1);
+__device__ __forceinline__ void group_sync(int g) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(g + 1), "n"(32 * LB_GWARPS) : "memory");
 }
-
-struct WinDesc {            // per-query footprint descriptor (shared memory)
-    int y_lo[QT];           // first footprint row (may be negative)
-    int x_s[QT];            // first footprint column rounded down to a multiple of 4
-    int n_row[QT];          // rows to stage   (0 = nothing: dead or far query)
-    int n_chunk[QT];        // 16-byte chunks per row to stage
-    long long q_off[QT];    // element offset of the query's map inside the level
-};
-
-template <int RADIUS, int CM>
-__device__ __forceinline__ void query_setup(const LookupParams& P, int level, int lane,
-                                            int gq0, bool live, int& b, int& p,
-                                            float& cx, float& cy, bool& near_,
-                                            WinDesc& d, bool write_desc) {
-    constexpr int R = 2 * RADIUS + 1;
-    // 32 consecutive flattened queries: one 32-bit division per thread, then a wrap
-    b = gq0 / P.N;
-    p = gq0 - b * P.N + lane;
-    while (p >= P.N) { p -= P.N; ++b; }
-    cx = 0.f; cy = 0.f;
-    if (live) {
-        const float* c = P.coords + (long long)b * 2 * P.N + p;
-        cx = __fmul_rn(__ldg(c), P.inv_scale[level]);
-        cy = __fmul_rn(__ldg(c + P.N), P.inv_scale[level]);
-    }
-    // beyond 2^20 every tap is out of bounds for any map this library accepts and the
-    // +-1 flip bound used to size the window no longer holds; NaN compares false.
-    near_ = live && (fabsf(cx) < 1048576.f) && (fabsf(cy) < 1048576.f);
-    if (write_desc) {
-        int nrow = 0, nchunk = 0, ylo = 0, xs = 0;
-        if (near_) {
-            int xl, xh, yl, yh; float t0, t1;
-            axis_tap<CM>(cx, -RADIUS, P.ax[level], xl, t0, t1);
-            axis_tap<CM>(cx, R - 1 - RADIUS, P.ax[level], xh, t0, t1);
-            axis_tap<CM>(cy, -RADIUS, P.ay[level], yl, t0, t1);
-            axis_tap<CM>(cy, R - 1 - RADIUS, P.ay[level], yh, t0, t1);
-            ylo = yl;
-            xs = xl & ~3;                                  // floor to multiple of 4 (two's complement)
-            nrow = min(yh + 1 - yl + 1, WIN_ROWS);
-            nchunk = min(((xh + 1 - xs) >> 2) + 1, WIN_PITCH / 4);
-        }
-        d.y_lo[lane] = ylo; d.x_s[lane] = xs; d.n_row[lane] = nrow; d.n_chunk[lane] = nchunk;
-        d.q_off[lane] = (long long)(gq0 + lane) * P.msize[level];
-    }
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
 }
-
-// Backward: the same window, used as an accumulator.  Every output gradient is
-// splatted into shared memory (4 shared atomics), then the window is flushed with
-// 16-byte vector reductions (red.global.add.v4.f32) into the gradient pyramid.
-__device__ __forceinline__ void red_add_v4(float* gptr, float4 v) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(gptr), "f"(v.x), "f"(v.y),
-                 "f"(v.z), "f"(v.w)
-                 : "memory");
+__device__ __forceinline__ float lds_f32b(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr) : "memory");
+    return v;
 }
 
 template <int RADIUS, int CM>
-__global__ void __launch_bounds__(LOOKUP_THREADS)
-lookup_bwd_kernel(const LookupParams P) {
+__global__ void __launch_bounds__(LB_THREADS, 1)
+lookup_bwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, int n_tiles) {
     constexpr int R = 2 * RADIUS + 1;
-    __shared__ __align__(16) float win[QT * WIN_STRIDE];
-    __shared__ WinDesc desc;
+    constexpr int NCOL = R + 1;                                      // window columns
+    constexpr int CPW = (NCOL + LB_GWARPS - 1) / LB_GWARPS;          // columns per warp (4 for r = 4)
+    extern __shared__ __align__(1024) uint8_t lb_smem[];
 
-    const int level = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gq0 = blockIdx.x * QT;
-    const int gq = gq0 + lane;
-    const bool live = gq < P.Q;
+    const int g = warp / LB_GWARPS, w = warp - g * LB_GWARPS;
+    const int tg = (threadIdx.x - g * 32 * LB_GWARPS);              // thread index inside the group
+    const uint32_t gbase = smem_u32(lb_smem) + (uint32_t)(g * LB_STAGES * LB_STAGE_BYTES);
 
-    float cx, cy; bool near_; int b, p;
-    query_setup<RADIUS, CM>(P, level, lane, gq0, live, b, p, cx, cy, near_, desc, warp == 0);
-    for (int i = threadIdx.x; i < QT * WIN_STRIDE / 4; i += LOOKUP_THREADS)
-        reinterpret_cast<float4*>(win)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
+    // this warp's window columns [c_lo, c_hi) and the x-taps they need: a in [c_lo - 1, c_hi - 1]
+    const int c_lo = min(w * CPW, NCOL), c_hi = min(c_lo + CPW, NCOL);
 
-    if (near_) {
+    const int n_groups = gridDim.x * LB_GROUPS;
+    int it = 0;
+    for (int tile = blockIdx.x * LB_GROUPS + g; tile < n_tiles; tile += n_groups, ++it) {
+        const int level = tile % P.L;
+        const int gq = (tile / P.L) * QT + lane;
+        const bool live = gq < P.Q;
+        float cx = 0.f, cy = 0.f;
+        int b = 0, p = 0;
+        if (live) {
+            b = gq / P.N; p = gq - b * P.N;
+            const float* c = P.coords + (long long)b * 2 * P.N + p;
+            cx = __fmul_rn(__ldg(c), P.inv_scale[level]);
+            cy = __fmul_rn(__ldg(c + P.N), P.inv_scale[level]);
+        }
+        const bool near_ = live && (fabsf(cx) < 1048576.f) && (fabsf(cy) < 1048576.f);
+        const float* gptr = P.io + ((long long)b * P.K + level * R * R) * P.N + p;
+
+        // ---- output gradients of this warp's taps: issued first, consumed after the zero fill
+        float gv[CPW + 1][R];
+#pragma unroll
+        for (int k = 0; k <= CPW; ++k) {
+            const int a = c_lo - 1 + k;
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+                gv[k][i] = (near_ && a >= 0 && a < R && a < c_hi) ? __ldg(gptr + (long long)(a * R + i) * P.N) : 0.f;
+        }
+
+        // ---- tap arithmetic (bit-exact integer part, shared with the forward)
         int y0[R]; float wy0[R], wy1[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) axis_tap<CM>(cy, j - RADIUS, P.ay[level], y0[j], wy0[j], wy1[j]);
-        const int ylo = desc.y_lo[lane], xs = desc.x_s[lane];
-        const float* gq_ptr = P.io + ((long long)b * P.K + level * R * R) * P.N + p;
-        float* wq = win + win_base(lane);
+        int x0a[R]; float wx0a[R], wx1a[R];
 #pragma unroll
-        for (int aa = 0; aa < A_PER_WARP; ++aa) {
-            const int a = warp * A_PER_WARP + aa;
-            if (a >= R) break;
-            int x0; float wx0, wx1;
-            axis_tap<CM>(cx, a - RADIUS, P.ax[level], x0, wx0, wx1);
-            const int rx = min(max(x0 - xs, 0), WIN_PITCH - 2);
+        for (int a = 0; a < R; ++a) axis_tap<CM>(cx, a - RADIUS, P.ax[level], x0a[a], wx0a[a], wx1a[a]);
+        bool regular = true;
 #pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const float g = __ldg(gq_ptr + (long long)(a * R + j) * P.N);
-                const int ry = min(max(y0[j] - ylo, 0), WIN_ROWS - 2);
-                float* w = wq + ry * WIN_PITCH + rx;
-                const float gt = g * wy0[j], gb = g * wy1[j];
-                atomicAdd(w, gt * wx0);
-                atomicAdd(w + 1, gt * wx1);
-                atomicAdd(w + WIN_PITCH, gb * wx0);
-                atomicAdd(w + WIN_PITCH + 1, gb * wx1);
-            }
-        }
-    }
-    __syncthreads();
+        for (int j = 1; j < R; ++j) regular = regular && (y0[j] == y0[0] + j) && (x0a[j] == x0a[0] + j);
 
-    // flush: only chunks that lie inside the map (out-of-bounds taps carry no gradient)
-    const int Hl = P.H[level], Wl = P.W[level], Wp = P.Wp[level];
-    float* base = P.gpyr + P.off[level];
-    for (int idx = threadIdx.x; idx < QT * WIN_ROWS * 4; idx += LOOKUP_THREADS) {
-        int q = idx / (WIN_ROWS * 4);
-        int rem = idx - q * (WIN_ROWS * 4);
-        int row = rem >> 2, chunk = rem & 3;
-        if (row < desc.n_row[q] && chunk < desc.n_chunk[q]) {
-            int y = desc.y_lo[q] + row;
-            int x = desc.x_s[q] + 4 * chunk;
-            if (y >= 0 && y < Hl && x >= 0 && x < Wl) {
-                float4 v = *reinterpret_cast<const float4*>(win + win_base(q) + row * WIN_PITCH + 4 * chunk);
-                // taps on pad columns [Wl, Wp) are out of bounds: keep the pads zero
-                if (x + 1 >= Wl) v.y = 0.f;
-                if (x + 2 >= Wl) v.z = 0.f;
-                if (x + 3 >= Wl) v.w = 0.f;
-                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
-                    red_add_v4(base + desc.q_off[q] + tile_off(y, x, Wp), v);
+        // footprint box as the forward sizes it, but clamped to non-negative tensor coordinates:
+        // TMA loads zero-fill at negative coordinates, TMA stores / reductions TRAP there
+        // (tools/probes/tma_reduce_probe.cu), while boxes overhanging the far edge are clipped
+        const int rp_lo = max(y0[0] >> 1, 0), pc_lo = max(x0a[0] >> 3, 0);
+        const int n_rp = ((y0[R - 1] + 1) >> 1) - rp_lo + 1;
+        const int n_pc = ((x0a[R - 1] + 1) >> 3) - pc_lo + 1;
+        const int sel = (n_rp > 5 ? 2 : 0) + (n_pc > 2 ? 1 : 0);
+        const int pitch = 64 * (n_pc > 2 ? 3 : 2);
+        const int ybase = 2 * rp_lo, xbase = 8 * pc_lo;
+        const int Hl = P.H[level], Wl = P.W[level];
+        // some part of the window lies inside the map
+        const bool touches = near_ && n_rp > 0 && n_pc > 0 && ybase < Hl && xbase < Wl;
+
+        // ---- the buffer used two tiles ago must have been read by its reduce-adds
+        const uint32_t stage = gbase + (uint32_t)((it & 1) * LB_STAGE_BYTES);
+        if (w == 0) tma_wait_group_read<LB_STAGES - 1>();
+        group_sync(g);
+        {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < LB_STAGE_BYTES / 16 / (32 * LB_GWARPS); ++i)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(stage + 16u * (uint32_t)(tg + i * 32 * LB_GWARPS)),
+                             "f"(z.x), "f"(z.y), "f"(z.z), "f"(z.w) : "memory");
+        }
+        group_sync(g);
+
+        const uint32_t wq = stage + (uint32_t)(lane * LB_WIN_BYTES);
+        if (touches && regular) {
+            // window row n (relative to ybase) sits at (n >> 1) * pitch + (n & 1) * 32 bytes
+            const int n0 = y0[0] - ybase;                                  // 0 or 1; negative above the map
+#pragma unroll
+            for (int k = 0; k < CPW; ++k) {
+                const int j = c_lo + k;                                    // window column
+                if (j < c_hi) {
+                    const int x = x0a[0] + j, xr = x - xbase;              // 0 <= xr <= 16
+                    const bool xin = (x >= 0) && (x < Wl);
+                    const uint32_t col = wq + 4u * (uint32_t)(xr + (xr & ~7));
+                    // horizontal weights: own tap a = j (left corner), tap a = j - 1 (right corner)
+                    float wl = 0.f, wr = 0.f;
+#pragma unroll
+                    for (int a = 0; a < R; ++a) {                          // static indexing of the tap arrays
+                        if (a == j) wl = wx0a[a];
+                        if (a == j - 1) wr = wx1a[a];
+                    }
+                    uint32_t rofs = (uint32_t)((n0 >> 1) * pitch + (n0 & 1) * 32);     // wraps for n0 < 0: never stored
+                    uint32_t step = (n0 & 1) ? (uint32_t)pitch - 32u : 32u;
+                    float hprev = 0.f;
+#pragma unroll
+                    for (int i = 0; i <= R; ++i) {
+                        float h = 0.f, wt = 0.f, wb = 0.f;
+                        if (i < R) { h = fmaf(wl, gv[k + 1][i], wr * gv[k][i]); wt = wy0[i]; }
+                        if (i > 0) wb = wy1[i - 1];
+                        const float v = fmaf(wt, h, wb * hprev);
+                        const int y = y0[0] + i;
+                        if (xin && y >= 0 && y < Hl) sts_f32(col + rofs, v);
+                        hprev = h;
+                        rofs += step;
+                        step = (uint32_t)pitch - step;
+                    }
+                }
+            }
+        } else if (touches && w == 0) {
+            // floor flips among the taps: every tap splats its four corners on its own
+            for (int a = 0; a < R; ++a) {
+                int xa; float wxa0, wxa1;
+                axis_tap<CM>(cx, a - RADIUS, P.ax[level], xa, wxa0, wxa1);
+                for (int j = 0; j < R; ++j) {
+                    int ya; float wya0, wya1;
+                    axis_tap<CM>(cy, j - RADIUS, P.ay[level], ya, wya0, wya1);
+                    const float gg = __ldg(gptr + (long long)(a * R + j) * P.N);
+#pragma unroll
+                    for (int cyy = 0; cyy < 2; ++cyy)
+#pragma unroll
+                        for (int cxx = 0; cxx < 2; ++cxx) {
+                            const int x = xa + cxx, y = ya + cyy;
+                            const int xr = x - xbase, n = y - ybase;
+                            if (x >= 0 && x < Wl && y >= 0 && y < Hl && xr >= 0 && xr < 24 && n >= 0 && n < 12) {
+                                const uint32_t ad = wq + 4u * (uint32_t)(xr + (xr & ~7)) + (uint32_t)((n >> 1) * pitch + (n & 1) * 32);
+                                const float wgt = (cyy ? wya1 : wya0) * (cxx ? wxa1 : wxa0);
+                                sts_f32(ad, fmaf(gg, wgt, lds_f32b(ad)));
+                            }
+                        }
+                }
             }
         }
+        fence_proxy_async_smem();
+        group_sync(g);
+        if (w == 0) {
+            if (touches) tma_reduce_add_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, gq);
+            tma_commit_group();
+        }
     }
+    if (w == 0) tma_wait_group<0>();
 }
 
-// ---------------------------------------------------------------- host side
 template <int RADIUS>
-static void launch_bwd(const LookupParams& P, int coord_mode, dim3 grid, cudaStream_t s) {
-    if (coord_mode == FC_COORD_CUDA)
-        lookup_bwd_kernel<RADIUS, FC_COORD_CUDA><<<grid, LOOKUP_THREADS, 0, s>>>(P);
-    else
-        lookup_bwd_kernel<RADIUS, FC_COORD_CPU><<<grid, LOOKUP_THREADS, 0, s>>>(P);
+static int launch_bwd(const LookupMaps& M, const LookupParams& P, int n_tiles, int n_sm, int coord_mode, cudaStream_t s) {
+    const size_t smem = (size_t)LB_GROUPS * LB_STAGES * LB_STAGE_BYTES;
+    const int want = (n_tiles + LB_GROUPS - 1) / LB_GROUPS;
+    const int grid = want < n_sm ? want : n_sm;
+    if (coord_mode == FC_COORD_CUDA) {
+        FC_CUDA(cudaFuncSetAttribute(lookup_bwd_kernel<RADIUS, FC_COORD_CUDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lookup_bwd_kernel<RADIUS, FC_COORD_CUDA><<<grid, LB_THREADS, smem, s>>>(M, P, n_tiles);
+    } else {
+        FC_CUDA(cudaFuncSetAttribute(lookup_bwd_kernel<RADIUS, FC_COORD_CPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lookup_bwd_kernel<RADIUS, FC_COORD_CPU><<<grid, LB_THREADS, smem, s>>>(M, P, n_tiles);
+    }
+    FC_LAUNCH_CHECK("lookup_bwd_kernel");
+    return FC_OK;
 }
 
 }  // namespace fc
@@ -164,6 +214,7 @@ extern "C" int fc_lookup_bwd(const float* grad_out, const float* coords, float* 
                              int B, int H, int W, int num_levels, int radius,
                              int coord_mode, void* stream) {
     FC_REQUIRE(grad_out && coords && grad_pyramid, "fc_lookup_bwd: null pointer");
+    FC_REQUIRE((reinterpret_cast<uintptr_t>(grad_pyramid) & 15u) == 0, "fc_lookup_bwd: grad_pyramid must be 16-byte aligned");
     Pyramid pyr;
     FC_REQUIRE(make_pyramid(pyr, B, H, W, num_levels), "fc_lookup_bwd: bad geometry B=%d H=%d W=%d L=%d", B, H, W, num_levels);
     if (int e = check_lookup_common(pyr, radius, coord_mode)) return e;
@@ -171,14 +222,16 @@ extern "C" int fc_lookup_bwd(const float* grad_out, const float* coords, float* 
     fill_params(P, pyr, radius);
     P.pyr = nullptr; P.coords = coords;
     P.io = const_cast<float*>(grad_out); P.gpyr = grad_pyramid;
-    dim3 grid((unsigned)((P.Q + QT - 1) / QT), (unsigned)pyr.L);
+    LookupMaps M;
+    if (int e = get_level_maps(M, grad_pyramid, pyr, H, W)) return e;
+    int n_sm = 0;
+    if (int e = sm_count(n_sm)) return e;
+    const int n_tiles = ((P.Q + QT - 1) / QT) * pyr.L;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (radius) {
-        case 1: launch_bwd<1>(P, coord_mode, grid, s); break;
-        case 2: launch_bwd<2>(P, coord_mode, grid, s); break;
-        case 3: launch_bwd<3>(P, coord_mode, grid, s); break;
-        default: launch_bwd<4>(P, coord_mode, grid, s); break;
+        case 1: return launch_bwd<1>(M, P, n_tiles, n_sm, coord_mode, s);
+        case 2: return launch_bwd<2>(M, P, n_tiles, n_sm, coord_mode, s);
+        case 3: return launch_bwd<3>(M, P, n_tiles, n_sm, coord_mode, s);
+        default: return launch_bwd<4>(M, P, n_tiles, n_sm, coord_mode, s);
     }
-    FC_LAUNCH_CHECK("lookup_bwd_kernel");
-    return FC_OK;
 }

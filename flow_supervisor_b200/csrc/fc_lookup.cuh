@@ -1,7 +1,7 @@
 // Shared between the lookup forward (fc_lookup_fwd.cu) and backward (fc_lookup.cu).
 #pragma once
 
-#include "fc_common.cuh"
+#include "fc_tma.cuh"
 
 namespace fc {
 
@@ -23,6 +23,16 @@ struct LookupParams {
     int32_t* dbg_y0;
     uint8_t* dbg_mask;
 };
+
+// Per level, four TMA views of the (gradient) pyramid as a 3-D tensor [query][row pair][2*Wp floats]
+// over the 2x8-patch layout: boxes of {2|3 patches, 5|6 row pairs, 1 query}.  Shared by the
+// forward (footprint loads) and the backward (footprint reduce-adds).  Memoised per
+// (pointer, geometry) in fc_lookup_fwd.cu.
+struct LookupMaps {
+    CUtensorMap m[FC_MAX_LEVELS][4];      // [level][(6 row pairs ? 2 : 0) + (3 patches ? 1 : 0)]
+};
+int get_level_maps(LookupMaps& M, const float* pyramid, const Pyramid& pyr, int H, int W);
+int sm_count(int& n_sm);
 
 inline void fill_params(LookupParams& P, const Pyramid& pyr, int radius) {
     P.Q = pyr.B * pyr.N;

@@ -38,10 +38,6 @@ constexpr int LF_WIN_FLOATS = 6 * 3 * 16;                     // 6 row pairs x 3
 constexpr int LF_WIN_BYTES = LF_WIN_FLOATS * 4;               // 1152
 constexpr int LF_STAGE_BYTES = QT * LF_WIN_BYTES;             // 36 864 B per stage
 
-struct LookupMaps {
-    CUtensorMap m[FC_MAX_LEVELS][4];      // [level][(6 row pairs ? 2 : 0) + (3 patches ? 1 : 0)]
-};
-
 struct alignas(16) QueryDesc {           // producer -> consumers, per stage and lane
     int ybase;                            // first window row    (2 * first row pair; may be negative)
     int xbase;                            // first window column (8 * first patch;    may be negative)
@@ -334,7 +330,7 @@ static int encode_level_maps(LookupMaps& M, const float* pyramid, const Pyramid&
     return FC_OK;
 }
 
-static int get_level_maps(LookupMaps& M, const float* pyramid, const Pyramid& pyr, int H, int W) {
+int get_level_maps(LookupMaps& M, const float* pyramid, const Pyramid& pyr, int H, int W) {
     const MapKey key{pyramid, pyr.B, H, W, pyr.L};
     {
         std::lock_guard<std::mutex> g(g_map_mutex);
@@ -367,7 +363,7 @@ static int launch_fwd2(const LookupMaps& M, const LookupParams& P, int n_tiles, 
                : launch_fwd3<RADIUS, FC_COORD_CPU, false>(M, P, n_tiles, n_sm, s);
 }
 
-static int sm_count(int& n_sm) {
+int sm_count(int& n_sm) {
     static thread_local int cached_dev = -1, cached_sm = 0;
     int dev = 0;
     FC_CUDA(cudaGetDevice(&dev));
