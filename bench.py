@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--math", default=os.environ.get("FLOWCORR_MATH", "3xbf16"),
                     choices=["fp32", "3xbf16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rows", action="store_true", help="skip the extra per-row timings (backward, on-demand)")
     return ap.parse_args()
 
 
@@ -370,6 +371,16 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if not args.no_rows:
+            # the other rows of SURVEY.md section 8 (lookup / build backward at config 3, on-demand at
+            # config 5 next to the compiled reference kernel when oracle/_ref holds it): auxiliary,
+            # measured after the timed regions above (tools/bench_rows.py states the work per row)
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_rows
+                line["rows"] = bench_rows.collect(reps=5, ref_kernel=False)   # no oracle/ here
+            except Exception as e:                      # noqa: BLE001
+                line["rows"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rate, reps, el = cpu_path_rate(H, W, iters, batch=1, budget_s=12.0, threads=threads)

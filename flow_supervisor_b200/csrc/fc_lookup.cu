@@ -41,48 +41,64 @@ __device__ __forceinline__ float lds_f32b(uint32_t addr) {
     return v;
 }
 
-template <int RADIUS, int CM>
-__global__ void __launch_bounds__(LB_THREADS, 1)
-lookup_bwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, int n_tiles) {
-    constexpr int R = 2 * RADIUS + 1;
-    constexpr int NCOL = R + 1;                                      // window columns
-    constexpr int CPW = (NCOL + LB_GWARPS - 1) / LB_GWARPS;          // columns per warp (4 for r = 4)
-    extern __shared__ __align__(1024) uint8_t lb_smem[];
+// Raw per-lane inputs of one tile: coordinates and the output gradients of the taps this warp
+// needs.  Loaded one tile AHEAD (nothing here depends on the coordinates' values).
+template <int RADIUS, int WI>
+struct LbTile {
+    static constexpr int R = 2 * RADIUS + 1;
+    static constexpr int NCOL = R + 1;
+    static constexpr int CPW = (NCOL + LB_GWARPS - 1) / LB_GWARPS;      // window columns per warp (4 for r = 4)
+    static constexpr int C_LO = WI * CPW < NCOL ? WI * CPW : NCOL;      // this warp's columns [C_LO, C_HI)
+    static constexpr int C_HI = C_LO + CPW < NCOL ? C_LO + CPW : NCOL;
+    static constexpr int NT = C_HI > C_LO ? C_HI - C_LO + 1 : 0;       // x-taps a = C_LO - 1 + k, k < NT
+    int level, gq;
+    bool live;
+    float cx, cy;                                                        // raw (unscaled) coordinates
+    float gv[NT > 0 ? NT : 1][R];
+    const float* gptr;
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = warp / LB_GWARPS, w = warp - g * LB_GWARPS;
-    const int tg = (threadIdx.x - g * 32 * LB_GWARPS);              // thread index inside the group
-    const uint32_t gbase = smem_u32(lb_smem) + (uint32_t)(g * LB_STAGES * LB_STAGE_BYTES);
-
-    // this warp's window columns [c_lo, c_hi) and the x-taps they need: a in [c_lo - 1, c_hi - 1]
-    const int c_lo = min(w * CPW, NCOL), c_hi = min(c_lo + CPW, NCOL);
-
-    const int n_groups = gridDim.x * LB_GROUPS;
-    int it = 0;
-    for (int tile = blockIdx.x * LB_GROUPS + g; tile < n_tiles; tile += n_groups, ++it) {
-        const int level = tile % P.L;
-        const int gq = (tile / P.L) * QT + lane;
-        const bool live = gq < P.Q;
-        float cx = 0.f, cy = 0.f;
+    __device__ __forceinline__ void load(const LookupParams& P, int tile, int lane) {
+        level = tile % P.L;
+        gq = (tile / P.L) * QT + lane;
+        live = gq < P.Q;
+        cx = 0.f; cy = 0.f;
         int b = 0, p = 0;
         if (live) {
             b = gq / P.N; p = gq - b * P.N;
             const float* c = P.coords + (long long)b * 2 * P.N + p;
-            cx = __fmul_rn(__ldg(c), P.inv_scale[level]);
-            cy = __fmul_rn(__ldg(c + P.N), P.inv_scale[level]);
+            cx = __ldg(c);
+            cy = __ldg(c + P.N);
         }
-        const bool near_ = live && (fabsf(cx) < 1048576.f) && (fabsf(cy) < 1048576.f);
-        const float* gptr = P.io + ((long long)b * P.K + level * R * R) * P.N + p;
-
-        // ---- output gradients of this warp's taps: issued first, consumed after the zero fill
-        float gv[CPW + 1][R];
+        gptr = P.io + ((long long)b * P.K + level * R * R) * P.N + p;
 #pragma unroll
-        for (int k = 0; k <= CPW; ++k) {
-            const int a = c_lo - 1 + k;
+        for (int k = 0; k < NT; ++k) {
+            const int a = C_LO - 1 + k;                                  // compile-time
 #pragma unroll
             for (int i = 0; i < R; ++i)
-                gv[k][i] = (near_ && a >= 0 && a < R && a < c_hi) ? __ldg(gptr + (long long)(a * R + i) * P.N) : 0.f;
+                gv[k][i] = (live && a >= 0 && a < R) ? __ldg(gptr + (long long)(a * R + i) * P.N) : 0.f;
         }
+    }
+};
+
+template <int RADIUS, int CM, int WI>
+__device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams& P, int n_tiles, int g, int lane,
+                                        uint32_t gbase) {
+    using T = LbTile<RADIUS, WI>;
+    constexpr int R = T::R, C_LO = T::C_LO, C_HI = T::C_HI;
+    const int tg = WI * 32 + lane;                                       // thread index inside the group
+    const int n_groups = gridDim.x * LB_GROUPS;
+    int tile = blockIdx.x * LB_GROUPS + g;
+    if (tile >= n_tiles) return;                                         // whole group leaves together
+    T cur;
+    cur.load(P, tile, lane);
+    for (int it = 0;; ++it) {
+        const int next = tile + n_groups;
+        T nxt = cur;
+        if (next < n_tiles) nxt.load(P, next, lane);                     // in flight while this tile is processed
+
+        const int level = cur.level;
+        const float cx = __fmul_rn(cur.cx, P.inv_scale[level]), cy = __fmul_rn(cur.cy, P.inv_scale[level]);
+        const bool near_ = cur.live && (fabsf(cx) < 1048576.f) && (fabsf(cy) < 1048576.f);
 
         // ---- tap arithmetic (bit-exact integer part, shared with the forward)
         int y0[R]; float wy0[R], wy1[R];
@@ -110,15 +126,11 @@ lookup_bwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, in
 
         // ---- the buffer used two tiles ago must have been read by its reduce-adds
         const uint32_t stage = gbase + (uint32_t)((it & 1) * LB_STAGE_BYTES);
-        if (w == 0) tma_wait_group_read<LB_STAGES - 1>();
+        if (WI == 0) tma_wait_group_read<LB_STAGES - 1>();
         group_sync(g);
-        {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < LB_STAGE_BYTES / 16 / (32 * LB_GWARPS); ++i)
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(stage + 16u * (uint32_t)(tg + i * 32 * LB_GWARPS)),
-                             "f"(z.x), "f"(z.y), "f"(z.z), "f"(z.w) : "memory");
-        }
+        for (int i = 0; i < LB_STAGE_BYTES / 16 / (32 * LB_GWARPS); ++i)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n" ::"r"(stage + 16u * (uint32_t)(tg + i * 32 * LB_GWARPS)), "f"(0.f) : "memory");
         group_sync(g);
 
         const uint32_t wq = stage + (uint32_t)(lane * LB_WIN_BYTES);
@@ -126,37 +138,32 @@ lookup_bwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, in
             // window row n (relative to ybase) sits at (n >> 1) * pitch + (n & 1) * 32 bytes
             const int n0 = y0[0] - ybase;                                  // 0 or 1; negative above the map
 #pragma unroll
-            for (int k = 0; k < CPW; ++k) {
-                const int j = c_lo + k;                                    // window column
-                if (j < c_hi) {
-                    const int x = x0a[0] + j, xr = x - xbase;              // 0 <= xr <= 16
-                    const bool xin = (x >= 0) && (x < Wl);
-                    const uint32_t col = wq + 4u * (uint32_t)(xr + (xr & ~7));
-                    // horizontal weights: own tap a = j (left corner), tap a = j - 1 (right corner)
-                    float wl = 0.f, wr = 0.f;
+            for (int k = 0; k + 1 < T::NT; ++k) {
+                constexpr int dummy = 0; (void)dummy;
+                const int j = C_LO + k;                                    // window column (compile-time)
+                const int x = x0a[0] + j, xr = x - xbase;                  // 0 <= xr <= 16 when x >= 0
+                const bool xin = (x >= 0) && (x < Wl);
+                const uint32_t col = wq + 4u * (uint32_t)(xr + (xr & ~7));
+                // horizontal weights: own tap a = j (left corner), tap a = j - 1 (right corner)
+                const float wl = (j < R) ? wx0a[j < R ? j : 0] : 0.f;
+                const float wr = (j >= 1) ? wx1a[j >= 1 ? j - 1 : 0] : 0.f;
+                uint32_t rofs = (uint32_t)((n0 >> 1) * pitch + (n0 & 1) * 32);     // wraps for n0 < 0: never stored
+                uint32_t step = (n0 & 1) ? (uint32_t)pitch - 32u : 32u;
+                float hprev = 0.f;
 #pragma unroll
-                    for (int a = 0; a < R; ++a) {                          // static indexing of the tap arrays
-                        if (a == j) wl = wx0a[a];
-                        if (a == j - 1) wr = wx1a[a];
-                    }
-                    uint32_t rofs = (uint32_t)((n0 >> 1) * pitch + (n0 & 1) * 32);     // wraps for n0 < 0: never stored
-                    uint32_t step = (n0 & 1) ? (uint32_t)pitch - 32u : 32u;
-                    float hprev = 0.f;
-#pragma unroll
-                    for (int i = 0; i <= R; ++i) {
-                        float h = 0.f, wt = 0.f, wb = 0.f;
-                        if (i < R) { h = fmaf(wl, gv[k + 1][i], wr * gv[k][i]); wt = wy0[i]; }
-                        if (i > 0) wb = wy1[i - 1];
-                        const float v = fmaf(wt, h, wb * hprev);
-                        const int y = y0[0] + i;
-                        if (xin && y >= 0 && y < Hl) sts_f32(col + rofs, v);
-                        hprev = h;
-                        rofs += step;
-                        step = (uint32_t)pitch - step;
-                    }
+                for (int i = 0; i <= R; ++i) {
+                    float h = 0.f, wt = 0.f, wb = 0.f;
+                    if (i < R) { h = fmaf(wl, cur.gv[k + 1][i < R ? i : 0], wr * cur.gv[k][i < R ? i : 0]); wt = wy0[i < R ? i : 0]; }
+                    if (i > 0) wb = wy1[i > 0 ? i - 1 : 0];
+                    const float v = fmaf(wt, h, wb * hprev);
+                    const int y = y0[0] + i;
+                    if (xin && y >= 0 && y < Hl) sts_f32(col + rofs, v);
+                    hprev = h;
+                    rofs += step;
+                    step = (uint32_t)pitch - step;
                 }
             }
-        } else if (touches && w == 0) {
+        } else if (touches && WI == 0) {
             // floor flips among the taps: every tap splats its four corners on its own
             for (int a = 0; a < R; ++a) {
                 int xa; float wxa0, wxa1;
@@ -164,7 +171,7 @@ lookup_bwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, in
                 for (int j = 0; j < R; ++j) {
                     int ya; float wya0, wya1;
                     axis_tap<CM>(cy, j - RADIUS, P.ay[level], ya, wya0, wya1);
-                    const float gg = __ldg(gptr + (long long)(a * R + j) * P.N);
+                    const float gg = __ldg(cur.gptr + (long long)(a * R + j) * P.N);
 #pragma unroll
                     for (int cyy = 0; cyy < 2; ++cyy)
 #pragma unroll
@@ -182,12 +189,27 @@ lookup_bwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, in
         }
         fence_proxy_async_smem();
         group_sync(g);
-        if (w == 0) {
-            if (touches) tma_reduce_add_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, gq);
+        if (WI == 0) {
+            if (touches) tma_reduce_add_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, cur.gq);
             tma_commit_group();
         }
+        if (next >= n_tiles) break;
+        tile = next; cur = nxt;
     }
-    if (w == 0) tma_wait_group<0>();
+    if (WI == 0) tma_wait_group<0>();
+}
+
+template <int RADIUS, int CM>
+__global__ void __launch_bounds__(LB_THREADS, 1)
+lookup_bwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, int n_tiles) {
+    extern __shared__ __align__(1024) uint8_t lb_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = warp / LB_GWARPS, w = warp - g * LB_GWARPS;
+    const uint32_t gbase = smem_u32(lb_smem) + (uint32_t)(g * LB_STAGES * LB_STAGE_BYTES);
+    // the three warps of a group run the same loop specialised on their window columns
+    if (w == 0) lb_warp<RADIUS, CM, 0>(M, P, n_tiles, g, lane, gbase);
+    else if (w == 1) lb_warp<RADIUS, CM, 1>(M, P, n_tiles, g, lane, gbase);
+    else lb_warp<RADIUS, CM, 2>(M, P, n_tiles, g, lane, gbase);
 }
 
 template <int RADIUS>

@@ -63,8 +63,28 @@ def inbounds_footprint(c, H, W):
     return tot
 
 
+ROWS = []
+
+
 def emit(**kw):
-    print(json.dumps(kw), flush=True)
+    """Collect a row (and print it when run as a script)."""
+    ROWS.append(kw)
+    if __name__ == "__main__":
+        print(json.dumps(kw), flush=True)
+
+
+def collect(reps=5, ref_kernel=True):
+    """All rows as a list of dicts: what bench.py embeds under "rows"."""
+    global USE_REF
+    USE_REF = ref_kernel
+    ROWS.clear()
+    row_backward(6, 46, 96, reps)
+    row_backward(6, 54, 128, reps)
+    row_ondemand(2, 136, 240, reps)
+    return list(ROWS)
+
+
+USE_REF = True
 
 
 def row_backward(B, H, W, reps):
@@ -83,7 +103,8 @@ def row_backward(B, H, W, reps):
     emit(row="a6 lookup_bwd", geometry=f"B={B} {H}x{W}", ms=ms, bytes_algorithmic=byts,
          gbs=byts / ms / 1e6, bound="hbm", peak=hbm, frac=byts / ms / 1e6 / hbm,
          note="per launch: grad read + footprint read-modify-write (in-bounds discounted) + coords")
-    for math_name, math in (("fp32", _lib.MATH_FP32), ("3xbf16", _lib.MATH_TC_3XBF16)):
+    modes = (("fp32", _lib.MATH_FP32), ("3xbf16", _lib.MATH_TC_3XBF16)) if __name__ == "__main__" else (("3xbf16", _lib.MATH_TC_3XBF16),)
+    for math_name, math in modes:
         def setup():
             gp.normal_()
         try:
@@ -115,7 +136,7 @@ def row_ondemand(B, H, W, reps):
                 query_lookups_per_s=Q / ms * 1e3)
     try:
         from oracle import ref_ext
-        if ref_ext.available():
+        if USE_REF and ref_ext.available():
             rblk = ref_ext.RefAlternateCorrBlock(f1, f2, L, R)
             want = rblk(c)
             got = blk(c)
