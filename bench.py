@@ -304,22 +304,43 @@ def main():
     h2d = f1h.numel() * 4 * 2 + ch.numel() * 4
     d2h = out_host.numel() * 4
 
-    def step_e2e():
-        a, b = f1h.cuda(non_blocking=True), f2h.cuda(non_blocking=True)
-        c = ch.cuda(non_blocking=True)
-        blk = fsb.CorrBlock(a, b, LEVELS, RADIUS)
-        for t in range(iters):
-            out_host[t].copy_(blk(c[t]), non_blocking=True)
+    # H2D of step i+1 (copy stream, double-buffered device inputs) overlaps the D2H of step i's
+    # lookup outputs (PCIe is full duplex); every step's copies stay inside the timed region.
+    copy_stream = torch.cuda.Stream()
+    dev_in = [(torch.empty_like(f1), torch.empty_like(f2), torch.empty_like(coords)) for _ in range(2)]
+    in_ready = [torch.cuda.Event() for _ in range(2)]
+    in_free = [torch.cuda.Event() for _ in range(2)]
 
-    for _ in range(2):
-        step_e2e()
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(in_free[slot])               # the step that last read this slot is done
+            a, b, c = dev_in[slot]
+            a.copy_(f1h, non_blocking=True); b.copy_(f2h, non_blocking=True); c.copy_(ch, non_blocking=True)
+            in_ready[slot].record(copy_stream)
+
+    def run_e2e(n):
+        cur = torch.cuda.current_stream()
+        for sl in range(2):
+            in_free[sl].record(cur)
+        upload(0)
+        for i in range(n):
+            slot = i & 1
+            if i + 1 < n:
+                upload(slot ^ 1)
+            cur.wait_event(in_ready[slot])
+            a, b, c = dev_in[slot]
+            blk = fsb.CorrBlock(a, b, LEVELS, RADIUS)
+            for t in range(iters):
+                out_host[t].copy_(blk(c[t]), non_blocking=True)
+            in_free[slot].record(cur)
+
+    run_e2e(2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_e2e = max(3, min(args.steps, 10))
     if sampler: sampler.resume()
     e0.record()
-    for _ in range(n_e2e):
-        step_e2e()
+    run_e2e(n_e2e)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / n_e2e
@@ -344,14 +365,25 @@ def main():
         N = H * W
         flop = 2.0 * B * N * N * DIM
         pyr_bytes, _ = _lib.pyramid_layout(B, H, W, LEVELS, _lib.VOL_F32)
-        bld = {"kernel": "build (gemm + pyramid)", "bound": "tensor" if math_id else "fp32-simt",
-               "achieved": flop / (build_ms * 1e-3) / 1e12, "peak": tf_sust, "unit": "TFLOP/s",
-               "traffic": ncu_traffic("tc_build_kernel") if math_id else None, "peak_source": peak_src,
-               "flop_per_launch": flop, "flop_issued": flop * (3 if math_id == 1 else 1),
-               "hbm_bytes_per_launch": pyr_bytes + 2 * B * DIM * N * 4,
-               "hbm_gbs": (pyr_bytes + 2 * B * DIM * N * 4) / (build_ms * 1e-3) / 1e9,
-               "ms_per_launch": build_ms, "share_of_step": build_ms / ms_step}
-        bld["frac"] = bld["achieved"] / tf_sust
+        # build sits on the ridge: bound = the larger of the two floors for the ALGORITHMIC work
+        # (SURVEY.md 8d): useful FLOP / tensor peak vs (fmaps read + pyramid written) / HBM peak
+        bld_bytes = pyr_bytes + 2 * B * DIM * N * 4
+        issued = flop * (3 if math_id == _lib.MATH_TC_3XBF16 else 1)
+        t_mma, t_hbm = flop / (tf_sust * 1e12), bld_bytes / (hbm * 1e9)
+        bld = {"kernel": "build (gemm + pyramid)", "peak_source": peak_src,
+               "traffic": ncu_traffic("tc_build_kernel") if math_id else None,
+               "ms_per_launch": build_ms, "share_of_step": build_ms / ms_step,
+               "bytes_per_launch": bld_bytes, "flop_per_launch": flop, "flop_issued": issued,
+               "floor_ms": {"hbm": 1e3 * t_hbm, "tensor_useful": 1e3 * t_mma,
+                            "tensor_issued": 1e3 * issued / (tf_sust * 1e12)},
+               "hbm": {"achieved": bld_bytes / (build_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s"},
+               "tensor": {"achieved": flop / (build_ms * 1e-3) / 1e12, "issued": issued / (build_ms * 1e-3) / 1e12,
+                          "peak": tf_sust, "unit": "TFLOP/s"}}
+        for k in ("hbm", "tensor"):
+            bld[k]["frac"] = bld[k]["achieved"] / bld[k]["peak"]
+        bld["tensor"]["frac_issued"] = bld["tensor"]["issued"] / tf_sust
+        which = "hbm" if (t_hbm >= t_mma or not math_id) else "tensor"
+        bld.update({"bound": which, **bld[which]})
         dominant, other = (look, bld) if look["share_of_step"] >= bld["share_of_step"] else (bld, look)
         line = {
             "metric": "RAFT corr-path pairs/s @436x1024 (12 iters)", "value": value, "unit": "pairs/s",

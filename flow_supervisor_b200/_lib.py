@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libflowcorr.so")
 # enums of include/flowcorr.h
 VOL_F32, VOL_BF16 = 0, 1
 MATH_FP32, MATH_TC_3XBF16, MATH_TC_BF16 = 0, 1, 2
-COORD_CUDA, COORD_CPU = 0, 1
+COORD_CUDA, COORD_CPU, COORD_RAW = 0, 1, 2
 MAX_LEVELS, MAX_RADIUS = 6, 4
 ABI_VERSION = 1
 

@@ -157,19 +157,56 @@ class CorrBlock:
 
 
 class AlternateCorrBlock:
-    """On-demand correlation (corr.py:63-91): nothing volume-sized is stored.  Like the
-    reference's, this block is inference-only (alt_cuda_corr.forward is a raw call with
-    no autograd, corr.py:86)."""
+    """On-demand correlation (corr.py:63-91).  Like the reference's, this block is
+    inference-only (alt_cuda_corr.forward is a raw call with no autograd, corr.py:86).
+
+    Two routes with the same indices and weights (``floor(coords / 2^l)``, no normalise
+    round trip -- FC_COORD_RAW) and values equal up to fp32 rounding:
+
+    * ``'ondemand'``: nothing volume-sized is stored; every call runs the fused
+      dot-product + sampling kernel (fc_ondemand_fwd).
+    * ``'materialise'``: the reference switches to this class when the volume does not fit
+      its GPU; a B200 holds 180 GB, where config 5 of BASELINE.json (1088x1920, batch 2)
+      needs 11.3 GB.  Building the pyramid once on the tensor cores and answering every
+      call with the HBM-bound lookup costs less than three on-demand calls.
+
+    ``AlternateCorrBlock.route`` (FLOWCORR_ALT_ROUTE) = 'auto' picks 'materialise' when the
+    pyramid plus the build workspace fit in ``materialise_fraction`` (default 1/4) of the
+    device memory that is free or cached-but-unused right now, else 'ondemand'.
+    """
+
+    route = os.environ.get("FLOWCORR_ALT_ROUTE", "auto")
+    materialise_fraction = float(os.environ.get("FLOWCORR_ALT_FRACTION", "0.25"))
 
     def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
         if not (fmap1.is_cuda and fmap2.is_cuda):
             raise RuntimeError("flow_supervisor_b200.AlternateCorrBlock needs CUDA feature maps "
                                "(no CPU fallback)")
+        if self.route not in ("auto", "ondemand", "materialise"):
+            raise ValueError(f"AlternateCorrBlock.route must be auto|ondemand|materialise, got {self.route!r}")
         self.num_levels = num_levels
         self.radius = radius
         self._shape = tuple(fmap1.shape)
-        self._ws = ops.ondemand_prepare(fmap1.detach().float(), fmap2.detach().float(), num_levels)
+        B, D, H, W = self._shape
+        f1, f2 = fmap1.detach().float(), fmap2.detach().float()
+        self.materialised = self.route == "materialise" or (
+            self.route == "auto" and self._fits(f1.device, B, D, H, W, num_levels))
+        if self.materialised:
+            self._math = resolve_math(CorrBlock.math, D, W)
+            self._pyramid = ops.build(f1, f2, num_levels, self._math, _lib.VOL_F32)
+        else:
+            self._ws = ops.ondemand_prepare(f1, f2, num_levels)
+
+    @classmethod
+    def _fits(cls, device, B, D, H, W, L) -> bool:
+        math = resolve_math(CorrBlock.math, D, W)
+        need = 4 * ops.pyramid_numel(B, H, W, L) + _lib.load().fc_build_workspace_bytes(B, D, H, W, L, math)
+        free, _total = torch.cuda.mem_get_info(device)
+        cached = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+        return need <= cls.materialise_fraction * (free + cached)
 
     def __call__(self, coords):
         B, D, H, W = self._shape
+        if self.materialised:
+            return ops.lookup(self._pyramid, coords.detach(), self.num_levels, self.radius, _lib.COORD_RAW)
         return ops.ondemand_lookup(self._ws, coords.detach(), D, self.num_levels, self.radius)

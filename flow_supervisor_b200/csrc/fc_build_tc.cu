@@ -124,6 +124,8 @@ struct TcParams {
     int units;             // B * mp * groups work units, split evenly over the resident CTA pairs
     int three_pass;        // 1 = hi*hi + lo*hi + hi*lo, 0 = hi*hi
     float scale;           // 1 / sqrt(D)
+    int probe;             // 0 in production; FLOWCORR_PROBE (tools/probe_bounds.py): 1 = epilogue without
+                           // global stores, 2 = no MMAs issued, 3 = epilogue neither reads TMEM nor stores
 };
 
 template <int KB>   // KB = D / 64 k-blocks
@@ -249,6 +251,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             const uint32_t al_addr = smem_u32(a_lo + kb * TC_ABLK_BYTES);
 #pragma unroll
                             for (int k = 0; k < TC_BK / 16; ++k) {
+                                if (P.probe == 2) break;
                                 const uint64_t bd = umma_desc_sw128(b_addr + k * 32);
                                 // part 0: B = hi -> A_hi*B_hi (+ A_lo*B_hi); part 1: B = lo -> A_hi*B_lo
                                 umma2_bf16(d_addr, umma_desc_sw128(ah_addr + k * 32), bd, idesc, (kb | part | k) != 0 ? 1u : 0u);
@@ -298,14 +301,14 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             fence_proxy_async_smem();
             __syncwarp();
             ++use;
-            if (lane == 0 && rows_valid > 0) {
+            if (lane == 0 && rows_valid > 0 && P.probe != 1) {
                 tma_store_3d(ncols >= 32 ? &SM.l0_c32 : &SM.l0_c16, smem_u32(buf), col, row0, b);
                 tma_commit_group();
             }
         };
         // pooled levels (1/4, 1/16, 1/64 of the data): 32-byte runs straight from registers
         auto store_small = [&](float* base, long long msz, long long off, int ncols, const float* v) {
-            if (rows_valid > lane) {
+            if (rows_valid > lane && P.probe != 1) {
                 float* dst = base + ((long long)b * P.N + row0 + lane) * msz + off;
 #pragma unroll
                 for (int g = 0; g < 4; ++g)
@@ -365,6 +368,12 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 mbar_wait(t_full + buf, (uint32_t)(tc >> 1) & 1u);
                 tc_fence_after();
                 float l1[32], l2[32];
+                if (P.probe == 3) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(t_empty + buf, 0);
+                    continue;
+                }
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {                  // 32 TMEM columns = 16 target columns x 2 rows
                     if (c * 32 < 2 * Wp) {
@@ -599,6 +608,7 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     P.units = B * P.mp * P.groups;
     P.three_pass = three ? 1 : 0;
     P.scale = fold_scale ? 1.0f : inv_sqrt_d;
+    { const char* pr = getenv("FLOWCORR_PROBE"); P.probe = pr ? atoi(pr) : 0; }
 
     CUtensorMap maps[4];
     if (int e = make_map(&maps[0], a_hi, (long long)B * N, D, TC_BM, TC_BK)) return e;

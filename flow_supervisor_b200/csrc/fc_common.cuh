@@ -98,6 +98,15 @@ __host__ __device__ inline AxisConst make_axis(int size) {
 template <int COORD_MODE>
 __device__ __forceinline__ void axis_tap(float c_l, int off, AxisConst ax,
                                          int& i0, float& w0, float& w1) {
+    if (COORD_MODE == FC_COORD_RAW) {
+        // on-demand semantics (corr.py:85, correlation_kernel.cu:67-76): no normalise round trip,
+        // one floor and one fraction per axis shared by every tap
+        const float f0 = floorf(c_l);
+        w1 = __fsub_rn(c_l, f0);
+        w0 = __fsub_rn(1.0f, w1);
+        i0 = (int)f0 + off;
+        return;
+    }
     float X = __fadd_rn(c_l, (float)off);
     float t = __fmul_rn(2.0f, X);
     float g = (COORD_MODE == FC_COORD_CUDA) ? __fmul_rn(t, ax.inv) : __fdiv_rn(t, ax.den);

@@ -190,7 +190,10 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
         fence_proxy_async_smem();
         group_sync(g);
         if (WI == 0) {
-            if (touches) tma_reduce_add_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, cur.gq);
+            if (touches && P.probe != 1) {
+                if (P.probe == 2) tma_store_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, cur.gq);
+                else tma_reduce_add_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, cur.gq);
+            }
             tma_commit_group();
         }
         if (next >= n_tiles) break;

@@ -1,6 +1,8 @@
 // Shared between the lookup forward (fc_lookup_fwd.cu) and backward (fc_lookup.cu).
 #pragma once
 
+#include <stdlib.h>
+
 #include "fc_tma.cuh"
 
 namespace fc {
@@ -19,6 +21,8 @@ struct LookupParams {
     int msize[FC_MAX_LEVELS];   // elements per query map (Hp * Wp)
     AxisConst ax[FC_MAX_LEVELS], ay[FC_MAX_LEVELS];
     float inv_scale[FC_MAX_LEVELS];
+    int probe;              // 0 in production; FLOWCORR_PROBE=n switches one pipeline stage off so that
+                            // tools/probe_bounds.py can time the others (results are then garbage)
     int32_t* dbg_x0;
     int32_t* dbg_y0;
     uint8_t* dbg_mask;
@@ -37,6 +41,8 @@ int sm_count(int& n_sm);
 inline void fill_params(LookupParams& P, const Pyramid& pyr, int radius) {
     P.Q = pyr.B * pyr.N;
     P.N = pyr.N; P.L = pyr.L;
+    const char* pr = getenv("FLOWCORR_PROBE");
+    P.probe = pr ? atoi(pr) : 0;
     const int R = 2 * radius + 1;
     P.K = pyr.L * R * R;
     for (int l = 0; l < pyr.L; ++l) {

@@ -105,9 +105,11 @@ __device__ __forceinline__ void lf_produce(const LookupParams& P, const LookupMa
         const int sel = (n_rp > 5 ? 2 : 0) + (n_pc > 2 ? 1 : 0);
         const int box_rp = n_rp > 5 ? 6 : 5, box_pc = n_pc > 2 ? 3 : 2;
         d.ybase = 2 * rp0; d.xbase = 8 * pc0; d.pitch = 64 * box_pc; d.valid = 1;
-        bytes = (uint32_t)(box_rp * box_pc * 64);
-        tma_load_3d(win + stage * LF_STAGE_BYTES + lane * LF_WIN_BYTES, &M.m[level][sel],
-                    smem_u32(&sh.full[stage]), 16 * pc0, rp0, q.gq);
+        if (P.probe != 1) {
+            bytes = (uint32_t)(box_rp * box_pc * 64);
+            tma_load_3d(win + stage * LF_STAGE_BYTES + lane * LF_WIN_BYTES, &M.m[level][sel],
+                        smem_u32(&sh.full[stage]), 16 * pc0, rp0, q.gq);
+        }
     }
     if (mine) sh.desc[stage][lane] = d;
     const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
@@ -187,7 +189,8 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
 #pragma unroll
                 for (int aa = 0; aa < APW; ++aa) {
                     const float hnext = fmaf(wx1[aa], v[aa + 1], wx0[aa] * v[aa]);
-                    if (w * APW + aa < R) oj[aa * sa] = fmaf(wy1[j], hnext, wy0[j] * hprev[aa]);
+                    const float o = fmaf(wy1[j], hnext, wy0[j] * hprev[aa]);
+                    if (w * APW + aa < R && (P.probe != 2 || o == 1.2345678e30f)) oj[aa * sa] = o;
                     hprev[aa] = hnext;
                 }
                 oj += P.N;
@@ -359,6 +362,9 @@ static int launch_fwd2(const LookupMaps& M, const LookupParams& P, int n_tiles, 
     if (coord_mode == FC_COORD_CUDA)
         return dbg ? launch_fwd3<RADIUS, FC_COORD_CUDA, true>(M, P, n_tiles, n_sm, s)
                    : launch_fwd3<RADIUS, FC_COORD_CUDA, false>(M, P, n_tiles, n_sm, s);
+    if (coord_mode == FC_COORD_RAW)
+        return dbg ? launch_fwd3<RADIUS, FC_COORD_RAW, true>(M, P, n_tiles, n_sm, s)
+                   : launch_fwd3<RADIUS, FC_COORD_RAW, false>(M, P, n_tiles, n_sm, s);
     return dbg ? launch_fwd3<RADIUS, FC_COORD_CPU, true>(M, P, n_tiles, n_sm, s)
                : launch_fwd3<RADIUS, FC_COORD_CPU, false>(M, P, n_tiles, n_sm, s);
 }
@@ -387,7 +393,7 @@ extern "C" int fc_lookup_fwd(const void* pyramid, const float* coords, float* ou
     FC_REQUIRE(vol_dtype == FC_VOL_F32, "fc_lookup_fwd: vol_dtype %d not supported yet", vol_dtype);
     Pyramid pyr;
     FC_REQUIRE(make_pyramid(pyr, B, H, W, num_levels), "fc_lookup_fwd: bad geometry B=%d H=%d W=%d L=%d", B, H, W, num_levels);
-    if (int e = check_lookup_common(pyr, radius, coord_mode)) return e;
+    if (int e = check_lookup_common(pyr, radius, coord_mode == FC_COORD_RAW ? FC_COORD_CUDA : coord_mode)) return e;
     FC_REQUIRE((reinterpret_cast<uintptr_t>(pyramid) & 15u) == 0, "fc_lookup_fwd: pyramid must be 16-byte aligned");
     LookupParams P{};
     fill_params(P, pyr, radius);

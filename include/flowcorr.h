@@ -61,6 +61,10 @@ extern "C" {
  * CUDA tensors multiply by fl(1/(W-1)), CPU tensors divide. */
 #define FC_COORD_CUDA 0
 #define FC_COORD_CPU 1
+/* AlternateCorrBlock's indexing (corr.py:85, correlation_kernel.cu:67-76): tap = floor(c) + offset,
+ * weights (1 - frac(c), frac(c)), no normalise / un-normalise round trip.  fc_lookup_fwd only:
+ * lets a materialised pyramid answer on-demand lookups with the on-demand kernel's indices. */
+#define FC_COORD_RAW 2
 
 int fc_abi_version(void);
 const char* fc_last_error(void);

@@ -243,21 +243,83 @@ def test_errors_are_loud(fsb):
 
 
 # ------------------------------------------------------------------ on-demand variant
+class altroute:
+    """Temporarily pin AlternateCorrBlock.route ('ondemand' = fused dot+sample kernel,
+    'materialise' = tensor-core build + FC_COORD_RAW lookup)."""
+
+    def __init__(self, fsb, route):
+        self.cls, self.route = fsb.AlternateCorrBlock, route
+
+    def __enter__(self):
+        self.old = self.cls.route
+        self.cls.route = self.route
+
+    def __exit__(self, *a):
+        self.cls.route = self.old
+
+
+@pytest.mark.parametrize("route", ["ondemand", "materialise"])
 @pytest.mark.parametrize("shape,r", [((1, 128, 16, 20), 3), ((2, 256, 24, 32), 4)])
-def test_ondemand_matches_spec(fsb, shape, r):
+def test_ondemand_matches_spec(fsb, shape, r, route):
     f1, f2, c = _case(*shape, seed=23, flow_std=3.0)
-    out = fsb.AlternateCorrBlock(f1, f2, num_levels=4, radius=r)(c)
+    with altroute(fsb, route):
+        blk = fsb.AlternateCorrBlock(f1, f2, num_levels=4, radius=r)
+        assert blk.materialised == (route == "materialise")
+        out = blk(c)
     ref = corr_spec.ondemand_lookup(f1.cpu().numpy(), f2.cpu().numpy(), c.cpu().numpy(), 4, r)
     assert out.shape == ref.shape
     assert rel_err(out, ref) < VAL_TOL
 
 
-def test_ondemand_matches_corrblock_at_cfg1_size(fsb):
+@pytest.mark.parametrize("route", ["ondemand", "materialise"])
+def test_ondemand_matches_corrblock_at_cfg1_size(fsb, route):
     f1, f2, c = _case(1, 256, 46, 62, seed=29, flow_std=6.0)
     with mode(fsb, math="fp32"):
         a = fsb.CorrBlock(f1, f2)(c)
-    b = fsb.AlternateCorrBlock(f1, f2)(c)
+    with altroute(fsb, route):
+        b = fsb.AlternateCorrBlock(f1, f2)(c)
     assert rel_err(b, a) < VAL_TOL
+
+
+def test_materialised_route_keeps_ondemand_indices(fsb):
+    """FC_COORD_RAW: tap = floor(c / 2^l) + offset with one fraction per axis
+    (correlation_kernel.cu:67-76), bit-exact -- including lattice coordinates, where
+    CorrBlock's normalise round trip flips floors."""
+    from flow_supervisor_b200 import ops, _lib
+    B, D, H, W, r = 1, 64, 24, 40, 4
+    f1, f2, c = _case(B, D, H, W, seed=37, flow_std=4.0)
+    c[:, :, ::2] = torch.round(c[:, :, ::2])                       # half the rows on the lattice
+    pyr = ops.build(f1, f2, 4, _lib.MATH_FP32, _lib.VOL_F32)
+    out, x0, y0, mask = ops.lookup_debug(pyr, c, 4, r, _lib.COORD_RAW)
+    cn = c.cpu().numpy()
+    cx, cy = cn[:, 0].reshape(-1), cn[:, 1].reshape(-1)
+    offs = np.arange(-r, r + 1, dtype=np.int32)
+    for l in range(4):
+        ex = np.floor(cx / np.float32(2 ** l)).astype(np.int32)[:, None] + offs
+        ey = np.floor(cy / np.float32(2 ** l)).astype(np.int32)[:, None] + offs
+        assert np.array_equal(x0[:, l].cpu().numpy(), ex)
+        assert np.array_equal(y0[:, l].cpu().numpy(), ey)
+    ref = corr_spec.ondemand_lookup(f1.cpu().numpy(), f2.cpu().numpy(), cn, 4, r)
+    assert rel_err(out, ref) < VAL_TOL
+    with altroute(fsb, "ondemand"):
+        od = fsb.AlternateCorrBlock(f1, f2)(c)
+    assert np.array_equal((out == 0).cpu().numpy(), (od == 0).cpu().numpy()) or rel_err(out, od) < 1e-5
+
+
+def test_alternate_routes_agree_at_cfg5_size(fsb):
+    """BASELINE.json config 5 geometry (1088x1920 -> 136x240 tokens; batch 1 here): the fused
+    on-demand kernel and the materialised route are independent kernels over the same
+    inputs; they must agree to fp32 rounding at full size."""
+    f1, f2, c = _case(1, 256, 136, 240, seed=41, flow_std=8.0)
+    with altroute(fsb, "ondemand"):
+        a = fsb.AlternateCorrBlock(f1, f2)(c)
+    with altroute(fsb, "auto"):
+        blk = fsb.AlternateCorrBlock(f1, f2)
+        assert blk.materialised, "5.7 GB must fit a B200 under the default policy"
+        b = blk(c)
+    assert rel_err(b, a) < VAL_TOL
+    del blk
+    torch.cuda.empty_cache()
 
 
 def test_alt_cuda_corr_shim(fsb):
@@ -282,3 +344,38 @@ def test_alt_cuda_corr_shim(fsb):
     assert rel_err(d1.permute(0, 3, 1, 2), r1) < VAL_TOL
     assert rel_err(d2.permute(0, 3, 1, 2), r2) < VAL_TOL
     assert not dc.any()
+
+
+# ------------------------------------------------------------------ CUDA graphs
+def test_build_and_lookups_capture_into_a_cuda_graph(fsb):
+    """include/flowcorr.h: every call is asynchronous, allocates nothing and never synchronises.
+    One RAFT-style sequence (CorrBlock + 3 lookups, raft.py:105-124) is captured into a CUDA
+    graph, replayed on NEW inputs written into the captured buffers, and must reproduce the
+    eager result bit for bit (same kernels, same launch geometry)."""
+    B, D, H, W = 2, 256, 24, 40
+    f1, f2, c = _case(B, D, H, W, seed=43, flow_std=3.0)
+    sf1, sf2 = torch.zeros_like(f1), torch.zeros_like(f2)
+    sc = [torch.zeros_like(c) for _ in range(3)]
+
+    def run():
+        blk = fsb.CorrBlock(sf1, sf2)
+        return [blk(x) for x in sc]
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run()                                               # warm-up: lazy module load, tensor maps
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs = run()
+    sf1.copy_(f1); sf2.copy_(f2)
+    for t, x in enumerate(sc):
+        x.copy_(c + 0.37 * t)
+    graph.replay()
+    torch.cuda.synchronize()
+    blk = fsb.CorrBlock(f1, f2)
+    for t in range(3):
+        want = blk(c + 0.37 * t)
+        assert torch.equal(outs[t], want)
+    assert float(outs[0].abs().max()) > 0

@@ -126,9 +126,32 @@ def row_ondemand(B, H, W, reps):
     f2 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
     c = (fsb.coords_grid(B, H, W) + 8.0 * torch.randn(B, 2, H, W, generator=g)).cuda()
     Q = B * H * W
+    keep = fsb.AlternateCorrBlock.route
+    fsb.AlternateCorrBlock.route = "ondemand"
     ms_prep = timed(lambda: fsb.AlternateCorrBlock(f1, f2, L, R), reps)
     blk = fsb.AlternateCorrBlock(f1, f2, L, R)
     ms = timed(lambda: blk(c), reps)
+    # the same block through the materialised route (tensor-core build once + HBM-bound lookups)
+    fsb.AlternateCorrBlock.route = "materialise"
+    try:
+        ms_build = timed(lambda: fsb.AlternateCorrBlock(f1, f2, L, R), max(2, reps // 2), warm=1)
+        mblk = fsb.AlternateCorrBlock(f1, f2, L, R)
+        ms_look = timed(lambda: mblk(c), reps)
+        diff = float((mblk(c) - blk(c)).abs().max() / blk(c).abs().max())
+        N = H * W
+        emit(row="a7 AlternateCorrBlock route=materialise (build once + FC_COORD_RAW lookups)",
+             geometry=f"B={B} {H}x{W}", build_ms=ms_build, lookup_ms=ms_look,
+             pyramid_gb=4 * ops.pyramid_numel(B, H, W, L) / 1e9,
+             build_tflops_useful=2.0 * B * N * N * D / ms_build / 1e9,
+             ms_12_lookups={"materialise": ms_build + 12 * ms_look, "ondemand": ms_prep + 12 * ms},
+             ms_32_lookups={"materialise": ms_build + 32 * ms_look, "ondemand": ms_prep + 32 * ms},
+             max_rel_diff_vs_ondemand=diff)
+        del mblk
+    except RuntimeError as e:
+        emit(row="a7 AlternateCorrBlock route=materialise", geometry=f"B={B} {H}x{W}", error=str(e))
+    finally:
+        fsb.AlternateCorrBlock.route = keep
+        torch.cuda.empty_cache()
     flop = Q * L * (2 * R + 2) ** 2 * 2.0 * D
     byts = Q * (D * 4 + K * 4 + 8) + sum(B * (H >> l) * (W >> l) * D * 4 for l in range(L))
     line = dict(row="a7 ondemand_fwd (4 levels, one launch)", geometry=f"B={B} {H}x{W}", ms=ms, prepare_ms=ms_prep,
