@@ -125,7 +125,8 @@ struct TcParams {
     int three_pass;        // 1 = hi*hi + lo*hi + hi*lo, 0 = hi*hi
     float scale;           // 1 / sqrt(D)
     int probe;             // 0 in production; FLOWCORR_PROBE (tools/probe_bounds.py): 1 = epilogue without
-                           // global stores, 2 = no MMAs issued, 3 = epilogue neither reads TMEM nor stores
+                           // global stores, 2 = no MMAs issued, 3 = epilogue neither reads TMEM nor stores,
+                           // 4 = (correct results) level 0 stored from registers instead of staged TMA stores
 };
 
 template <int KB>   // KB = D / 64 k-blocks
@@ -284,6 +285,19 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // rows are swizzled like the store map (SWIZZLE_128B / SWIZZLE_64B) so that a quarter
         // warp's 16-byte stores hit all 32 banks.
         auto store_l0 = [&](const float* v, int col, int ncols) {
+            if (P.probe == 4) {                                // variant: 256-bit stores straight from registers
+                if (rows_valid > lane) {
+                    float* dst = P.vol0 + ((long long)b * P.N + row0 + lane) * P.NP + col;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        if (8 * g < ncols)
+                            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst + g * 8),
+                                         "f"(v[8 * g]), "f"(v[8 * g + 1]), "f"(v[8 * g + 2]), "f"(v[8 * g + 3]),
+                                         "f"(v[8 * g + 4]), "f"(v[8 * g + 5]), "f"(v[8 * g + 6]), "f"(v[8 * g + 7])
+                                         : "memory");
+                }
+                return;
+            }
             float* buf = sbuf + (use & 1u) * TC_STG_FLOATS;
             if (lane == 0) tma_wait_group_read<1>();           // the store that last read this buffer is done
             __syncwarp();

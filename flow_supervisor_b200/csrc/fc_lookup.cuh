@@ -8,6 +8,7 @@
 namespace fc {
 
 constexpr int QT = 32;            // queries per tile (one per lane)
+constexpr int FC_L2HINT_DEFAULT = 0;
 
 struct LookupParams {
     const float* pyr;
@@ -23,6 +24,8 @@ struct LookupParams {
     float inv_scale[FC_MAX_LEVELS];
     int probe;              // 0 in production; FLOWCORR_PROBE=n switches one pipeline stage off so that
                             // tools/probe_bounds.py can time the others (results are then garbage)
+    int l2hint;             // FLOWCORR_L2HINT bit mask (forward): 1 = coarsest level evict_last, 2 = level L-2 evict_last,
+                            // 4 = levels 0/1 evict_first, 8 = streaming (.cs) output stores
     int32_t* dbg_x0;
     int32_t* dbg_y0;
     uint8_t* dbg_mask;
@@ -43,6 +46,8 @@ inline void fill_params(LookupParams& P, const Pyramid& pyr, int radius) {
     P.N = pyr.N; P.L = pyr.L;
     const char* pr = getenv("FLOWCORR_PROBE");
     P.probe = pr ? atoi(pr) : 0;
+    const char* hn = getenv("FLOWCORR_L2HINT");
+    P.l2hint = hn ? atoi(hn) : FC_L2HINT_DEFAULT;
     const int R = 2 * radius + 1;
     P.K = pyr.L * R * R;
     for (int l = 0; l < pyr.L; ++l) {

@@ -107,8 +107,18 @@ __device__ __forceinline__ void lf_produce(const LookupParams& P, const LookupMa
         d.ybase = 2 * rp0; d.xbase = 8 * pc0; d.pitch = 64 * box_pc; d.valid = 1;
         if (P.probe != 1) {
             bytes = (uint32_t)(box_rp * box_pc * 64);
-            tma_load_3d(win + stage * LF_STAGE_BYTES + lane * LF_WIN_BYTES, &M.m[level][sel],
-                        smem_u32(&sh.full[stage]), 16 * pc0, rp0, q.gq);
+            // L2 residency across the GRU iterations: the coarse levels (a few tens of MB) are re-read by
+            // every lookup of the block and may stay; the fine levels stream through
+            const int from_top = P.L - 1 - level;
+            const bool keep = (from_top == 0 && (P.l2hint & 1)) || (from_top == 1 && (P.l2hint & 2));
+            const bool stream = level < 2 && from_top > 1 && (P.l2hint & 4);
+            const uint32_t dst = win + stage * LF_STAGE_BYTES + lane * LF_WIN_BYTES;
+            if (keep)
+                tma_load_3d_hint(dst, &M.m[level][sel], smem_u32(&sh.full[stage]), 16 * pc0, rp0, q.gq, l2_policy_evict_last());
+            else if (stream)
+                tma_load_3d_hint(dst, &M.m[level][sel], smem_u32(&sh.full[stage]), 16 * pc0, rp0, q.gq, l2_policy_evict_first());
+            else
+                tma_load_3d(dst, &M.m[level][sel], smem_u32(&sh.full[stage]), 16 * pc0, rp0, q.gq);
         }
     }
     if (mine) sh.desc[stage][lane] = d;
@@ -179,6 +189,7 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
                 for (int aa = 0; aa < APW; ++aa) hprev[aa] = fmaf(wx1[aa], v[aa + 1], wx0[aa] * v[aa]);
             }
             float* oj = outq;
+            const bool cs = (P.l2hint & 8) != 0;
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 rofs += step;
@@ -190,7 +201,9 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
                 for (int aa = 0; aa < APW; ++aa) {
                     const float hnext = fmaf(wx1[aa], v[aa + 1], wx0[aa] * v[aa]);
                     const float o = fmaf(wy1[j], hnext, wy0[j] * hprev[aa]);
-                    if (w * APW + aa < R && (P.probe != 2 || o == 1.2345678e30f)) oj[aa * sa] = o;
+                    if (w * APW + aa < R && (P.probe != 2 || o == 1.2345678e30f)) {
+                        if (cs) __stcs(oj + aa * sa, o); else oj[aa * sa] = o;
+                    }
                     hprev[aa] = hnext;
                 }
                 oj += P.N;

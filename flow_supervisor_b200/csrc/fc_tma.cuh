@@ -49,6 +49,25 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// the same load with an L2 eviction-priority policy (createpolicy.fractional.L2::evict_*)
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;\n" ::"r"(
+            smem_dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
 // shared -> global element-wise fp32 add of a box (out-of-bounds parts are dropped)
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
     asm volatile(

@@ -35,15 +35,38 @@ def timed(fn, reps=20, warm=5):
     return e0.elapsed_time(e1) / reps
 
 
+def hbm_rates():
+    """What the memory system gives a pure write / pure read / copy of the pyramid's size."""
+    n = 2_070_000_000 // 4
+    a = torch.empty(n, device="cuda")
+    b = torch.empty(n, device="cuda")
+    for name, fn, nbytes in (("write-only (fill_)", lambda: a.fill_(1.0), 4 * n),
+                             ("read-only (sum)", lambda: a.sum(), 4 * n),
+                             ("copy (read + write)", lambda: b.copy_(a), 8 * n)):
+        ms = timed(fn, reps=10, warm=3)
+        print(json.dumps({"kernel": "hbm " + name, "GB": nbytes / 1e9, "us": 1e3 * ms, "GB/s": nbytes / ms / 1e6}), flush=True)
+    del a, b
+
+
 def main():
+    hbm_rates()
     g = torch.Generator().manual_seed(0)
     B, H, W = 8, 55, 128
     f1 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
     f2 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
     cs = [(fsb.coords_grid(B, H, W) + 5.0 * torch.randn(B, 2, H, W, generator=g)).cuda() for _ in range(4)]
+    os.environ["FLOWCORR_PROBE"] = "0"
+    ref = ops.build(f1, f2, L, _lib.MATH_TC_3XBF16, _lib.VOL_F32)
+    os.environ["FLOWCORR_PROBE"] = "4"
+    alt = ops.build(f1, f2, L, _lib.MATH_TC_3XBF16, _lib.VOL_F32)
+    print(json.dumps({"check": "probe 4 pyramid bit-identical to the staged-store build", "mismatched_elements": int((ref != alt).sum()),
+                      "of": ref.numel()}),
+          flush=True)
+    del ref, alt
     for math, mname in ((_lib.MATH_TC_3XBF16, "3xbf16"), (_lib.MATH_TC_BF16, "bf16")):
         for probe, what in ((0, "real"), (1, "epilogue without global stores"), (2, "no MMAs issued"),
-                            (3, "epilogue neither reads TMEM nor stores"), (0, "real again")):
+                            (3, "epilogue neither reads TMEM nor stores"),
+                            (4, "level 0 stored from registers (correct results)"), (0, "real again")):
             os.environ["FLOWCORR_PROBE"] = str(probe)
             print(json.dumps({"kernel": "build (pack + tc_build)", "math": mname, "geometry": f"B={B} {H}x{W}",
                               "probe": probe, "what": what,
@@ -61,6 +84,13 @@ def main():
         os.environ["FLOWCORR_PROBE"] = str(probe)
         print(json.dumps({"kernel": "lookup_fwd", "geometry": f"B={B} {H}x{W}", "probe": probe, "what": what,
                           "us": 1e3 * timed(fwd)}), flush=True)
+    os.environ["FLOWCORR_PROBE"] = "0"
+    # L2 eviction-priority variants (FLOWCORR_L2HINT bit mask, fc_lookup.cuh); 12 lookups back to back like a step
+    for hint in (0, 1, 3, 5, 7, 9, 13, 15, 0):
+        os.environ["FLOWCORR_L2HINT"] = str(hint)
+        print(json.dumps({"kernel": "lookup_fwd", "geometry": f"B={B} {H}x{W}", "l2hint": hint,
+                          "us": 1e3 * timed(fwd, reps=36, warm=12)}), flush=True)
+    os.environ.pop("FLOWCORR_L2HINT")
     del pyr
     B, H, W = 6, 54, 128
     K = L * (2 * R + 1) ** 2
