@@ -13,12 +13,13 @@
 //                   into the same fp32 TMEM accumulator (error ~4e-6);
 //                   FC_MATH_TC_BF16 issues hi*hi only.  Two 256-column accumulators double
 //                   buffer the MMA against the epilogue.
-//   epilogue      : 4 warps, tcgen05.ld 32 lanes x 32 columns, scale by 1/sqrt(D), transpose
-//                   through shared memory so every global store instruction writes whole
-//                   128-byte rows of the (B*N, H, Wp) level-0 volume.
+//   epilogue      : 8 warps, tcgen05.ld 32 lanes x 32 columns, swizzled staging box + one TMA
+//                   tensor store per 32 queries x 128 bytes of level 0; levels 1-3 are pooled
+//                   thread-locally (bit-exact avg_pool2d) and leave as 32-byte runs.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 =
-// epilogue (TMEM lane quarter = warp_id % 4).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-3 idle,
+// warps 4-11 = epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter split the
+// tile's columns).
 #include <cstdlib>
 
 #include "fc_umma.cuh"
@@ -28,14 +29,15 @@ namespace fc {
 int simt_pool_levels(float* pyramid, const Pyramid& pyr, int first_level, cudaStream_t s);   // fc_simt.cu
 int simt_zero_pad_rows(float* pyramid, const Pyramid& pyr, int first, int last, cudaStream_t s);
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 384;          // warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4-11 epilogue
+constexpr int TC_FIRST_EPI_WARP = 4;
 constexpr int TC_BM = 128;           // queries per CTA (UMMA M)
 constexpr int TC_BK = 64;            // bf16 elements per 128-byte swizzle row
 constexpr int TC_STAGES = 4;
 constexpr int TC_STAGE_BYTES = 128 * TC_BK * 2;           // 16 KB: this CTA's half (<= 128 rows) of a target tile x 64 k
 constexpr int TC_ABLK_BYTES = TC_BM * TC_BK * 2;          // 16 KB per k-block of the query tile
 constexpr int TC_STG_FLOATS = 32 * 32;                    // one TMA-store box: [32 queries][32 floats] = 4 KB
-constexpr int TC_STG_BYTES = 4 * 2 * TC_STG_FLOATS * 4;   // 4 epilogue warps x 2 buffers = 32 KB
+constexpr int TC_STG_BYTES = 8 * TC_STG_FLOATS * 4;       // 8 epilogue warps x 1 buffer = 32 KB
 
 
 // ---------------------------------------------------------------- pack pre-pass
@@ -105,6 +107,12 @@ __global__ void __launch_bounds__(256) pack_bf16_kernel(const PackParams P) {
 }
 
 // ---------------------------------------------------------------- GEMM
+__device__ __forceinline__ void st_v8(float* dst, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
 struct TcStoreMaps {
     CUtensorMap l0_c32, l0_c16;    // level 0 as {NP, N, B}: boxes of 32 queries x 32 / 16 columns
 };
@@ -126,7 +134,7 @@ struct TcParams {
     float scale;           // 1 / sqrt(D)
     int probe;             // 0 in production; FLOWCORR_PROBE (tools/probe_bounds.py): 1 = epilogue without
                            // global stores, 2 = no MMAs issued, 3 = epilogue neither reads TMEM nor stores,
-                           // 4 = (correct results) level 0 stored from registers instead of staged TMA stores
+                           // 5 = pooled-level stores off, 6 = level-0 stores off, 7 = no target-operand loads
 };
 
 template <int KB>   // KB = D / 64 k-blocks
@@ -177,7 +185,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }   // 4 epilogue warps x 2 CTAs
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 16); }   // 8 epilogue warps x 2 CTAs
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -215,6 +223,10 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             const int s = it % TC_STAGES;
                             const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
                             mbar_wait(b_empty + s, ph ^ 1u);
+                            if (P.probe == 7) {                // no target loads (stage probe)
+                                if (leader) mbar_arrive(b_full + s);
+                                continue;
+                            }
                             if (leader) mbar_expect_tx(b_full + s, (uint32_t)(P.NT * TC_BK * 2));  // both halves
                             tma2_load_2d(ring + s * TC_STAGE_BYTES, part == 0 ? &map_b_hi : &map_b_lo, b_full + s,
                                          kb * TC_BK, row0);
@@ -265,216 +277,183 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 }
             }
         }
-    } else {
-        // ================= epilogue =================
+    } else if (warp >= TC_FIRST_EPI_WARP) {
+        // ================= epilogue (8 warps) =================
         // TMEM -> registers -> (scale, 2x2 pooling) -> shared staging -> TMA tensor store.
-        // A thread owns one query row; 32 accumulator columns = 4 groups of 8 floats that are
-        // contiguous in the query's map (patch layout).  The staging box [group][query][8] is
-        // what the store maps describe, so one elected lane writes 32 queries x 128 bytes with a
-        // single instruction; rows beyond the sample and groups beyond the map are clipped by
-        // the TMA unit.
-        const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32)
-        float* sbuf = stg + quarter * 2 * TC_STG_FLOATS;
-        int b = 0, row0 = 0, rows_valid = 0;                   // sample, first query row of this warp inside it
-        int tc = 0;                                            // running tile count: accumulator buffer / phase
+        // A thread owns one query row (TMEM lane quarter = warp % 4); the two warps of a quarter
+        // split the tile's 32-column chunks (half = first or second run of `CH` chunks), so every
+        // scheduler holds two epilogue warps and one warp's dependent-issue and TMA-store waits
+        // are covered by the other (one warp per scheduler ran at 0.17 IPC and bounded the
+        // kernel: profiles/r01f).  A chunk = 32 accumulator columns = 2 patches = 16 target
+        // columns x 2 rows = 128 contiguous bytes of the query's map.  The staging box
+        // [32 queries][32 floats] is what the store maps describe: one elected lane writes
+        // 32 queries x 128 bytes with a single instruction; rows beyond the sample are clipped
+        // by the TMA unit.
+        const int ew = warp - TC_FIRST_EPI_WARP;
+        const int quarter = warp & 3, half_id = ew >> 2;
+        float* sbuf = stg + ew * TC_STG_FLOATS;                // one 4 KB staging box per warp
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        uint32_t use = 0;
-
-        // level 0: this thread's columns [col, col + 32) (or 16 on the last chunk of a tile whose
-        // width is an odd multiple of 16) are 128 (64) contiguous bytes of its query's map.  Staging
-        // rows are swizzled like the store map (SWIZZLE_128B / SWIZZLE_64B) so that a quarter
-        // warp's 16-byte stores hit all 32 banks.
-        auto store_l0 = [&](const float* v, int col, int ncols) {
-            if (P.probe == 4) {                                // variant: 256-bit stores straight from registers
-                if (rows_valid > lane) {
-                    float* dst = P.vol0 + ((long long)b * P.N + row0 + lane) * P.NP + col;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g)
-                        if (8 * g < ncols)
-                            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst + g * 8),
-                                         "f"(v[8 * g]), "f"(v[8 * g + 1]), "f"(v[8 * g + 2]), "f"(v[8 * g + 3]),
-                                         "f"(v[8 * g + 4]), "f"(v[8 * g + 5]), "f"(v[8 * g + 6]), "f"(v[8 * g + 7])
-                                         : "memory");
-                }
-                return;
-            }
-            float* buf = sbuf + (use & 1u) * TC_STG_FLOATS;
-            if (lane == 0) tma_wait_group_read<1>();           // the store that last read this buffer is done
-            __syncwarp();
-            if (ncols >= 32) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    *reinterpret_cast<float4*>(buf + lane * 32 + ((c ^ (lane & 7)) << 2)) =
-                        make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    *reinterpret_cast<float4*>(buf + lane * 16 + ((c ^ ((lane >> 1) & 3)) << 2)) =
-                        make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            ++use;
-            if (lane == 0 && rows_valid > 0 && P.probe != 1) {
-                tma_store_3d(ncols >= 32 ? &SM.l0_c32 : &SM.l0_c16, smem_u32(buf), col, row0, b);
-                tma_commit_group();
-            }
-        };
-        // pooled levels (1/4, 1/16, 1/64 of the data): 32-byte runs straight from registers
-        auto store_small = [&](float* base, long long msz, long long off, int ncols, const float* v) {
-            if (rows_valid > lane && P.probe != 1) {
-                float* dst = base + ((long long)b * P.N + row0 + lane) * msz + off;
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    if (8 * g < ncols)
-                        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst + g * 16),
-                                     "f"(v[8 * g]), "f"(v[8 * g + 1]), "f"(v[8 * g + 2]), "f"(v[8 * g + 3]),
-                                     "f"(v[8 * g + 4]), "f"(v[8 * g + 5]), "f"(v[8 * g + 6]), "f"(v[8 * g + 7])
-                                     : "memory");
-            }
-        };
         const bool do_scale = P.scale != 1.0f;
+        const bool fused = P.n_fused > 1;
+        const int n_chunks = (P.NT + 31) >> 5;                 // chunks per full tile (the last may be 16 wide)
+        const int CH = n_chunks > 4 ? 4 : (n_chunks > 2 ? 2 : n_chunks);   // chunks per warp (even when split)
+        // chunk of this warp's cc-th slot.  Wide tiles: the two warps of a quarter alternate PAIRS of chunks
+        // ({0,1,4,5} / {2,3,6,7}) so that the four lines of a 512-byte run reach L2 close together;
+        // narrow tiles (<= 2 chunks): the second warp only keeps the barriers moving
+        const bool ilv = n_chunks > 4;
+        const int c_lo = (n_chunks > 2 || half_id == 0) ? half_id * CH : 8;
+        auto chunk_of = [&](int cc) { return ilv ? ((cc >> 1) * 4 + half_id * 2 + (cc & 1)) : (c_lo + cc); };
+        const int W1 = P.lvW[1], W2 = P.lvW[2], W3 = P.lvW[3];
+        const long long ms1 = (long long)P.lvHp[1] * P.lvWp[1];
+        const long long ms2 = (long long)P.lvHp[2] * P.lvWp[2], ms3 = (long long)P.lvHp[3] * P.lvWp[3];
+        int b = 0, tc = 0;
+        float s2[4][4], s3[4][2];                              // level-2 / level-3 partial sums across tiles
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s2[i][j] = 0.f;
+            s3[i][0] = s3[i][1] = 0.f;
+        }
 
-        if (P.n_fused <= 1) {
-            for (int u = u_begin; u < u_end; ++u) {
-              int m0, t0, t1;
-              decode(u, b, m0, t0, t1);
-              row0 = m0 + quarter * 32; rows_valid = P.N - row0;
-              for (int t = t0; t < t1; ++t, ++tc) {
-                const int buf = tc & 1;
-                mbar_wait(t_full + buf, (uint32_t)(tc >> 1) & 1u);
-                tc_fence_after();
-                const int q0 = t * P.NT;                       // first padded target of the tile
-                const int ncols = min(P.NT, P.NP - q0);
-                for (int c0 = 0; c0 < ncols; c0 += 32) {
+        for (int u = u_begin; u < u_end; ++u) {
+          int m0, t0, t1;
+          decode(u, b, m0, t0, t1);
+          const int row0 = m0 + quarter * 32;                  // first query row of this warp inside the sample
+          const int rows_valid = P.N - row0;
+          const bool mine = rows_valid > lane;
+          const long long qrow = (long long)b * P.N + row0 + lane;
+          for (int t = t0; t < t1; ++t, ++tc) {
+            const int buf = tc & 1;
+            mbar_wait(t_full + buf, (uint32_t)(tc >> 1) & 1u);
+            tc_fence_after();
+            const int q0 = t * P.NT;                           // first padded target of the tile
+            const int ncols = min(P.NT, P.NP - q0);
+            float l2[4][4];
+            if (P.probe != 3) {
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                const int c = chunk_of(cc);
+                if (cc < CH && c * 32 < ncols) {
                     float v[32];
-                    tmem_ld32(lane_addr + (uint32_t)(buf * 256 + c0), v);
+                    tmem_ld32(lane_addr + (uint32_t)(buf * 256 + c * 32), v);
                     tmem_ld_wait();
                     if (do_scale) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] *= P.scale;
                     }
-                    store_l0(v, q0 + c0, ncols - c0);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(t_empty + buf, 0);
-              }
-            }
-        } else {
-            // Fused pyramid.  Tile t = row pair t of THIS thread's query map in patch order:
-            // 32 TMEM columns = 2 patches = [row 2t: x0..7][row 2t+1: x0..7][row 2t: x8..15][...],
-            // so every 2x2 pooling quad is thread-local and inside one tcgen05.ld.  Levels 2 / 3
-            // combine two / four consecutive tiles through the stashes s2 / s3.  Summation
-            // order ((a + b) + c) + d, then * 0.25: bit-exact avg_pool2d of the level below
-            // (oracle/corr_spec.py::pool_pyramid).
-            const int Wp = P.Wp;
-            const int W1 = P.lvW[1], W2 = P.lvW[2], W3 = P.lvW[3];
-            const long long ms1 = (long long)P.lvHp[1] * P.lvWp[1];
-            const long long ms2 = (long long)P.lvHp[2] * P.lvWp[2], ms3 = (long long)P.lvHp[3] * P.lvWp[3];
-            float s2[32], s3[16];
-            for (int u = u_begin; u < u_end; ++u) {
-              int m0, t0, t1;
-              decode(u, b, m0, t0, t1);
-              row0 = m0 + quarter * 32; rows_valid = P.N - row0;
-              for (int t = t0; t < t1; ++t, ++tc) {
-                const int buf = tc & 1;
-                mbar_wait(t_full + buf, (uint32_t)(tc >> 1) & 1u);
-                tc_fence_after();
-                float l1[32], l2[32];
-                if (P.probe == 3) {
-                    tc_fence_before();
+                    // ---- level 0: staging (swizzled like the store map) -> TMA store
+                    const int rem = ncols - c * 32;
+                    if (lane == 0) tma_wait_group_read<0>();   // the store that last read this buffer is done
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(t_empty + buf, 0);
-                    continue;
-                }
+                    if (rem >= 32) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {                  // 32 TMEM columns = 16 target columns x 2 rows
-                    if (c * 32 < 2 * Wp) {
-                        float v[32];
-                        tmem_ld32(lane_addr + (uint32_t)(buf * 256 + c * 32), v);
-                        tmem_ld_wait();
-                        if (do_scale) {
+                        for (int k = 0; k < 8; ++k)
+                            *reinterpret_cast<float4*>(sbuf + lane * 32 + ((k ^ (lane & 7)) << 2)) =
+                                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                    } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] *= P.scale;
-                        }
-                        store_l0(v, t * 2 * Wp + c * 32, 2 * Wp - c * 32);
+                        for (int k = 0; k < 4; ++k)
+                            *reinterpret_cast<float4*>(sbuf + lane * 16 + ((k ^ ((lane >> 1) & 3)) << 2)) =
+                                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && rows_valid > 0 && P.probe != 1 && P.probe != 6) {
+                        tma_store_3d(rem >= 32 ? &SM.l0_c32 : &SM.l0_c16, smem_u32(sbuf), q0 + c * 32, row0, b);
+                        tma_commit_group();
+                    }
+                    if (fused) {
+                        // ---- level 1: row t, columns [8c, 8c + 8); ((a + b) + c) + d, then * 0.25:
+                        // bit-exact avg_pool2d of the level below (oracle/corr_spec.py::pool_pyramid)
+                        float l1[8];
 #pragma unroll
                         for (int pp = 0; pp < 2; ++pp)
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const float a = __fadd_rn(__fadd_rn(__fadd_rn(v[16 * pp + 2 * j], v[16 * pp + 2 * j + 1]),
                                                                     v[16 * pp + 8 + 2 * j]), v[16 * pp + 8 + 2 * j + 1]);
-                                l1[(c & 3) * 8 + 4 * pp + j] = (8 * c + 4 * pp + j < W1) ? a * 0.25f : 0.f;
+                                l1[4 * pp + j] = (8 * c + 4 * pp + j < W1) ? a * 0.25f : 0.f;
                             }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) l1[(c & 3) * 8 + j] = 0.f;
-                    }
-                    if ((c & 3) == 3 && (c - 3) * 32 < 2 * Wp) {
-                        const int g = c >> 2;                  // level-1 columns [32g, 32g + 32)
-                        if (t < P.lvH[1])
-                            store_small(P.lvl[1], ms1, (long long)(t >> 1) * 2 * P.lvWp[1] + g * 64 + (t & 1) * 8,
-                                        P.lvWp[1] - g * 32, l1);
+                        if (t < P.lvH[1] && 8 * c < P.lvWp[1] && mine && P.probe != 1 && P.probe != 5)
+                            st_v8(P.lvl[1] + qrow * ms1 + (long long)(t >> 1) * 2 * P.lvWp[1] + c * 16 + (t & 1) * 8, l1);
                         if (P.n_fused > 2) {
+                            if ((t & 1) == 0) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                if ((t & 1) == 0) {
-                                    s2[g * 16 + j] = __fadd_rn(l1[2 * j], l1[2 * j + 1]);
-                                } else {
-                                    const float a = __fadd_rn(__fadd_rn(s2[g * 16 + j], l1[2 * j]), l1[2 * j + 1]);
-                                    l2[g * 16 + j] = (g * 16 + j < W2) ? a * 0.25f : 0.f;
+                                for (int j = 0; j < 4; ++j) s2[cc][j] = __fadd_rn(l1[2 * j], l1[2 * j + 1]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float a = __fadd_rn(__fadd_rn(s2[cc][j], l1[2 * j]), l1[2 * j + 1]);
+                                    l2[cc][j] = (4 * c + j < W2) ? a * 0.25f : 0.f;
                                 }
                             }
                         }
-                    } else if ((c & 3) == 3) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) l2[(c >> 2) * 16 + j] = 0.f;
                     }
-                }
-                // all TMEM reads of this tile are done: hand the accumulator back early
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(t_empty + buf, 0);
-
-                if (P.n_fused > 2 && (t & 1)) {
-                    const int y2 = t >> 1;
-                    if (y2 < P.lvH[2])
-                        store_small(P.lvl[2], ms2, (long long)(y2 >> 1) * 2 * P.lvWp[2] + (y2 & 1) * 8, P.lvWp[2], l2);
-                    if (P.n_fused > 3) {
-                        float l3[32];
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if ((y2 & 1) == 0) {
-                                s3[j] = __fadd_rn(l2[2 * j], l2[2 * j + 1]);
-                                l3[j] = 0.f;
-                            } else {
-                                const float a = __fadd_rn(__fadd_rn(s3[j], l2[2 * j]), l2[2 * j + 1]);
-                                l3[j] = (j < W3) ? a * 0.25f : 0.f;
-                            }
-                            l3[16 + j] = 0.f;
-                        }
-                        const int y3 = t >> 2;
-                        if ((y2 & 1) && y3 < P.lvH[3])
-                            store_small(P.lvl[3], ms3, (long long)(y3 >> 1) * 2 * P.lvWp[3] + (y3 & 1) * 8, P.lvWp[3], l3);
-                    }
-                }
-                if (t == P.n_tiles - 1) {
-                    // pad row (y = Hl, Hl odd) of every pooled level: the lookup's TMA boxes read whole
-                    // row pairs, so it must hold zeros (the tile loop itself never produces it)
-                    float z[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) z[j] = 0.f;
-                    for (int l = 1; l < P.n_fused; ++l)
-                        if (P.lvHp[l] > P.lvH[l]) {
-                            const int y = P.lvH[l], wp = P.lvWp[l];
-                            for (int g = 0; g * 32 < wp; ++g)
-                                store_small(P.lvl[l], (long long)P.lvHp[l] * wp,
-                                            (long long)(y >> 1) * 2 * wp + g * 64 + (y & 1) * 8, wp - g * 32, z);
-                        }
+                    for (int j = 0; j < 4; ++j) l2[cc][j] = 0.f;
                 }
               }
             }
+            // all TMEM reads of this tile are done: hand the accumulator back early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(t_empty + buf, 0);
+
+            if (P.n_fused > 2 && (t & 1) && P.probe != 3) {
+                // ---- level 2: row y2 = t / 2, columns [4c, 4c + 4) per chunk -> 32-byte runs per chunk pair
+                const int y2 = t >> 1;
+                const bool st = mine && P.probe != 1 && P.probe != 5;
+#pragma unroll
+                for (int cp = 0; cp < 2; ++cp) {
+                    const int c = chunk_of(2 * cp);
+                    if (2 * cp < CH && y2 < P.lvH[2] && 4 * c < P.lvWp[2] && st) {
+                        const float o[8] = {l2[2 * cp][0], l2[2 * cp][1], l2[2 * cp][2], l2[2 * cp][3],
+                                            l2[2 * cp + 1][0], l2[2 * cp + 1][1], l2[2 * cp + 1][2], l2[2 * cp + 1][3]};
+                        st_v8(P.lvl[2] + qrow * ms2 + (long long)(y2 >> 1) * 2 * P.lvWp[2] + (c >> 1) * 16 + (y2 & 1) * 8, o);
+                    }
+                }
+                if (P.n_fused > 3) {
+                    // ---- level 3: row y3 = t / 4, columns [2c, 2c + 2) per chunk -> 16-byte runs per chunk pair
+                    const int y3 = t >> 2;
+                    if ((y2 & 1) == 0) {
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            s3[cc][0] = __fadd_rn(l2[cc][0], l2[cc][1]);
+                            s3[cc][1] = __fadd_rn(l2[cc][2], l2[cc][3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int cp = 0; cp < 2; ++cp) {
+                            const int c = chunk_of(2 * cp);
+                            float o[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int cc = 2 * cp + (i >> 1), j = i & 1;
+                                const float a = __fadd_rn(__fadd_rn(s3[cc][j], l2[cc][2 * j]), l2[cc][2 * j + 1]);
+                                o[i] = (2 * c + i < W3) ? a * 0.25f : 0.f;
+                            }
+                            // (narrow tiles: the one active warp also writes the zero pad columns 4..7 of the patch)
+                            if ((2 * cp < CH || n_chunks <= 2) && y3 < P.lvH[3] && 2 * c < P.lvWp[3] && st)
+                                *reinterpret_cast<float4*>(P.lvl[3] + qrow * ms3 + (long long)(y3 >> 1) * 2 * P.lvWp[3] +
+                                                           (c >> 2) * 16 + (y3 & 1) * 8 + ((c >> 1) & 1) * 4) =
+                                    make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                }
+            }
+            if (fused && t == P.n_tiles - 1 && mine && P.probe != 1 && P.probe != 5) {
+                // pad row (y = Hl, Hl odd) of every pooled level: the lookup's TMA boxes read whole
+                // row pairs, so it must hold zeros (the tile loop itself never produces it)
+                const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int l = 1; l < P.n_fused; ++l)
+                    if (P.lvHp[l] > P.lvH[l]) {
+                        const int y = P.lvH[l], wp = P.lvWp[l];
+                        float* rowp = P.lvl[l] + qrow * ((long long)P.lvHp[l] * wp) + (long long)(y >> 1) * 2 * wp + (y & 1) * 8;
+                        for (int g = half_id; g * 8 < wp; g += 2) st_v8(rowp + g * 16, z);
+                    }
+            }
+          }
         }
         if (lane == 0) tma_wait_group<0>();                    // staging is read and the stores have landed
         __syncwarp();

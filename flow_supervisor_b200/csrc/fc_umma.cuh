@@ -36,6 +36,13 @@ __device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* 
         "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma2_load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
