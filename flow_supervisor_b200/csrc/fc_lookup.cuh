@@ -8,7 +8,6 @@
 namespace fc {
 
 constexpr int QT = 32;            // queries per tile (one per lane)
-constexpr int FC_L2HINT_DEFAULT = 0;
 
 struct LookupParams {
     const float* pyr;
@@ -24,8 +23,7 @@ struct LookupParams {
     float inv_scale[FC_MAX_LEVELS];
     int probe;              // 0 in production; FLOWCORR_PROBE=n switches one pipeline stage off so that
                             // tools/probe_bounds.py can time the others (results are then garbage)
-    int l2hint;             // FLOWCORR_L2HINT bit mask (forward): 1 = coarsest level evict_last, 2 = level L-2 evict_last,
-                            // 4 = levels 0/1 evict_first, 8 = streaming (.cs) output stores
+    uint32_t div_m, div_s;  // gq / N without a division: (__umulhi(div_m, gq) + gq) >> div_s   (gq < 2^31)
     int32_t* dbg_x0;
     int32_t* dbg_y0;
     uint8_t* dbg_mask;
@@ -41,13 +39,23 @@ struct LookupMaps {
 int get_level_maps(LookupMaps& M, const float* pyramid, const Pyramid& pyr, int H, int W);
 int sm_count(int& n_sm);
 
+#ifdef __CUDACC__
+// sample index of global query gq (< 2^31) and its token inside the sample
+__device__ __forceinline__ void split_query(const LookupParams& P, int gq, int& b, int& p) {
+    b = (int)((__umulhi(P.div_m, (uint32_t)gq) + (uint32_t)gq) >> P.div_s);
+    p = gq - b * P.N;
+}
+#endif
+
 inline void fill_params(LookupParams& P, const Pyramid& pyr, int radius) {
     P.Q = pyr.B * pyr.N;
     P.N = pyr.N; P.L = pyr.L;
     const char* pr = getenv("FLOWCORR_PROBE");
     P.probe = pr ? atoi(pr) : 0;
-    const char* hn = getenv("FLOWCORR_L2HINT");
-    P.l2hint = hn ? atoi(hn) : FC_L2HINT_DEFAULT;
+    // Granlund-Montgomery round-up multiplier for the divisor N
+    P.div_s = 0;
+    while ((1ull << P.div_s) < (unsigned long long)pyr.N) ++P.div_s;
+    P.div_m = (uint32_t)(((1ull << 32) * ((1ull << P.div_s) - (unsigned long long)pyr.N)) / (unsigned long long)pyr.N + 1);
     const int R = 2 * radius + 1;
     P.K = pyr.L * R * R;
     for (int l = 0; l < pyr.L; ++l) {

@@ -1,7 +1,8 @@
 // Pyramid lookup FORWARD (CorrBlock.__call__, corr.py:29-50 + utils.py:57-65 + ATen
 // grid_sample(bilinear, zeros, align_corners=True)): the per-GRU-iteration HBM-bound gather.
 //
-// Persistent CTAs (one per SM) walk over tiles = (32 consecutive queries) x (one pyramid level).
+// Persistent CTAs (one per SM) walk over tiles = (32 consecutive queries) x (one pyramid level);
+// the level of a tile rotates with its query block so that every CTA sees all levels.
 // A query's footprint is ONE TMA tensor load: the level is described to the TMA unit as a
 // 3-D tensor [query][row pair][2*Wp floats] over the 2x8-patch layout (include/flowcorr.h),
 // and a box of {2|3 patches, 5|6 row pairs, 1 query} at signed coordinates lands the
@@ -57,18 +58,32 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     return v;
 }
 
-struct LfQuery { int level, gq; bool live, near_; float cx, cy; };
+// A CTA walks tiles first, first + stride, ...; tile = qt * L + level.  Roles step by a fixed
+// number of tiles, so (qt, level) advance by precomputed increments instead of a division per tile.
+struct TileIt {
+    int qt, slot, qm;       // tile t = qt * L + slot; qm = qt % L; the tile's level is (slot + qm) % L
+    // The rotation by qt makes consecutive tiles of a CTA (stride = grid size, usually a multiple of L) walk
+    // through the levels: the in-bounds share of a footprint (hence the DRAM bytes of a tile) differs per level,
+    // and a CTA pinned to one level would set the pace.
+    __device__ __forceinline__ int level(int L) const { const int l = slot + qm; return l >= L ? l - L : l; }
+    __device__ __forceinline__ void advance(int dq, int dl, int dqm, int L) {
+        qt += dq; slot += dl; qm += dqm;
+        if (slot >= L) { slot -= L; ++qt; ++qm; }
+        while (qm >= L) qm -= L;
+    }
+};
 
-template <int RADIUS, int CM>
-__device__ __forceinline__ LfQuery lf_load_query(const LookupParams& P, int tile, int lane) {
+struct LfQuery { int level, gq, b, p; bool live, near_; float cx, cy; };
+
+__device__ __forceinline__ LfQuery lf_load_query(const LookupParams& P, const TileIt& it, int lane) {
     LfQuery q;
-    q.level = tile % P.L;
-    q.gq = (tile / P.L) * QT + lane;
+    q.level = it.level(P.L);
+    q.gq = it.qt * QT + lane;
     q.live = q.gq < P.Q;
-    q.cx = 0.f; q.cy = 0.f;
+    q.cx = 0.f; q.cy = 0.f; q.b = 0; q.p = 0;
     if (q.live) {
-        const int b = q.gq / P.N, p = q.gq - b * P.N;
-        const float* c = P.coords + (long long)b * 2 * P.N + p;
+        split_query(P, q.gq, q.b, q.p);
+        const float* c = P.coords + (long long)q.b * 2 * P.N + q.p;
         q.cx = __ldg(c);                                             // raw: scaled by lf_finish_query,
         q.cy = __ldg(c + P.N);                                       // so a prefetch does not stall on the load
     }
@@ -87,10 +102,12 @@ __device__ __forceinline__ void lf_finish_query(const LookupParams& P, LfQuery& 
 // Producer: one warp issues the 32 footprint loads of a tile into ring stage `stage`.
 template <int RADIUS, int CM>
 __device__ __forceinline__ void lf_produce(const LookupParams& P, const LookupMaps& M, LfShared& sh,
-                                           uint32_t win, const LfQuery& q, int stage, int lane, int member) {
+                                           uint32_t win, const LfQuery& q, int stage, int lane, int member,
+                                           bool wait_empty, uint32_t empty_parity) {
     constexpr int R = 2 * RADIUS + 1;
     QueryDesc d{0, 0, 128, 0};
     uint32_t bytes = 0;
+    int sel = 0, c0 = 0, c1 = 0;
     const bool mine = (lane / (32 / LF_PSPLIT)) == member;          // this warp's share of the tile's queries
     if (q.near_ && mine) {
         const int level = q.level;
@@ -102,29 +119,51 @@ __device__ __forceinline__ void lf_produce(const LookupParams& P, const LookupMa
         const int rp0 = yl >> 1, pc0 = xl >> 3;                       // arithmetic shifts: floor
         const int n_rp = ((yh + 1) >> 1) - rp0 + 1;                   // <= 6 (taps are monotone, span <= R)
         const int n_pc = ((xh + 1) >> 3) - pc0 + 1;                   // <= 3
-        const int sel = (n_rp > 5 ? 2 : 0) + (n_pc > 2 ? 1 : 0);
+        sel = (n_rp > 5 ? 2 : 0) + (n_pc > 2 ? 1 : 0);
         const int box_rp = n_rp > 5 ? 6 : 5, box_pc = n_pc > 2 ? 3 : 2;
         d.ybase = 2 * rp0; d.xbase = 8 * pc0; d.pitch = 64 * box_pc; d.valid = 1;
-        if (P.probe != 1) {
-            bytes = (uint32_t)(box_rp * box_pc * 64);
-            // L2 residency across the GRU iterations: the coarse levels (a few tens of MB) are re-read by
-            // every lookup of the block and may stay; the fine levels stream through
-            const int from_top = P.L - 1 - level;
-            const bool keep = (from_top == 0 && (P.l2hint & 1)) || (from_top == 1 && (P.l2hint & 2));
-            const bool stream = level < 2 && from_top > 1 && (P.l2hint & 4);
-            const uint32_t dst = win + stage * LF_STAGE_BYTES + lane * LF_WIN_BYTES;
-            if (keep)
-                tma_load_3d_hint(dst, &M.m[level][sel], smem_u32(&sh.full[stage]), 16 * pc0, rp0, q.gq, l2_policy_evict_last());
-            else if (stream)
-                tma_load_3d_hint(dst, &M.m[level][sel], smem_u32(&sh.full[stage]), 16 * pc0, rp0, q.gq, l2_policy_evict_first());
-            else
-                tma_load_3d(dst, &M.m[level][sel], smem_u32(&sh.full[stage]), 16 * pc0, rp0, q.gq);
-        }
+        bytes = (uint32_t)(box_rp * box_pc * 64);
+        c0 = 16 * pc0; c1 = rp0;
     }
+    // the footprint arithmetic above ran while the stage was still being drained
+    if (wait_empty) mbar_wait(&sh.empty[stage], empty_parity);
+    if (P.probe & 2) bytes = 0;                                      // stage probe: no loads
+    if (bytes)
+        tma_load_3d(win + stage * LF_STAGE_BYTES + lane * LF_WIN_BYTES, &M.m[q.level][sel], smem_u32(&sh.full[stage]),
+                    c0, c1, q.gq);
     if (mine) sh.desc[stage][lane] = d;
     const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
     __syncwarp();
     if (lane == 0) mbar_expect_tx(&sh.full[stage], total);
+}
+
+// Debug outputs of one consumer thread: floor indices per tap and the 4 corner in-bounds predicates per sample.
+template <int RADIUS, int APW, bool DBG>
+__device__ __forceinline__ void lf_debug_out(const LookupParams& P, const LfQuery& q, int w, const int* x0, const int* y0) {
+    constexpr int R = 2 * RADIUS + 1;
+    if (!DBG || !q.live) return;
+    const int level = q.level, gq = q.gq;
+    const int Hl = P.H[level], Wl = P.W[level];
+    if (P.dbg_y0 != nullptr && w == 0) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) P.dbg_y0[((long long)gq * P.L + level) * R + j] = y0[j];
+    }
+#pragma unroll
+    for (int aa = 0; aa < APW; ++aa) {
+        const int a = w * APW + aa;
+        if (a >= R) break;
+        if (P.dbg_x0 != nullptr) P.dbg_x0[((long long)gq * P.L + level) * R + a] = x0[aa];
+        if (P.dbg_mask != nullptr) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const bool xa = (x0[aa] >= 0 && x0[aa] < Wl), xb = (x0[aa] + 1 >= 0 && x0[aa] + 1 < Wl);
+                const bool ya = (y0[j] >= 0 && y0[j] < Hl), yb = (y0[j] + 1 >= 0 && y0[j] + 1 < Hl);
+                uint8_t m = (uint8_t)((ya && xa) | ((ya && xb) << 1) | ((yb && xa) << 2) | ((yb && xb) << 3));
+                if (!q.near_) m = 0;
+                P.dbg_mask[(((long long)gq * P.L + level) * R + a) * R + j] = m;
+            }
+        }
+    }
 }
 
 // Consumer: warp `w` of a group interpolates x-offsets [w*APW, w*APW + APW) of the tile.
@@ -133,6 +172,7 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
                                            int stage, uint32_t parity, int lane, int w) {
     constexpr int R = 2 * RADIUS + 1;
     constexpr int APW = (R + LF_GWARPS - 1) / LF_GWARPS;             // x-offsets per warp
+    constexpr bool EVEN = (R % APW) == 0;                            // every warp owns APW valid x-offsets
     const int level = q.level, gq = q.gq;
 
     // tap arithmetic overlaps the loads in flight
@@ -142,7 +182,7 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
     int x0[APW]; float wx0[APW], wx1[APW];
 #pragma unroll
     for (int aa = 0; aa < APW; ++aa) {
-        const int a = min(w * APW + aa, R - 1);
+        const int a = EVEN ? w * APW + aa : min(w * APW + aa, R - 1);
         axis_tap<CM>(q.cx, a - RADIUS, P.ax[level], x0[aa], wx0[aa], wx1[aa]);
     }
     bool regular = true;
@@ -151,62 +191,74 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
 #pragma unroll
     for (int aa = 1; aa < APW; ++aa) regular = regular && (x0[aa] == x0[0] + aa);
 
-    const int b = q.live ? gq / P.N : 0, p = gq - b * P.N;
-    float* outq = P.io + ((long long)b * P.K + level * R * R + w * APW * R) * P.N + p;
-    const long long sa = (long long)R * P.N;                         // stride between x-offsets
+    // outputs of this thread: out[b][level*R*R + (w*APW + aa)*R + j][p] = outq[(aa*R + j) * N]
+    float* outq = P.io + ((long long)q.b * P.K + level * R * R + w * APW * R) * P.N + q.p;
+    const int N = P.N;
 
     mbar_wait(&sh.full[stage], parity);
     const QueryDesc d = sh.desc[stage][lane];
+    const uint32_t wq = win + stage * LF_STAGE_BYTES + lane * LF_WIN_BYTES;
+    const int pitch = d.pitch;
+    const bool fast = q.live && d.valid && regular;                  // this lane reads its sub-window on the fast path
+    // when no lane needs the per-tap slow path, the ring stage is handed back as soon as the
+    // sub-windows sit in registers: a stage is then busy for the loads only, not for the
+    // arithmetic and the stores
+    const bool early = !__any_sync(0xffffffffu, q.live && d.valid && !regular) && !(P.probe & 1);   // FLOWCORR_PROBE=1: late release (stage probe)
+
+    // horizontally interpolated (R + 1) x APW sub-window of a regular lane
+    float h[R + 1][APW];
+    if (fast) {
+        // byte addresses of window columns x0[0] .. x0[0]+APW (a patch jump every 8 columns)
+        uint32_t col[APW + 1];
+#pragma unroll
+        for (int i = 0; i <= APW; ++i) {
+            const int xr = min(max(x0[0] + i - d.xbase, 0), 23);
+            col[i] = wq + 4u * (uint32_t)(xr + (xr & ~7));
+        }
+        // footprint row n = y0[0] - ybase + r sits at (n >> 1) * pitch + (n & 1) * 32 bytes
+        const int n0 = min(max(y0[0] - d.ybase, 0), 1);
+        uint32_t rofs = 32u * n0;
+        uint32_t step = n0 ? (uint32_t)pitch - 32u : 32u;             // n even -> +32, n odd -> +pitch-32
+        float v[R + 1][APW + 1];
+#pragma unroll
+        for (int n = 0; n <= R; ++n) {
+#pragma unroll
+            for (int i = 0; i <= APW; ++i) v[n][i] = lds_f32(col[i] + rofs);
+            rofs += step;
+            step = (uint32_t)pitch - step;
+        }
+#pragma unroll
+        for (int n = 0; n <= R; ++n)
+#pragma unroll
+            for (int aa = 0; aa < APW; ++aa) h[n][aa] = fmaf(wx1[aa], v[n][aa + 1], wx0[aa] * v[n][aa]);
+    }
+    if (early) {
+        // The arrive must not overtake the shared loads: they drain through the LSU (bank conflicts make
+        // that take a while) whereas the barrier unit answers at once, and a refill racing them was
+        // observed.  h[R][APW-1] depends on the LAST load issued; a warp's shared loads return in order.
+        __syncwarp();
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];   // after %1\n" ::"r"(smem_u32(&sh.empty[stage])),
+                         "f"(fast ? h[R][APW - 1] : 0.f)
+                         : "memory");
+    }
 
     if (q.live) {
-        const uint32_t wq = win + stage * LF_STAGE_BYTES + lane * LF_WIN_BYTES;
-        const int pitch = d.pitch;
         if (!d.valid) {
 #pragma unroll
             for (int aa = 0; aa < APW; ++aa)
-                if (w * APW + aa < R) {
+                if (EVEN || w * APW + aa < R) {
 #pragma unroll
-                    for (int j = 0; j < R; ++j) outq[aa * sa + (long long)j * P.N] = 0.f;
+                    for (int j = 0; j < R; ++j) outq[(aa * R + j) * N] = 0.f;
                 }
         } else if (regular) {
-            // byte addresses of window columns x0[0] .. x0[0]+APW (a patch jump every 8 columns)
-            uint32_t col[APW + 1];
-#pragma unroll
-            for (int i = 0; i <= APW; ++i) {
-                const int xr = min(max(x0[0] + i - d.xbase, 0), 23);
-                col[i] = wq + 4u * (uint32_t)(xr + (xr & ~7));
-            }
-            // footprint row n = y0[0] - ybase + r sits at (n >> 1) * pitch + (n & 1) * 32 bytes
-            const int n0 = min(max(y0[0] - d.ybase, 0), 1);
-            uint32_t rofs = 32u * n0;
-            uint32_t step = n0 ? (uint32_t)pitch - 32u : 32u;         // n even -> +32, n odd -> +pitch-32
-            float hprev[APW];
-            {
-                float v[APW + 1];
-#pragma unroll
-                for (int i = 0; i <= APW; ++i) v[i] = lds_f32(col[i] + rofs);
-#pragma unroll
-                for (int aa = 0; aa < APW; ++aa) hprev[aa] = fmaf(wx1[aa], v[aa + 1], wx0[aa] * v[aa]);
-            }
-            float* oj = outq;
-            const bool cs = (P.l2hint & 8) != 0;
+            float* oj = outq;                                        // row j of every x-offset: oj[aa * R * N]
 #pragma unroll
             for (int j = 0; j < R; ++j) {
-                rofs += step;
-                step = (uint32_t)pitch - step;
-                float v[APW + 1];
 #pragma unroll
-                for (int i = 0; i <= APW; ++i) v[i] = lds_f32(col[i] + rofs);
-#pragma unroll
-                for (int aa = 0; aa < APW; ++aa) {
-                    const float hnext = fmaf(wx1[aa], v[aa + 1], wx0[aa] * v[aa]);
-                    const float o = fmaf(wy1[j], hnext, wy0[j] * hprev[aa]);
-                    if (w * APW + aa < R && (P.probe != 2 || o == 1.2345678e30f)) {
-                        if (cs) __stcs(oj + aa * sa, o); else oj[aa * sa] = o;
-                    }
-                    hprev[aa] = hnext;
-                }
-                oj += P.N;
+                for (int aa = 0; aa < APW; ++aa)
+                    if (EVEN || w * APW + aa < R) oj[aa * R * N] = fmaf(wy1[j], h[j + 1][aa], wy0[j] * h[j][aa]);
+                oj += N;
             }
         } else {
             // floor flips among the taps (lattice coordinates): every tap addressed on its own
@@ -215,7 +267,7 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
                 if (w * APW + aa >= R) break;
                 const int xa = min(max(x0[aa] - d.xbase, 0), 22), xb = xa + 1;
                 const uint32_t ca = wq + 4u * (uint32_t)(xa + (xa & ~7)), cb = wq + 4u * (uint32_t)(xb + (xb & ~7));
-                float* oa = outq + aa * sa;
+                float* oa = outq + aa * R * N;
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
                     const int ya = min(max(y0[j] - d.ybase, 0), 10), yb = ya + 1;
@@ -224,36 +276,16 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
                     const float top = fmaf(wx1[aa], lds_f32(cb + ra), wx0[aa] * lds_f32(ca + ra));
                     const float bot = fmaf(wx1[aa], lds_f32(cb + rb), wx0[aa] * lds_f32(ca + rb));
                     *oa = fmaf(wy1[j], bot, wy0[j] * top);
-                    oa += P.N;
-                }
-            }
-        }
-        if (DBG) {
-            const int Hl = P.H[level], Wl = P.W[level];
-            if (P.dbg_y0 != nullptr && w == 0) {
-#pragma unroll
-                for (int j = 0; j < R; ++j) P.dbg_y0[((long long)gq * P.L + level) * R + j] = y0[j];
-            }
-#pragma unroll
-            for (int aa = 0; aa < APW; ++aa) {
-                const int a = w * APW + aa;
-                if (a >= R) break;
-                if (P.dbg_x0 != nullptr) P.dbg_x0[((long long)gq * P.L + level) * R + a] = x0[aa];
-                if (P.dbg_mask != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < R; ++j) {
-                        const bool xa = (x0[aa] >= 0 && x0[aa] < Wl), xb = (x0[aa] + 1 >= 0 && x0[aa] + 1 < Wl);
-                        const bool ya = (y0[j] >= 0 && y0[j] < Hl), yb = (y0[j] + 1 >= 0 && y0[j] + 1 < Hl);
-                        uint8_t m = (uint8_t)((ya && xa) | ((ya && xb) << 1) | ((yb && xa) << 2) | ((yb && xb) << 3));
-                        if (!q.near_) m = 0;
-                        P.dbg_mask[(((long long)gq * P.L + level) * R + a) * R + j] = m;
-                    }
+                    oa += N;
                 }
             }
         }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sh.empty[stage]);
+    lf_debug_out<RADIUS, APW, DBG>(P, q, w, x0, y0);
+    if (!early) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.empty[stage]);
+    }
 }
 
 template <int RADIUS, int CM, bool DBG>
@@ -271,41 +303,35 @@ lookup_fwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, in
     __syncthreads();
 
     // tiles of this CTA: blockIdx.x, + gridDim.x, ...   (k-th local tile lives in stage k % LF_STAGES)
-    const int first = blockIdx.x, stride = gridDim.x;
+    const int first = blockIdx.x, stride = gridDim.x, L = P.L;
     const int n_local = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+    static_assert(LF_PTEAMS == LF_GROUPS, "producers and consumers step by the same number of tiles");
+    const int hop = LF_GROUPS * stride, hop_q = hop / L, hop_l = hop - hop_q * L, hop_qm = hop_q % L;   // tiles between two turns of a role
 
-    if (warp < LF_PRODUCERS) {
-        const int team = warp / LF_PSPLIT, member = warp - team * LF_PSPLIT;
-        int k = team;
-        if (k < n_local) {
-            LfQuery q = lf_load_query<RADIUS, CM>(P, first + k * stride, lane);
-            while (true) {
-                const int kn = k + LF_PTEAMS;
-                LfQuery qn = q;
-                if (kn < n_local) qn = lf_load_query<RADIUS, CM>(P, first + kn * stride, lane);   // prefetch coords
-                const int s = k % LF_STAGES;
-                if (k >= LF_STAGES) mbar_wait(&sh.empty[s], ((uint32_t)(k / LF_STAGES) & 1u) ^ 1u);
-                lf_finish_query(P, q);
-                lf_produce<RADIUS, CM>(P, M, sh, win, q, s, lane, member);
-                if (kn >= n_local) break;
-                k = kn; q = qn;
-            }
+    // role index r in [0, 3): local tiles r, r + 3, ...
+    const bool producer = warp < LF_PRODUCERS;
+    const int cw = warp - LF_PRODUCERS;
+    const int r = producer ? warp / LF_PSPLIT : cw / LF_GWARPS;
+    const int sub = producer ? warp - r * LF_PSPLIT : cw - r * LF_GWARPS;
+    int k = r;
+    if (k >= n_local) return;
+    TileIt it;
+    { const int t0 = first + k * stride; it.qt = t0 / L; it.slot = t0 - it.qt * L; it.qm = it.qt % L; }
+    LfQuery q = lf_load_query(P, it, lane);
+    while (true) {
+        const int kn = k + LF_GROUPS;
+        LfQuery qn = q;
+        if (kn < n_local) { it.advance(hop_q, hop_l, hop_qm, L); qn = lf_load_query(P, it, lane); }   // prefetch coords
+        const int s = k % LF_STAGES;
+        const uint32_t round = (uint32_t)(k / LF_STAGES);
+        lf_finish_query(P, q);
+        if (producer) {
+            lf_produce<RADIUS, CM>(P, M, sh, win, q, s, lane, sub, k >= LF_STAGES, (round & 1u) ^ 1u);
+        } else {
+            lf_consume<RADIUS, CM, DBG>(P, sh, win, q, s, round & 1u, lane, sub);
         }
-    } else {
-        const int cw = warp - LF_PRODUCERS, g = cw / LF_GWARPS, w = cw - g * LF_GWARPS;
-        int k = g;
-        if (k < n_local) {
-            LfQuery q = lf_load_query<RADIUS, CM>(P, first + k * stride, lane);
-            while (true) {
-                const int kn = k + LF_GROUPS;
-                LfQuery qn = q;
-                if (kn < n_local) qn = lf_load_query<RADIUS, CM>(P, first + kn * stride, lane);   // prefetch coords
-                lf_finish_query(P, q);
-                lf_consume<RADIUS, CM, DBG>(P, sh, win, q, k % LF_STAGES, (uint32_t)(k / LF_STAGES) & 1u, lane, w);
-                if (kn >= n_local) break;
-                k = kn; q = qn;
-            }
-        }
+        if (kn >= n_local) break;
+        k = kn; q = qn;
     }
 }
 

@@ -1,0 +1,5 @@
+set -x
+mkdir -p gpurun_out
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"lookup_fwd" -s 6 -c 1 \
+      -o gpurun_out/prof_lookup -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-rows > gpurun_out/ncu_lookup.log 2>&1
+tail -2 gpurun_out/ncu_lookup.log

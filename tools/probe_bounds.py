@@ -6,7 +6,7 @@ launch each stage accounts for.  Results of probed launches are garbage by const
   build    (cfg 2: B=8, 55x128):  0 = real, 1 = epilogue without global stores, 2 = no MMAs issued,
                                   3 = epilogue neither reads TMEM nor stores,
                                   5 = pooled-level stores off, 6 = level-0 stores off
-  forward  (cfg 2: B=8, 55x128):  0 = real, 1 = no footprint TMA loads, 2 = no output stores
+  forward  (cfg 2: B=8, 55x128):  timing only (its probes lived until r01f)
   backward (cfg 3 teacher: B=6, 54x128): 0 = real, 1 = no reduce-add, 2 = TMA store instead of reduce
 One JSON line per measurement."""
 import json
@@ -73,17 +73,9 @@ def main():
         it[0] += 1
         return ops.lookup(pyr, cs[it[0] % 4], L, R, _lib.COORD_CUDA)
 
-    for probe, what in ((0, "real"), (1, "no footprint loads"), (2, "no output stores"), (0, "real again")):
-        os.environ["FLOWCORR_PROBE"] = str(probe)
-        print(json.dumps({"kernel": "lookup_fwd", "geometry": f"B={B} {H}x{W}", "probe": probe, "what": what,
-                          "us": 1e3 * timed(fwd)}), flush=True)
-    os.environ["FLOWCORR_PROBE"] = "0"
-    # L2 eviction-priority variants (FLOWCORR_L2HINT bit mask, fc_lookup.cuh); 12 lookups back to back like a step
-    for hint in (0, 1, 3, 5, 7, 9, 13, 15, 0):
-        os.environ["FLOWCORR_L2HINT"] = str(hint)
-        print(json.dumps({"kernel": "lookup_fwd", "geometry": f"B={B} {H}x{W}", "l2hint": hint,
-                          "us": 1e3 * timed(fwd, reps=36, warm=12)}), flush=True)
-    os.environ.pop("FLOWCORR_L2HINT")
+    # (forward stage probes and L2 eviction hints were measured in r01f and then removed from the kernel:
+    #  profiles/r01f_stage_probes.jsonl)
+    print(json.dumps({"kernel": "lookup_fwd", "geometry": f"B={B} {H}x{W}", "us": 1e3 * timed(fwd, reps=36, warm=12)}), flush=True)
     del pyr
     B, H, W = 6, 54, 128
     K = L * (2 * R + 1) ** 2
