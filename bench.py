@@ -221,8 +221,11 @@ def run_reference(args, H, W):
         "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CorrBlock build + {args.iters} lookups, {H}x{W} tokens, D=256, L=4, r=4",
-                   "sample": f"{sample_b} pairs per step on CPU (GPU arm: {args.batch} per GPU)"},
+        "config": {"workload": f"CorrBlock build + {args.iters} lookups per pair, {args.height}x{args.width} px "
+                               f"-> {H}x{W} tokens, D={DIM}, L={LEVELS}, r={RADIUS}, batch {args.batch}/GPU",
+                   "math": "fp32 (torch CPU ops)", "volume": "f32",
+                   "sample": f"{sample_b} pairs per step on the host cores (bounded sample of the {args.batch}-pair batch)",
+                   "coords": "grid + N(0,5^2) 1/8-px flow"},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps x {sample_b} pairs, torch {torch.__version__} CPU ops"},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -57,14 +57,14 @@ struct LbTile {
     float gv[NT > 0 ? NT : 1][R];
     const float* gptr;
 
-    __device__ __forceinline__ void load(const LookupParams& P, int tile, int lane) {
-        level = tile % P.L;
-        gq = (tile / P.L) * QT + lane;
+    __device__ __forceinline__ void load(const LookupParams& P, const TileIt& it, int lane) {
+        level = it.level(P.L);
+        gq = it.qt * QT + lane;
         live = gq < P.Q;
         cx = 0.f; cy = 0.f;
         int b = 0, p = 0;
         if (live) {
-            b = gq / P.N; p = gq - b * P.N;
+            split_query(P, gq, b, p);
             const float* c = P.coords + (long long)b * 2 * P.N + p;
             cx = __ldg(c);
             cy = __ldg(c + P.N);
@@ -89,12 +89,16 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
     const int n_groups = gridDim.x * LB_GROUPS;
     int tile = blockIdx.x * LB_GROUPS + g;
     if (tile >= n_tiles) return;                                         // whole group leaves together
+    // tile = qt * L + slot, level = (slot + qt) % L: a group's tiles rotate through the levels (their cost differs)
+    const int L = P.L, hop_q = n_groups / L, hop_l = n_groups - hop_q * L, hop_qm = hop_q % L;
+    TileIt ti;
+    ti.qt = tile / L; ti.slot = tile - ti.qt * L; ti.qm = ti.qt % L;
     T cur;
-    cur.load(P, tile, lane);
+    cur.load(P, ti, lane);
     for (int it = 0;; ++it) {
         const int next = tile + n_groups;
         T nxt = cur;
-        if (next < n_tiles) nxt.load(P, next, lane);                     // in flight while this tile is processed
+        if (next < n_tiles) { ti.advance(hop_q, hop_l, hop_qm, L); nxt.load(P, ti, lane); }   // in flight while this tile is processed
 
         const int level = cur.level;
         const float cx = __fmul_rn(cur.cx, P.inv_scale[level]), cy = __fmul_rn(cur.cy, P.inv_scale[level]);

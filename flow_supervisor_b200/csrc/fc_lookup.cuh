@@ -47,6 +47,24 @@ __device__ __forceinline__ void split_query(const LookupParams& P, int gq, int& 
 }
 #endif
 
+#ifdef __CUDACC__
+// A role walks tiles t0, t0 + hop, ...; tile = qt * L + slot.  Roles step by a fixed
+// number of tiles, so (qt, level) advance by precomputed increments instead of a division per tile.
+struct TileIt {
+    int qt, slot, qm;       // tile t = qt * L + slot; qm = qt % L; the tile's level is (slot + qm) % L
+    // The rotation by qt makes consecutive tiles of a CTA (stride = grid size, usually a multiple of L) walk
+    // through the levels: the in-bounds share of a footprint (hence the DRAM bytes of a tile) differs per level,
+    // and a CTA pinned to one level would set the pace.
+    __device__ __forceinline__ int level(int L) const { const int l = slot + qm; return l >= L ? l - L : l; }
+    __device__ __forceinline__ void advance(int dq, int dl, int dqm, int L) {
+        qt += dq; slot += dl; qm += dqm;
+        if (slot >= L) { slot -= L; ++qt; ++qm; }
+        while (qm >= L) qm -= L;
+    }
+};
+
+#endif
+
 inline void fill_params(LookupParams& P, const Pyramid& pyr, int radius) {
     P.Q = pyr.B * pyr.N;
     P.N = pyr.N; P.L = pyr.L;

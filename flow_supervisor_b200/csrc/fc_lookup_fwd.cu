@@ -58,21 +58,6 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     return v;
 }
 
-// A CTA walks tiles first, first + stride, ...; tile = qt * L + level.  Roles step by a fixed
-// number of tiles, so (qt, level) advance by precomputed increments instead of a division per tile.
-struct TileIt {
-    int qt, slot, qm;       // tile t = qt * L + slot; qm = qt % L; the tile's level is (slot + qm) % L
-    // The rotation by qt makes consecutive tiles of a CTA (stride = grid size, usually a multiple of L) walk
-    // through the levels: the in-bounds share of a footprint (hence the DRAM bytes of a tile) differs per level,
-    // and a CTA pinned to one level would set the pace.
-    __device__ __forceinline__ int level(int L) const { const int l = slot + qm; return l >= L ? l - L : l; }
-    __device__ __forceinline__ void advance(int dq, int dl, int dqm, int L) {
-        qt += dq; slot += dl; qm += dqm;
-        if (slot >= L) { slot -= L; ++qt; ++qm; }
-        while (qm >= L) qm -= L;
-    }
-};
-
 struct LfQuery { int level, gq, b, p; bool live, near_; float cx, cy; };
 
 __device__ __forceinline__ LfQuery lf_load_query(const LookupParams& P, const TileIt& it, int lane) {
