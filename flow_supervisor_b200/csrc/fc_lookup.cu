@@ -130,7 +130,7 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
 
         // ---- the buffer used two tiles ago must have been read by its reduce-adds
         const uint32_t stage = gbase + (uint32_t)((it & 1) * LB_STAGE_BYTES);
-        if (WI == 0) tma_wait_group_read<LB_STAGES - 1>();
+        tma_wait_group_read<LB_STAGES - 1>();                            // every lane waits for its own reduce-adds
         group_sync(g);
 #pragma unroll
         for (int i = 0; i < LB_STAGE_BYTES / 16 / (32 * LB_GWARPS); ++i)
@@ -193,17 +193,17 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
         }
         fence_proxy_async_smem();
         group_sync(g);
-        if (WI == 0) {
-            if (touches && P.probe != 1) {
-                if (P.probe == 2) tma_store_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, cur.gq);
-                else tma_reduce_add_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, cur.gq);
-            }
-            tma_commit_group();
+        // every warp holds every query's box geometry: the 32 reduce-adds of the tile (one per lane, serialised
+        // by the hardware's uniform-operand issue) are dealt out over the group's three warps
+        if (touches && P.probe != 1 && (lane % LB_GWARPS) == WI) {
+            if (P.probe == 2) tma_store_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, cur.gq);
+            else tma_reduce_add_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, cur.gq);
         }
+        tma_commit_group();
         if (next >= n_tiles) break;
         tile = next; cur = nxt;
     }
-    if (WI == 0) tma_wait_group<0>();
+    tma_wait_group<0>();
 }
 
 template <int RADIUS, int CM>
