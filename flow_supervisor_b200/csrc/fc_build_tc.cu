@@ -8,8 +8,8 @@
 //                   pad entries come out as exact zeros.
 //   GEMM          : one CTA per (sample, 128-query tile).  The query operand (hi and lo, all
 //                   of K) stays resident in shared memory; target tiles of NT = 2 rows x Wp
-//                   (or 1 row when 2*Wp > 256) stream through a 4-stage TMA ring in
-//                   128-row x 64-k sub-stages.  FC_MATH_TC_3XBF16 issues hi*hi + lo*hi + hi*lo
+//                   (two tiles per row pair, split at a patch boundary, when 2*Wp > 256) stream
+//                   through a 4-stage TMA ring in 128-row x 64-k sub-stages.  FC_MATH_TC_3XBF16 issues hi*hi + lo*hi + hi*lo
 //                   into the same fp32 TMEM accumulator (error ~4e-6);
 //                   FC_MATH_TC_BF16 issues hi*hi only.  Two 256-column accumulators double
 //                   buffer the MMA against the epilogue.
@@ -124,11 +124,13 @@ struct TcParams {
     int W;                 // valid target columns of level 0
     float* vol0;           // level 0: (B*N, NP)
     int N, NP, H, Wp;      // queries per sample, padded targets per sample
-    int NT;                // padded targets per tile (multiple of 16, <= 256)
-    int n_tiles;           // ceil(NP / NT)
+    int halves;            // tiles per row pair: 1 (2 * Wp <= 256) or 2 (tile 0 = first NT targets of the row pair in patch
+                           // order = both rows x columns [0, NT / 2); tile 1 = the remaining 2 * Wp - NT)
+    int NT, NT2;           // targets (accumulator columns) of tile 0 / tile 1 of a row pair (multiples of 16, <= 256)
+    int n_rp;              // row pairs per map (Hp / 2)
     int m_tiles;           // ceil(N / 128)
     int mp;                // CTA pairs (256 query rows) per sample
-    int groups;            // groups of 4 consecutive target tiles per sample (the level-3 pooling period)
+    int groups;            // groups of 4 consecutive row pairs per sample (the level-3 pooling period)
     int units;             // B * mp * groups work units, split evenly over the resident CTA pairs
     int three_pass;        // 1 = hi*hi + lo*hi + hi*lo, 0 = hi*hi
     float scale;           // 1 / sqrt(D)
@@ -141,6 +143,7 @@ template <int KB>   // KB = D / 64 k-blocks
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const __grid_constant__ CUtensorMap map_b2_hi, const __grid_constant__ CUtensorMap map_b2_lo,
                 const __grid_constant__ TcStoreMaps SM, const TcParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve (all operand regions 1024-byte aligned for SWIZZLE_128B)
@@ -165,7 +168,6 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     // barriers are signalled in both CTAs by multicast commits.
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    const int half = P.NT / 2;                     // target rows of a tile held by each CTA
 
     // Persistent schedule: work unit u = (sample, query pair-tile, group of 4 target tiles), units
     // [u_begin, u_end) of this CTA pair are consecutive, so the resident query operand is
@@ -173,12 +175,12 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
     const int u_begin = (int)((long long)P.units * cluster_id / n_clusters);
     const int u_end = (int)((long long)P.units * (cluster_id + 1) / n_clusters);
-    auto decode = [&](int u, int& b, int& m0, int& t0, int& t1) {
+    auto decode = [&](int u, int& b, int& m0, int& t0, int& t1) {        // [t0, t1): ROW PAIRS of the unit
         const int am = u / P.groups, g = u - am * P.groups;
         b = am / P.mp;
         m0 = ((am - b * P.mp) * 2 + (int)rank) * TC_BM;
         t0 = 4 * g;
-        t1 = min(t0 + 4, P.n_tiles);
+        t1 = min(t0 + 4, P.n_rp);
     };
 
     if (threadIdx.x == 0) {
@@ -216,8 +218,10 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     ++a_use; cur_am = am;
                 }
                 // target operand: stages of [NT/2 rows][64 k], hi then lo of each k-block
-                for (int t = t0; t < t1; ++t) {
-                    const int row0 = b * P.NP + t * P.NT + (int)rank * half;
+                for (int h = 0; h < P.halves; ++h)                 // tile order of a unit: half 0 of its 4 row pairs, then half 1
+                  for (int rp = t0; rp < t1; ++rp) {
+                    const int ncols = h ? P.NT2 : P.NT;            // each CTA streams its half of the tile's targets
+                    const int row0 = b * P.NP + rp * 2 * P.Wp + h * P.NT + (int)rank * (ncols >> 1);
                     for (int kb = 0; kb < KB; ++kb)
                         for (int part = 0; part < n_parts; ++part, ++it) {
                             const int s = it % TC_STAGES;
@@ -227,17 +231,17 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                                 if (leader) mbar_arrive(b_full + s);
                                 continue;
                             }
-                            if (leader) mbar_expect_tx(b_full + s, (uint32_t)(P.NT * TC_BK * 2));  // both halves
-                            tma2_load_2d(ring + s * TC_STAGE_BYTES, part == 0 ? &map_b_hi : &map_b_lo, b_full + s,
-                                         kb * TC_BK, row0);
+                            if (leader) mbar_expect_tx(b_full + s, (uint32_t)(ncols * TC_BK * 2));  // both halves
+                            const CUtensorMap* mp = part == 0 ? (h ? &map_b2_hi : &map_b_hi) : (h ? &map_b2_lo : &map_b_lo);
+                            tma2_load_2d(ring + s * TC_STAGE_BYTES, mp, b_full + s, kb * TC_BK, row0);
                         }
-                }
+                  }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA only) =================
         if (lane == 0 && leader) {
-            const uint32_t idesc = umma_idesc_bf16(2 * TC_BM, P.NT);
+            const uint32_t idesc0 = umma_idesc_bf16(2 * TC_BM, P.NT), idesc1 = umma_idesc_bf16(2 * TC_BM, P.NT2 > 0 ? P.NT2 : P.NT);
             int it = 0, tc = 0, a_use = 0, cur_am = -1;
             for (int u = u_begin; u < u_end; ++u) {
                 int b, m0, t0, t1;
@@ -249,7 +253,8 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     tc_fence_after();
                     ++a_use; cur_am = am;
                 }
-                for (int t = t0; t < t1; ++t, ++tc) {
+                for (int tt = 0; tt < (t1 - t0) * P.halves; ++tt, ++tc) {
+                    const uint32_t idesc = tt >= (t1 - t0) ? idesc1 : idesc0;      // second run of the unit = half 1
                     const int buf = tc & 1;
                     mbar_wait(t_empty + buf, ((uint32_t)(tc >> 1) & 1u) ^ 1u);
                     tc_fence_after();
@@ -295,44 +300,43 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const bool do_scale = P.scale != 1.0f;
         const bool fused = P.n_fused > 1;
-        const int n_chunks = (P.NT + 31) >> 5;                 // chunks per full tile (the last may be 16 wide)
-        const int CH = n_chunks > 4 ? 4 : (n_chunks > 2 ? 2 : n_chunks);   // chunks per warp (even when split)
-        // chunk of this warp's cc-th slot.  Wide tiles: the two warps of a quarter alternate PAIRS of chunks
-        // ({0,1,4,5} / {2,3,6,7}) so that the four lines of a 512-byte run reach L2 close together;
-        // narrow tiles (<= 2 chunks): the second warp only keeps the barriers moving
-        const bool ilv = n_chunks > 4;
-        const int c_lo = (n_chunks > 2 || half_id == 0) ? half_id * CH : 8;
-        auto chunk_of = [&](int cc) { return ilv ? ((cc >> 1) * 4 + half_id * 2 + (cc & 1)) : (c_lo + cc); };
         const int W1 = P.lvW[1], W2 = P.lvW[2], W3 = P.lvW[3];
         const long long ms1 = (long long)P.lvHp[1] * P.lvWp[1];
         const long long ms2 = (long long)P.lvHp[2] * P.lvWp[2], ms3 = (long long)P.lvHp[3] * P.lvWp[3];
         int b = 0, tc = 0;
-        float s2[4][4], s3[4][2];                              // level-2 / level-3 partial sums across tiles
+        float s2[4][4], s3[4][2];                              // level-2 / level-3 partial sums across the row pairs of a run
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) s2[i][j] = 0.f;
             s3[i][0] = s3[i][1] = 0.f;
         }
+        int row0 = 0, rows_valid = 0;                          // first query row of this warp inside the sample
+        bool mine = false;
+        long long qrow = 0;
 
-        for (int u = u_begin; u < u_end; ++u) {
-          int m0, t0, t1;
-          decode(u, b, m0, t0, t1);
-          const int row0 = m0 + quarter * 32;                  // first query row of this warp inside the sample
-          const int rows_valid = P.N - row0;
-          const bool mine = rows_valid > lane;
-          const long long qrow = (long long)b * P.N + row0 + lane;
-          for (int t = t0; t < t1; ++t, ++tc) {
+        // One tile = half H of row pair rp (the whole row pair when 2 * Wp <= 256).  A unit walks half 0 of its four
+        // row pairs, then half 1, so one set of stashes serves both.
+        auto tile_body = [&](const int H, int rp) {
             const int buf = tc & 1;
             mbar_wait(t_full + buf, (uint32_t)(tc >> 1) & 1u);
             tc_fence_after();
-            const int q0 = t * P.NT;                           // first padded target of the tile
-            const int ncols = min(P.NT, P.NP - q0);
+            const int q0 = rp * 2 * P.Wp + H * P.NT;           // first padded target of the tile
+            const int ncols = H ? P.NT2 : P.NT;
+            const int n_chunks = (ncols + 31) >> 5;            // 32-column chunks of the tile (the last may be 16 wide)
+            const int CH = n_chunks > 4 ? 4 : (n_chunks > 2 ? 2 : n_chunks);   // chunks per warp (even when split)
+            // chunk of this warp's cc-th slot.  Wide tiles: the two warps of a quarter alternate PAIRS of chunks
+            // ({0,1,4,5} / {2,3,6,7}) so that the four lines of a 512-byte run reach L2 close together;
+            // narrow tiles (<= 2 chunks): the second warp only keeps the barriers moving
+            const bool ilv = n_chunks > 4;
+            const int c_lo = (n_chunks > 2 || half_id == 0) ? half_id * CH : 8;
+            auto chunk_of = [&](int cc) { return ilv ? ((cc >> 1) * 4 + half_id * 2 + (cc & 1)) : (c_lo + cc); };
             float l2[4][4];
             if (P.probe != 3) {
 #pragma unroll
               for (int cc = 0; cc < 4; ++cc) {
-                const int c = chunk_of(cc);
+                const int c = chunk_of(cc);                    // chunk inside the tile
+                const int gc = H * (P.NT >> 5) + c;                      // chunk inside the row pair: level-0 columns [16 gc, 16 gc + 16)
                 if (cc < CH && c * 32 < ncols) {
                     float v[32];
                     tmem_ld32(lane_addr + (uint32_t)(buf * 256 + c * 32), v);
@@ -363,7 +367,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         tma_commit_group();
                     }
                     if (fused) {
-                        // ---- level 1: row t, columns [8c, 8c + 8); ((a + b) + c) + d, then * 0.25:
+                        // ---- level 1: row rp, columns [8 gc, 8 gc + 8); ((a + b) + c) + d, then * 0.25:
                         // bit-exact avg_pool2d of the level below (oracle/corr_spec.py::pool_pyramid)
                         float l1[8];
 #pragma unroll
@@ -372,19 +376,19 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             for (int j = 0; j < 4; ++j) {
                                 const float a = __fadd_rn(__fadd_rn(__fadd_rn(v[16 * pp + 2 * j], v[16 * pp + 2 * j + 1]),
                                                                     v[16 * pp + 8 + 2 * j]), v[16 * pp + 8 + 2 * j + 1]);
-                                l1[4 * pp + j] = (8 * c + 4 * pp + j < W1) ? a * 0.25f : 0.f;
+                                l1[4 * pp + j] = (8 * gc + 4 * pp + j < W1) ? a * 0.25f : 0.f;
                             }
-                        if (t < P.lvH[1] && 8 * c < P.lvWp[1] && mine && P.probe != 1 && P.probe != 5)
-                            st_v8(P.lvl[1] + qrow * ms1 + (long long)(t >> 1) * 2 * P.lvWp[1] + c * 16 + (t & 1) * 8, l1);
+                        if (rp < P.lvH[1] && 8 * gc < P.lvWp[1] && mine && P.probe != 1 && P.probe != 5)
+                            st_v8(P.lvl[1] + qrow * ms1 + (long long)(rp >> 1) * 2 * P.lvWp[1] + gc * 16 + (rp & 1) * 8, l1);
                         if (P.n_fused > 2) {
-                            if ((t & 1) == 0) {
+                            if ((rp & 1) == 0) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) s2[cc][j] = __fadd_rn(l1[2 * j], l1[2 * j + 1]);
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     const float a = __fadd_rn(__fadd_rn(s2[cc][j], l1[2 * j]), l1[2 * j + 1]);
-                                    l2[cc][j] = (4 * c + j < W2) ? a * 0.25f : 0.f;
+                                    l2[cc][j] = (4 * gc + j < W2) ? a * 0.25f : 0.f;
                                 }
                             }
                         }
@@ -400,22 +404,22 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(t_empty + buf, 0);
 
-            if (P.n_fused > 2 && (t & 1) && P.probe != 3) {
-                // ---- level 2: row y2 = t / 2, columns [4c, 4c + 4) per chunk -> 32-byte runs per chunk pair
-                const int y2 = t >> 1;
+            if (P.n_fused > 2 && (rp & 1) && P.probe != 3) {
+                // ---- level 2: row y2 = rp / 2, columns [4 gc, 4 gc + 4) per chunk -> 32-byte runs per chunk pair
+                const int y2 = rp >> 1;
                 const bool st = mine && P.probe != 1 && P.probe != 5;
 #pragma unroll
                 for (int cp = 0; cp < 2; ++cp) {
-                    const int c = chunk_of(2 * cp);
-                    if (2 * cp < CH && y2 < P.lvH[2] && 4 * c < P.lvWp[2] && st) {
+                    const int gc = H * (P.NT >> 5) + chunk_of(2 * cp);
+                    if (2 * cp < CH && y2 < P.lvH[2] && 4 * gc < P.lvWp[2] && st) {
                         const float o[8] = {l2[2 * cp][0], l2[2 * cp][1], l2[2 * cp][2], l2[2 * cp][3],
                                             l2[2 * cp + 1][0], l2[2 * cp + 1][1], l2[2 * cp + 1][2], l2[2 * cp + 1][3]};
-                        st_v8(P.lvl[2] + qrow * ms2 + (long long)(y2 >> 1) * 2 * P.lvWp[2] + (c >> 1) * 16 + (y2 & 1) * 8, o);
+                        st_v8(P.lvl[2] + qrow * ms2 + (long long)(y2 >> 1) * 2 * P.lvWp[2] + (gc >> 1) * 16 + (y2 & 1) * 8, o);
                     }
                 }
                 if (P.n_fused > 3) {
-                    // ---- level 3: row y3 = t / 4, columns [2c, 2c + 2) per chunk -> 16-byte runs per chunk pair
-                    const int y3 = t >> 2;
+                    // ---- level 3: row y3 = rp / 4, columns [2 gc, 2 gc + 2) per chunk -> 16-byte runs per chunk pair
+                    const int y3 = rp >> 2;
                     if ((y2 & 1) == 0) {
 #pragma unroll
                         for (int cc = 0; cc < 4; ++cc) {
@@ -425,24 +429,24 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     } else {
 #pragma unroll
                         for (int cp = 0; cp < 2; ++cp) {
-                            const int c = chunk_of(2 * cp);
+                            const int gc = H * (P.NT >> 5) + chunk_of(2 * cp);
                             float o[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int cc = 2 * cp + (i >> 1), j = i & 1;
                                 const float a = __fadd_rn(__fadd_rn(s3[cc][j], l2[cc][2 * j]), l2[cc][2 * j + 1]);
-                                o[i] = (2 * c + i < W3) ? a * 0.25f : 0.f;
+                                o[i] = (2 * gc + i < W3) ? a * 0.25f : 0.f;
                             }
                             // (narrow tiles: the one active warp also writes the zero pad columns 4..7 of the patch)
-                            if ((2 * cp < CH || n_chunks <= 2) && y3 < P.lvH[3] && 2 * c < P.lvWp[3] && st)
+                            if ((2 * cp < CH || n_chunks <= 2) && y3 < P.lvH[3] && 2 * gc < P.lvWp[3] && st)
                                 *reinterpret_cast<float4*>(P.lvl[3] + qrow * ms3 + (long long)(y3 >> 1) * 2 * P.lvWp[3] +
-                                                           (c >> 2) * 16 + (y3 & 1) * 8 + ((c >> 1) & 1) * 4) =
+                                                           (gc >> 2) * 16 + (y3 & 1) * 8 + ((gc >> 1) & 1) * 4) =
                                     make_float4(o[0], o[1], o[2], o[3]);
                         }
                     }
                 }
             }
-            if (fused && t == P.n_tiles - 1 && mine && P.probe != 1 && P.probe != 5) {
+            if (fused && rp == P.n_rp - 1 && H == P.halves - 1 && mine && P.probe != 1 && P.probe != 5) {
                 // pad row (y = Hl, Hl odd) of every pooled level: the lookup's TMA boxes read whole
                 // row pairs, so it must hold zeros (the tile loop itself never produces it)
                 const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -453,7 +457,18 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         for (int g = half_id; g * 8 < wp; g += 2) st_v8(rowp + g * 16, z);
                     }
             }
-          }
+            ++tc;
+        };
+
+        for (int u = u_begin; u < u_end; ++u) {
+            int m0, t0, t1;
+            decode(u, b, m0, t0, t1);
+            row0 = m0 + quarter * 32;
+            rows_valid = P.N - row0;
+            mine = rows_valid > lane;
+            qrow = (long long)b * P.N + row0 + lane;
+            for (int h = 0; h < P.halves; ++h)
+                for (int rp = t0; rp < t1; ++rp) tile_body(h, rp);
         }
         if (lane == 0) tma_wait_group<0>();                    // staging is read and the stores have landed
         __syncwarp();
@@ -537,7 +552,7 @@ static int launch_tc(const CUtensorMap* maps, const TcStoreMaps& SM, const TcPar
     if (n_clusters < 1) { set_error("fc_build: no CTA pair of the tensor-core kernel fits on this device"); return FC_ECUDA; }
     if (n_clusters > P.units) n_clusters = P.units;
     dim3 grid(2 * n_clusters);
-    tc_build_kernel<KB><<<grid, TC_THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], SM, P);
+    tc_build_kernel<KB><<<grid, TC_THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], SM, P);
     FC_LAUNCH_CHECK("tc_build_kernel");
     return FC_OK;
 }
@@ -585,29 +600,35 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     P.vol0 = static_cast<float*>(pyramid) + pyr.lv[0].offset;
     P.W = W;
     // the epilogue produces the pyramid itself when a tile holds two whole target rows
-    const bool fuse = (2 * Wp <= 256) && pyr.L >= 2 && getenv("FLOWCORR_NO_FUSE") == nullptr;
+    const bool fuse = pyr.L >= 2 && getenv("FLOWCORR_NO_FUSE") == nullptr;
     P.n_fused = fuse ? (pyr.L < 4 ? pyr.L : 4) : 1;
     for (int l = 0; l < 4 && l < pyr.L; ++l) {
         P.lvl[l] = static_cast<float*>(pyramid) + pyr.lv[l].offset;
         P.lvH[l] = pyr.lv[l].H; P.lvW[l] = pyr.lv[l].W; P.lvWp[l] = pyr.lv[l].Wp; P.lvHp[l] = pyr.lv[l].Hp;
     }
     P.N = N; P.NP = (int)NP; P.H = H; P.Wp = Wp;
-    P.NT = (2 * Wp <= 256) ? 2 * Wp : Wp;
-    if (P.NT % 16 != 0) P.NT = round_up(P.NT, 16);     // single-row tile with Wp % 16 == 8: over-read 8 targets, masked at the store
-    P.n_tiles = (int)((NP + P.NT - 1) / P.NT);
+    // a tile = a row pair in patch order (both rows of every 8-column patch), split in two when it exceeds the 256
+    // accumulator columns of an MMA; the split keeps whole patches together, so pooling stays thread-local
+    P.halves = (2 * Wp <= 256) ? 1 : 2;
+    P.NT = (P.halves == 1) ? 2 * Wp : (2 * Wp - 256 >= 32 ? 256 : 192);   // (no 16-column MMA: N >= 32 for M = 256)
+    P.NT2 = (P.halves == 1) ? 0 : 2 * Wp - P.NT;
+    P.n_rp = pyr.lv[0].Hp / 2;
     P.m_tiles = (N + TC_BM - 1) / TC_BM;
     P.mp = (P.m_tiles + 1) / 2;
-    P.groups = (P.n_tiles + 3) / 4;
+    P.groups = (P.n_rp + 3) / 4;
     P.units = B * P.mp * P.groups;
     P.three_pass = three ? 1 : 0;
     P.scale = fold_scale ? 1.0f : inv_sqrt_d;
     { const char* pr = getenv("FLOWCORR_PROBE"); P.probe = pr ? atoi(pr) : 0; }
 
-    CUtensorMap maps[4];
+    CUtensorMap maps[6];
     if (int e = make_map(&maps[0], a_hi, (long long)B * N, D, TC_BM, TC_BK)) return e;
     if (int e = make_map(&maps[1], three ? a_lo : a_hi, (long long)B * N, D, TC_BM, TC_BK)) return e;
     if (int e = make_map(&maps[2], b_hi, (long long)B * NP, D, P.NT / 2, TC_BK)) return e;
     if (int e = make_map(&maps[3], three ? b_lo : b_hi, (long long)B * NP, D, P.NT / 2, TC_BK)) return e;
+    const int box2 = (P.halves == 2 ? P.NT2 : P.NT) / 2;               // second tile of a row pair: its own (narrower) box
+    if (int e = make_map(&maps[4], b_hi, (long long)B * NP, D, box2, TC_BK)) return e;
+    if (int e = make_map(&maps[5], three ? b_lo : b_hi, (long long)B * NP, D, box2, TC_BK)) return e;
 
     // store maps (see the epilogue)
     TcStoreMaps SM;

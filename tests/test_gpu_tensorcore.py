@@ -12,7 +12,8 @@ from oracle import corr_spec
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(1, 256, 46, 62), (2, 256, 55, 128), (1, 64, 17, 19), (1, 256, 47, 156), (2, 128, 16, 24),
-          (1, 256, 24, 132)]
+          (1, 256, 24, 132),                  # row pairs split 192 + 80 accumulator columns
+          (1, 64, 19, 240), (1, 64, 10, 250)]   # cfg 5 width (256 + 224) and the widest map (256 + 256)
 
 
 @pytest.fixture(scope="module")
