@@ -365,6 +365,9 @@ def main():
                 "bytes_per_launch": lb, "bytes_nominal": lookup_bytes(B, H, W), "ms_per_launch": look_ms,
                 "share_of_step": iters * look_ms / ms_step}
         look["frac"] = look["achieved"] / hbm
+        # what HBM3e gives this kernel's READ pattern (scattered 128-byte runs of 64-byte patches) with unlimited
+        # parallelism, measured by tools/probes/gather_pattern.cu on this pool's B200 (profiles/r01h_gather_pattern_probe.jsonl)
+        look["pattern_ceiling"] = {"reads_gbs": 4232.0, "source": "profiles/r01h_gather_pattern_probe.jsonl"}
         N = H * W
         flop = 2.0 * B * N * N * DIM
         pyr_bytes, _ = _lib.pyramid_layout(B, H, W, LEVELS, _lib.VOL_F32)
@@ -373,7 +376,8 @@ def main():
         bld_bytes = pyr_bytes + 2 * B * DIM * N * 4
         issued = flop * (3 if math_id == _lib.MATH_TC_3XBF16 else 1)
         t_mma, t_hbm = flop / (tf_sust * 1e12), bld_bytes / (hbm * 1e9)
-        bld = {"kernel": "build (gemm + pyramid)", "peak_source": peak_src,
+        bld = {"kernel": "build (gemm + pyramid)", "launches": ["pack_bf16_kernel", "tc_build_kernel"] if math_id else ["simt"],
+               "peak_source": peak_src,
                "traffic": ncu_traffic("tc_build_kernel") if math_id else None,
                "ms_per_launch": build_ms, "share_of_step": build_ms / ms_step,
                "bytes_per_launch": bld_bytes, "flop_per_launch": flop, "flop_issued": issued,

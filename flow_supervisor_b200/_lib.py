@@ -11,7 +11,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflowcorr.so")
+LIB_PATH = os.environ.get("FLOWCORR_LIB") or os.path.join(_HERE, "libflowcorr.so")   # FLOWCORR_LIB: A/B builds (tools/)
 
 # enums of include/flowcorr.h
 VOL_F32, VOL_BF16 = 0, 1

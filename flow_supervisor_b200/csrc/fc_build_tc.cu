@@ -33,7 +33,10 @@ constexpr int TC_THREADS = 384;          // warp 0 TMA, warp 1 MMA, warps 2-3 id
 constexpr int TC_FIRST_EPI_WARP = 4;
 constexpr int TC_BM = 128;           // queries per CTA (UMMA M)
 constexpr int TC_BK = 64;            // bf16 elements per 128-byte swizzle row
-constexpr int TC_STAGES = 4;
+#ifndef FC_TC_STAGES
+#define FC_TC_STAGES 4
+#endif
+constexpr int TC_STAGES = FC_TC_STAGES;
 constexpr int TC_STAGE_BYTES = 128 * TC_BK * 2;           // 16 KB: this CTA's half (<= 128 rows) of a target tile x 64 k
 constexpr int TC_ABLK_BYTES = TC_BM * TC_BK * 2;          // 16 KB per k-block of the query tile
 constexpr int TC_STG_FLOATS = 32 * 32;                    // one TMA-store box: [32 queries][32 floats] = 4 KB
