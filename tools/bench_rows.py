@@ -185,6 +185,44 @@ def row_ondemand(B, H, W, reps):
     emit(**line)
 
 
+def row_same_gpu(B, Himg, Wimg, reps, iters=12):
+    """Standalone only (imports oracle/): the reference's own PyTorch path (matmul + avg_pool2d + grid_sample,
+    oracle/corr_torch.py = corr.py's library calls) ON THIS GPU next to the drop-in block, for the bare correlation
+    path and inside the whole RAFT forward (oracle/raft_model.py, random init, BASELINE.json configs[1] geometry)."""
+    from oracle import corr_torch, raft_model
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    H, W = (Himg + 7) // 8, Wimg // 8
+    g = torch.Generator().manual_seed(0)
+    f1 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
+    f2 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
+    cs = [(fsb.coords_grid(B, H, W) + 5.0 * torch.randn(B, 2, H, W, generator=g)).cuda() for _ in range(iters)]
+
+    def path(block):
+        blk = block(f1, f2, L, R)
+        for c in cs:
+            out = blk(c)
+        return out
+
+    with torch.no_grad():
+        ms_ref = timed(lambda: path(corr_torch.TorchCorrBlock), max(2, reps // 3), warm=1)
+        ms_our = timed(lambda: path(fsb.CorrBlock), reps)
+    emit(row="corr path on the same GPU (build + 12 lookups): torch ops vs this library", geometry=f"B={B} {H}x{W}",
+         torch_ops_ms=ms_ref, ms=ms_our, speedup=ms_ref / ms_our)
+    torch.manual_seed(1234)
+    model = raft_model.Raft().eval().cuda()
+    im1 = torch.rand(B, 3, 8 * H, Wimg, generator=g).cuda() * 255.0
+    im2 = torch.rand(B, 3, 8 * H, Wimg, generator=g).cuda() * 255.0
+    with torch.no_grad():
+        ms_ref = timed(lambda: model(im1, im2, iters=iters, corr_block=corr_torch.TorchCorrBlock), max(2, reps // 3), warm=1)
+        ms_our = timed(lambda: model(im1, im2, iters=iters, corr_block=fsb.CorrBlock), max(2, reps // 2), warm=1)
+    emit(row="RAFT forward, 12 iterations, fp32 convolutions (oracle/raft_model.py): reference-path block vs drop-in block",
+         geometry=f"B={B} {8 * H}x{Wimg} px", torch_block_ms=ms_ref, ms=ms_our, pairs_per_s_ref=B / ms_ref * 1e3,
+         pairs_per_s=B / ms_our * 1e3, speedup=ms_ref / ms_our)
+    del model
+    torch.cuda.empty_cache()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=10)
@@ -195,3 +233,5 @@ if __name__ == "__main__":
         row_backward(6, 54, 128, a.reps)
     if "ondemand" in a.rows:
         row_ondemand(2, 136, 240, a.reps)
+    if "samegpu" in a.rows:
+        row_same_gpu(8, 436, 1024, a.reps)
