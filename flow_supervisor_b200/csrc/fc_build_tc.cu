@@ -137,6 +137,7 @@ struct TcParams {
     int units;             // B * mp * groups work units, split evenly over the resident CTA pairs
     int three_pass;        // 1 = hi*hi + lo*hi + hi*lo, 0 = hi*hi
     float scale;           // 1 / sqrt(D)
+    int stages;            // operand ring depth in use (<= TC_STAGES; FLOWCORR_BUILD_STAGES for the ring-depth measurement)
     int probe;             // 0 in production; FLOWCORR_PROBE (tools/probe_bounds.py): 1 = epilogue without
                            // global stores, 2 = no MMAs issued, 3 = epilogue neither reads TMEM nor stores,
                            // 5 = pooled-level stores off, 6 = level-0 stores off, 7 = no target-operand loads
@@ -205,7 +206,8 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
         if (lane == 0) {
-            int it = 0, a_use = 0, cur_am = -1;
+            int it = 0, a_use = 0, cur_am = -1, slot = 0;
+            uint32_t phase = 0;                                // ring position: stage `slot`, use parity `phase`
             for (int u = u_begin; u < u_end; ++u) {
                 int b, m0, t0, t1;
                 decode(u, b, m0, t0, t1);
@@ -227,8 +229,9 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     const int row0 = b * P.NP + rp * 2 * P.Wp + h * P.NT + (int)rank * (ncols >> 1);
                     for (int kb = 0; kb < KB; ++kb)
                         for (int part = 0; part < n_parts; ++part, ++it) {
-                            const int s = it % TC_STAGES;
-                            const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                            const int s = slot;
+                            const uint32_t ph = phase;
+                            if (++slot == P.stages) { slot = 0; phase ^= 1u; }
                             mbar_wait(b_empty + s, ph ^ 1u);
                             if (P.probe == 7) {                // no target loads (stage probe)
                                 if (leader) mbar_arrive(b_full + s);
@@ -245,7 +248,8 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // ================= MMA issuer (leader CTA only) =================
         if (lane == 0 && leader) {
             const uint32_t idesc0 = umma_idesc_bf16(2 * TC_BM, P.NT), idesc1 = umma_idesc_bf16(2 * TC_BM, P.NT2 > 0 ? P.NT2 : P.NT);
-            int it = 0, tc = 0, a_use = 0, cur_am = -1;
+            int it = 0, tc = 0, a_use = 0, cur_am = -1, slot = 0;
+            uint32_t phase = 0;
             for (int u = u_begin; u < u_end; ++u) {
                 int b, m0, t0, t1;
                 decode(u, b, m0, t0, t1);
@@ -264,8 +268,10 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     const uint32_t d_addr = tmem_base + (uint32_t)(buf * 256);
                     for (int kb = 0; kb < KB; ++kb)
                         for (int part = 0; part < n_parts; ++part, ++it) {
-                            const int s = it % TC_STAGES;
-                            mbar_wait(b_full + s, (uint32_t)(it / TC_STAGES) & 1u);
+                            const int s = slot;
+                            const uint32_t ph = phase;
+                            if (++slot == P.stages) { slot = 0; phase ^= 1u; }
+                            mbar_wait(b_full + s, ph);
                             tc_fence_after();
                             const uint32_t b_addr = smem_u32(ring + s * TC_STAGE_BYTES);
                             const uint32_t ah_addr = smem_u32(a_hi + kb * TC_ABLK_BYTES);
@@ -621,6 +627,8 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     P.groups = (P.n_rp + 3) / 4;
     P.units = B * P.mp * P.groups;
     P.three_pass = three ? 1 : 0;
+    P.stages = TC_STAGES;
+    if (const char* st = getenv("FLOWCORR_BUILD_STAGES")) { const int v = atoi(st); if (v >= 1 && v <= TC_STAGES) P.stages = v; }
     P.scale = fold_scale ? 1.0f : inv_sqrt_d;
     { const char* pr = getenv("FLOWCORR_PROBE"); P.probe = pr ? atoi(pr) : 0; }
 

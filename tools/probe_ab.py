@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Round-robin A/B of build variants (env switches read per call): medians over `rounds` x `reps` launches, so
-slow drifts of the box hit every variant alike.   python probe_ab.py  [math]"""
+"""Round-robin A/B of build variants (env switches read per call): medians over rounds x reps launches, so slow drifts
+of the box hit every variant alike.  Here: operand ring depth FLOWCORR_BUILD_STAGES per math mode."""
 import json
 import os
 import statistics
@@ -18,13 +18,13 @@ g = torch.Generator().manual_seed(0)
 B, H, W, D, L = 8, 55, 128, 256, 4
 f1 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
 f2 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
-variants = [{"FLOWCORR_BUILD_L2HINT": str(h), "FLOWCORR_L0STORE": str(d)} for d in (0, 1) for h in (0, 8, 1, 2, 3, 9)]
+variants = [{"FLOWCORR_BUILD_STAGES": v} for v in ("2", "3", "4")]
 for math, mname in ((_lib.MATH_TC_3XBF16, "3xbf16"), (_lib.MATH_TC_BF16, "bf16")):
     res = {i: [] for i in range(len(variants))}
-    for rnd in range(6):
+    for rnd in range(5):
         for i, v in enumerate(variants):
             os.environ.update(v)
-            res[i].append(1e3 * timed(lambda: ops.build(f1, f2, L, math, _lib.VOL_F32), reps=20, warm=2))
+            res[i].append(1e3 * timed(lambda: ops.build(f1, f2, L, math, _lib.VOL_F32), reps=12, warm=2))
     for i, v in enumerate(variants):
         print(json.dumps({"kernel": "build (pack + tc_build)", "math": mname, **v, "us_median": statistics.median(res[i]),
                           "us_min": min(res[i]), "us_max": max(res[i])}), flush=True)
