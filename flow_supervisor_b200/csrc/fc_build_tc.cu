@@ -29,8 +29,11 @@ namespace fc {
 int simt_pool_levels(float* pyramid, const Pyramid& pyr, int first_level, cudaStream_t s);   // fc_simt.cu
 int simt_zero_pad_rows(float* pyramid, const Pyramid& pyr, int first, int last, cudaStream_t s);
 
-constexpr int TC_THREADS = 384;          // warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4-11 epilogue
-constexpr int TC_FIRST_EPI_WARP = 4;
+// Epilogue warps per CTA (template parameter EW): 4 -> 192 threads (warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, one per
+// TMEM lane quarter, two staging boxes each), 8 -> 384 threads (warps 2-3 idle, warps 4-11 epilogue, two per quarter
+// splitting the tile's chunks, one staging box each).
+__host__ __device__ constexpr int tc_threads(int ew) { return ew == 4 ? 192 : 384; }
+__host__ __device__ constexpr int tc_first_epi_warp(int ew) { return ew == 4 ? 2 : 4; }
 constexpr int TC_BM = 128;           // queries per CTA (UMMA M)
 constexpr int TC_BK = 64;            // bf16 elements per 128-byte swizzle row
 #ifndef FC_TC_STAGES
@@ -40,7 +43,7 @@ constexpr int TC_STAGES = FC_TC_STAGES;
 constexpr int TC_STAGE_BYTES = 128 * TC_BK * 2;           // 16 KB: this CTA's half (<= 128 rows) of a target tile x 64 k
 constexpr int TC_ABLK_BYTES = TC_BM * TC_BK * 2;          // 16 KB per k-block of the query tile
 constexpr int TC_STG_FLOATS = 32 * 32;                    // one TMA-store box: [32 queries][32 floats] = 4 KB
-constexpr int TC_STG_BYTES = 8 * TC_STG_FLOATS * 4;       // 8 epilogue warps x 1 buffer = 32 KB
+constexpr int TC_STG_BYTES = 8 * TC_STG_FLOATS * 4;       // 8 staging boxes (EW warps x 8 / EW buffers) = 32 KB
 
 
 // ---------------------------------------------------------------- pack pre-pass
@@ -143,8 +146,8 @@ struct TcParams {
                            // 5 = pooled-level stores off, 6 = level-0 stores off, 7 = no target-operand loads
 };
 
-template <int KB>   // KB = D / 64 k-blocks
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+template <int KB, int EW>   // KB = D / 64 k-blocks, EW = epilogue warps (4 or 8)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc_threads(EW), 1)
 tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                 const __grid_constant__ CUtensorMap map_b2_hi, const __grid_constant__ CUtensorMap map_b2_lo,
@@ -191,7 +194,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 16); }   // 8 epilogue warps x 2 CTAs
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 2 * EW); }   // EW epilogue warps x 2 CTAs
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -291,7 +294,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 }
             }
         }
-    } else if (warp >= TC_FIRST_EPI_WARP) {
+    } else if (warp >= tc_first_epi_warp(EW)) {
         // ================= epilogue (8 warps) =================
         // TMEM -> registers -> (scale, 2x2 pooling) -> shared staging -> TMA tensor store.
         // A thread owns one query row (TMEM lane quarter = warp % 4); the two warps of a quarter
@@ -303,9 +306,13 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // [32 queries][32 floats] is what the store maps describe: one elected lane writes
         // 32 queries x 128 bytes with a single instruction; rows beyond the sample are clipped
         // by the TMA unit.
-        const int ew = warp - TC_FIRST_EPI_WARP;
+        constexpr int NH = EW / 4;                             // warps per TMEM lane quarter
+        constexpr int CMAX = 8 / NH;                           // chunk slots per warp
+        constexpr int NBUF = 8 / EW;                           // staging boxes per warp
+        const int ew = warp - tc_first_epi_warp(EW);
         const int quarter = warp & 3, half_id = ew >> 2;
-        float* sbuf = stg + ew * TC_STG_FLOATS;                // one 4 KB staging box per warp
+        float* sbuf0 = stg + ew * NBUF * TC_STG_FLOATS;        // this warp's 4 KB staging box(es)
+        uint32_t use = 0;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const bool do_scale = P.scale != 1.0f;
         const bool fused = P.n_fused > 1;
@@ -313,9 +320,9 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const long long ms1 = (long long)P.lvHp[1] * P.lvWp[1];
         const long long ms2 = (long long)P.lvHp[2] * P.lvWp[2], ms3 = (long long)P.lvHp[3] * P.lvWp[3];
         int b = 0, tc = 0;
-        float s2[4][4], s3[4][2];                              // level-2 / level-3 partial sums across the row pairs of a run
+        float s2[CMAX][4], s3[CMAX][2];                        // level-2 / level-3 partial sums across the row pairs of a run
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < CMAX; ++i) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) s2[i][j] = 0.f;
             s3[i][0] = s3[i][1] = 0.f;
@@ -333,17 +340,17 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const int q0 = rp * 2 * P.Wp + H * P.NT;           // first padded target of the tile
             const int ncols = H ? P.NT2 : P.NT;
             const int n_chunks = (ncols + 31) >> 5;            // 32-column chunks of the tile (the last may be 16 wide)
-            const int CH = n_chunks > 4 ? 4 : (n_chunks > 2 ? 2 : n_chunks);   // chunks per warp (even when split)
-            // chunk of this warp's cc-th slot.  Wide tiles: the two warps of a quarter alternate PAIRS of chunks
-            // ({0,1,4,5} / {2,3,6,7}) so that the four lines of a 512-byte run reach L2 close together;
-            // narrow tiles (<= 2 chunks): the second warp only keeps the barriers moving
-            const bool ilv = n_chunks > 4;
-            const int c_lo = (n_chunks > 2 || half_id == 0) ? half_id * CH : 8;
+            // chunks per warp and the chunk of its cc-th slot.  One warp per quarter: all chunks in order.  Two warps:
+            // wide tiles alternate PAIRS of chunks ({0,1,4,5} / {2,3,6,7}) so that the four lines of a 512-byte run reach
+            // L2 close together; narrow tiles (<= 2 chunks): the second warp only keeps the barriers moving
+            const int CH = NH == 1 ? n_chunks : (n_chunks > 4 ? 4 : (n_chunks > 2 ? 2 : n_chunks));
+            const bool ilv = NH == 2 && n_chunks > 4;
+            const int c_lo = NH == 1 ? 0 : ((n_chunks > 2 || half_id == 0) ? half_id * CH : 8);
             auto chunk_of = [&](int cc) { return ilv ? ((cc >> 1) * 4 + half_id * 2 + (cc & 1)) : (c_lo + cc); };
-            float l2[4][4];
+            float l2[CMAX][4];
             if (P.probe != 3) {
 #pragma unroll
-              for (int cc = 0; cc < 4; ++cc) {
+              for (int cc = 0; cc < CMAX; ++cc) {
                 const int c = chunk_of(cc);                    // chunk inside the tile
                 const int gc = H * (P.NT >> 5) + c;                      // chunk inside the row pair: level-0 columns [16 gc, 16 gc + 16)
                 if (cc < CH && c * 32 < ncols) {
@@ -356,7 +363,9 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     }
                     // ---- level 0: staging (swizzled like the store map) -> TMA store
                     const int rem = ncols - c * 32;
-                    if (lane == 0) tma_wait_group_read<0>();   // the store that last read this buffer is done
+                    float* sbuf = sbuf0 + (use & (NBUF - 1)) * TC_STG_FLOATS;
+                    ++use;
+                    if (lane == 0) tma_wait_group_read<NBUF - 1>();   // the store that last read this box is done
                     __syncwarp();
                     if (rem >= 32) {
 #pragma unroll
@@ -418,7 +427,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const int y2 = rp >> 1;
                 const bool st = mine && P.probe != 1 && P.probe != 5;
 #pragma unroll
-                for (int cp = 0; cp < 2; ++cp) {
+                for (int cp = 0; cp < CMAX / 2; ++cp) {
                     const int gc = H * (P.NT >> 5) + chunk_of(2 * cp);
                     if (2 * cp < CH && y2 < P.lvH[2] && 4 * gc < P.lvWp[2] && st) {
                         const float o[8] = {l2[2 * cp][0], l2[2 * cp][1], l2[2 * cp][2], l2[2 * cp][3],
@@ -431,13 +440,13 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     const int y3 = rp >> 2;
                     if ((y2 & 1) == 0) {
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
+                        for (int cc = 0; cc < CMAX; ++cc) {
                             s3[cc][0] = __fadd_rn(l2[cc][0], l2[cc][1]);
                             s3[cc][1] = __fadd_rn(l2[cc][2], l2[cc][3]);
                         }
                     } else {
 #pragma unroll
-                        for (int cp = 0; cp < 2; ++cp) {
+                        for (int cp = 0; cp < CMAX / 2; ++cp) {
                             const int gc = H * (P.NT >> 5) + chunk_of(2 * cp);
                             float o[4];
 #pragma unroll
@@ -447,7 +456,8 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                                 o[i] = (2 * gc + i < W3) ? a * 0.25f : 0.f;
                             }
                             // (narrow tiles: the one active warp also writes the zero pad columns 4..7 of the patch)
-                            if ((2 * cp < CH || n_chunks <= 2) && y3 < P.lvH[3] && 2 * gc < P.lvWp[3] && st)
+                            // (a warp that owns whole level-3 patches completes them: 4 chunks = 8 columns, zeros past the map)
+                            if ((2 * cp < (NH == 1 ? ((CH + 3) & ~3) : CH) || n_chunks <= 2) && y3 < P.lvH[3] && 2 * gc < P.lvWp[3] && st)
                                 *reinterpret_cast<float4*>(P.lvl[3] + qrow * ms3 + (long long)(y3 >> 1) * 2 * P.lvWp[3] +
                                                            (gc >> 2) * 16 + (y3 & 1) * 8 + ((gc >> 1) & 1) * 4) =
                                     make_float4(o[0], o[1], o[2], o[3]);
@@ -463,7 +473,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     if (P.lvHp[l] > P.lvH[l]) {
                         const int y = P.lvH[l], wp = P.lvWp[l];
                         float* rowp = P.lvl[l] + qrow * ((long long)P.lvHp[l] * wp) + (long long)(y >> 1) * 2 * wp + (y & 1) * 8;
-                        for (int g = half_id; g * 8 < wp; g += 2) st_v8(rowp + g * 16, z);
+                        for (int g = half_id; g * 8 < wp; g += NH) st_v8(rowp + g * 16, z);
                     }
             }
             ++tc;
@@ -543,25 +553,25 @@ size_t tc_build_workspace_bytes(int B, int D, int H, int W, int, int) {
     return tc_layout(B, D, H, W).total + 1024;   // slack to align the base to 1 KB
 }
 
-template <int KB>
+template <int KB, int EW>
 static int launch_tc(const CUtensorMap* maps, const TcStoreMaps& SM, const TcParams& P, int B, cudaStream_t s) {
     const size_t smem = 1024 + 2 * KB * TC_ABLK_BYTES + TC_STAGES * TC_STAGE_BYTES + TC_STG_BYTES + 256;
-    FC_CUDA(cudaFuncSetAttribute(tc_build_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FC_CUDA(cudaFuncSetAttribute(tc_build_kernel<KB, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // persistent: one CTA pair (cluster 2x1x1) per co-resident SM pair
     int n_clusters = 0;
     {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem;
+        cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(tc_threads(EW)); cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute attr;
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr; cfg.numAttrs = 1;
-        FC_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, tc_build_kernel<KB>, &cfg));
+        FC_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, tc_build_kernel<KB, EW>, &cfg));
     }
     if (n_clusters < 1) { set_error("fc_build: no CTA pair of the tensor-core kernel fits on this device"); return FC_ECUDA; }
     if (n_clusters > P.units) n_clusters = P.units;
     dim3 grid(2 * n_clusters);
-    tc_build_kernel<KB><<<grid, TC_THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], SM, P);
+    tc_build_kernel<KB, EW><<<grid, tc_threads(EW), smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], SM, P);
     FC_LAUNCH_CHECK("tc_build_kernel");
     return FC_OK;
 }
@@ -653,11 +663,17 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     }
 
     int e;
-    switch (D / 64) {
-        case 1: e = launch_tc<1>(maps, SM, P, B, s); break;
-        case 2: e = launch_tc<2>(maps, SM, P, B, s); break;
-        case 3: e = launch_tc<3>(maps, SM, P, B, s); break;
-        default: e = launch_tc<4>(maps, SM, P, B, s); break;
+    // 4 epilogue warps measured 2.5 % faster than 8 in the three-pass mode at cfg 2 (same box, round robin:
+    // profiles/r01j_build_epilogue_warps_ab.jsonl) and equal in single-pass mode; FLOWCORR_BUILD_EPI_WARPS=8 selects the other
+    int ewarps = 4;
+    if (const char* ev = getenv("FLOWCORR_BUILD_EPI_WARPS")) ewarps = atoi(ev) == 8 ? 8 : 4;
+    const int kbs = D / 64;
+    if (ewarps == 8) {
+        e = kbs == 1 ? launch_tc<1, 8>(maps, SM, P, B, s) : kbs == 2 ? launch_tc<2, 8>(maps, SM, P, B, s)
+          : kbs == 3 ? launch_tc<3, 8>(maps, SM, P, B, s) : launch_tc<4, 8>(maps, SM, P, B, s);
+    } else {
+        e = kbs == 1 ? launch_tc<1, 4>(maps, SM, P, B, s) : kbs == 2 ? launch_tc<2, 4>(maps, SM, P, B, s)
+          : kbs == 3 ? launch_tc<3, 4>(maps, SM, P, B, s) : launch_tc<4, 4>(maps, SM, P, B, s);
     }
     if (e) return e;
     return simt_pool_levels(static_cast<float*>(pyramid), pyr, P.n_fused, s);

@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 SHAPES = [(1, 256, 46, 62), (2, 256, 55, 128), (1, 64, 17, 19), (1, 256, 47, 156), (2, 128, 16, 24),
           (1, 256, 24, 132),                  # row pairs split 192 + 80 accumulator columns
-          (1, 64, 19, 240), (1, 64, 10, 250)]   # cfg 5 width (256 + 224) and the widest map (256 + 256)
+          (1, 64, 19, 240), (1, 64, 10, 250),   # cfg 5 width (256 + 224) and the widest map (256 + 256)
+          (1, 64, 18, 78), (1, 64, 12, 44)]     # 5 and 3 chunks per row pair: partially filled level-2/3 patches
 
 
 @pytest.fixture(scope="module")
