@@ -140,6 +140,7 @@ struct TcParams {
     int units;             // B * mp * groups work units, split evenly over the resident CTA pairs
     int three_pass;        // 1 = hi*hi + lo*hi + hi*lo, 0 = hi*hi
     float scale;           // 1 / sqrt(D)
+    int sched;             // 1: pair-tiles strided over the CTA pairs (default), 0: contiguous unit ranges
     int stages;            // operand ring depth in use (<= TC_STAGES; FLOWCORR_BUILD_STAGES for the ring-depth measurement)
     int probe;             // 0 in production; FLOWCORR_PROBE (tools/probe_bounds.py): 1 = epilogue without
                            // global stores, 2 = no MMAs issued, 3 = epilogue neither reads TMEM nor stores,
@@ -176,13 +177,32 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
 
-    // Persistent schedule: work unit u = (sample, query pair-tile, group of 4 target tiles), units
-    // [u_begin, u_end) of this CTA pair are consecutive, so the resident query operand is
-    // reloaded only when (sample, pair-tile) changes.  All three roles walk the same sequence.
+    // Persistent schedule: work unit u = (sample, query pair-tile, group of 4 row pairs), u = pair-tile * groups + group.
+    // A CTA pair takes WHOLE pair-tiles c, c + n_clusters, c + 2 n_clusters, ... (the resident query operand is reloaded
+    // only when the pair-tile changes) so that at any time all pairs work on neighbouring pair-tiles, i.e. on two or
+    // three samples whose target operand stays hot in L2 instead of all B of them (FLOWCORR_BUILD_SCHED=0: contiguous
+    // unit ranges); the pair-tiles left over after the last full round are dealt out unit by unit.  All three roles
+    // walk the same sequence.
     const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
-    const int u_begin = (int)((long long)P.units * cluster_id / n_clusters);
-    const int u_end = (int)((long long)P.units * (cluster_id + 1) / n_clusters);
-    auto decode = [&](int u, int& b, int& m0, int& t0, int& t1) {        // [t0, t1): ROW PAIRS of the unit
+    const int n_pt = P.units / P.groups;                               // pair-tiles in all
+    const int full_rounds = n_pt / n_clusters;
+    const int tail_units = (n_pt - full_rounds * n_clusters) * P.groups;
+    int u_begin = 0, u_end = 0;                                        // local unit counter [u_begin, u_end)
+    if (P.sched == 0) {
+        u_begin = (int)((long long)P.units * cluster_id / n_clusters);
+        u_end = (int)((long long)P.units * (cluster_id + 1) / n_clusters);
+    } else {
+        // the tail's units go round robin: cluster c takes tail units c, c + n_clusters, ...
+        u_end = full_rounds * P.groups + (tail_units > cluster_id ? (tail_units - cluster_id + n_clusters - 1) / n_clusters : 0);
+    }
+    auto unit_of = [&](int j) {                                        // j-th local unit -> global unit
+        if (P.sched == 0) return j;
+        const int k = j / P.groups;
+        if (k < full_rounds) return (cluster_id + k * n_clusters) * P.groups + (j - k * P.groups);
+        return full_rounds * n_clusters * P.groups + cluster_id + (j - full_rounds * P.groups) * n_clusters;
+    };
+    auto decode = [&](int j, int& b, int& m0, int& t0, int& t1) {        // [t0, t1): ROW PAIRS of the unit
+        const int u = unit_of(j);
         const int am = u / P.groups, g = u - am * P.groups;
         b = am / P.mp;
         m0 = ((am - b * P.mp) * 2 + (int)rank) * TC_BM;
@@ -214,7 +234,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             for (int u = u_begin; u < u_end; ++u) {
                 int b, m0, t0, t1;
                 decode(u, b, m0, t0, t1);
-                const int am = u / P.groups;
+                const int am = unit_of(u) / P.groups;
                 if (am != cur_am) {
                     // query operand (resident): wait until the MMAs reading the old one have retired
                     if (a_use > 0) mbar_wait(a_empty, (uint32_t)(a_use - 1) & 1u);
@@ -256,7 +276,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             for (int u = u_begin; u < u_end; ++u) {
                 int b, m0, t0, t1;
                 decode(u, b, m0, t0, t1);
-                const int am = u / P.groups;
+                const int am = unit_of(u) / P.groups;
                 if (am != cur_am) {
                     if (cur_am >= 0) umma2_commit(a_empty);    // old query operand is free once everything issued retires
                     mbar_wait(a_full, (uint32_t)a_use & 1u);
@@ -638,6 +658,7 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     P.units = B * P.mp * P.groups;
     P.three_pass = three ? 1 : 0;
     P.stages = TC_STAGES;
+    { const char* sc = getenv("FLOWCORR_BUILD_SCHED"); P.sched = sc ? atoi(sc) : 1; }
     if (const char* st = getenv("FLOWCORR_BUILD_STAGES")) { const int v = atoi(st); if (v >= 1 && v <= TC_STAGES) P.stages = v; }
     P.scale = fold_scale ? 1.0f : inv_sqrt_d;
     { const char* pr = getenv("FLOWCORR_PROBE"); P.probe = pr ? atoi(pr) : 0; }
