@@ -6,20 +6,25 @@
 //                   patch order q' = tile_off(y, x) (fc_common.cuh; pad rows are zero), so a
 //                   GEMM output row IS a query's level-0 map in its final memory layout and
 //                   pad entries come out as exact zeros.
-//   GEMM          : one CTA per (sample, 128-query tile).  The query operand (hi and lo, all
-//                   of K) stays resident in shared memory; target tiles of NT = 2 rows x Wp
-//                   (two tiles per row pair, split at a patch boundary, when 2*Wp > 256) stream
-//                   through a 4-stage TMA ring in 128-row x 64-k sub-stages.  FC_MATH_TC_3XBF16 issues hi*hi + lo*hi + hi*lo
+//   GEMM          : persistent CTA pairs (cta_group::2, M = 256).  A pair takes whole query pair-tiles
+//                   c, c + n_pairs, ... so that all pairs work on two or three samples at a time and the
+//                   packed target operand stays hot in L2.  The query operand (hi and lo, all of K)
+//                   stays resident in shared memory; target tiles of NT = 2 rows x Wp (two tiles per
+//                   row pair, split at a patch boundary, when 2*Wp > 256) stream through a 4-stage TMA
+//                   ring in 128-row x 64-k sub-stages.  FC_MATH_TC_3XBF16 issues hi*hi + lo*hi + hi*lo
 //                   into the same fp32 TMEM accumulator (error ~4e-6);
 //                   FC_MATH_TC_BF16 issues hi*hi only.  Two 256-column accumulators double
 //                   buffer the MMA against the epilogue.
-//   epilogue      : 8 warps, tcgen05.ld 32 lanes x 32 columns, swizzled staging box + one TMA
-//                   tensor store per 32 queries x 128 bytes of level 0; levels 1-3 are pooled
+//   epilogue      : 4 (default) or 8 warps, tcgen05.ld 32 lanes x 32 columns, swizzled staging box +
+//                   one TMA tensor store per 32 queries x 128 bytes of level 0; levels 1-3 are pooled
 //                   thread-locally (bit-exact avg_pool2d) and leave as 32-byte runs.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-3 idle,
-// warps 4-11 = epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter split the
-// tile's columns).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, then the epilogue
+// warps (TMEM lane quarter = warp_id % 4): warps 2-5, or warps 4-11 with two warps per quarter
+// splitting the tile's columns.
+//
+// Diagnostic switches (read per call, none needed in production): FLOWCORR_PROBE (stage probes, results are
+// garbage), FLOWCORR_BUILD_EPI_WARPS=4|8, FLOWCORR_BUILD_STAGES=1..4, FLOWCORR_BUILD_SCHED=0|1, FLOWCORR_NO_FUSE.
 #include <cstdlib>
 
 #include "fc_umma.cuh"
