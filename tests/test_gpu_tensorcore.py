@@ -144,3 +144,26 @@ def test_tc_backward_matches_oracle(fsb):
     w1, w2 = corr_spec.build_backward(G, f1.numpy(), f2.numpy())
     assert float(np.abs(d1.cpu().numpy() - w1).max() / np.abs(w1).max()) < 1e-4
     assert float(np.abs(d2.cpu().numpy() - w2).max() / np.abs(w2).max()) < 1e-4
+
+
+@pytest.mark.parametrize("env", [{"FLOWCORR_BUILD_EPI_WARPS": "8"}, {"FLOWCORR_BUILD_SCHED": "0"},
+                                 {"FLOWCORR_BUILD_STAGES": "2"}, {"FLOWCORR_BUILD_EPI_WARPS": "8", "FLOWCORR_BUILD_SCHED": "0"}])
+@pytest.mark.parametrize("shape", [(2, 256, 55, 128), (1, 128, 21, 156), (3, 64, 17, 23)])
+def test_tc_build_variants_are_bit_identical(fsb, monkeypatch, env, shape):
+    """The alternative epilogue width, unit schedule and ring depth (diagnostic switches of fc_build_tc.cu) change
+    who computes a tile and when, never the arithmetic: the pyramid must come out bit for bit the same."""
+    import os
+    B, D, H, W = shape
+    gen = torch.Generator().manual_seed(7)
+    f1 = (1.57 * torch.randn(B, D, H, W, generator=gen)).cuda()
+    f2 = (1.57 * torch.randn(B, D, H, W, generator=gen)).cuda()
+    for k in ("FLOWCORR_BUILD_EPI_WARPS", "FLOWCORR_BUILD_SCHED", "FLOWCORR_BUILD_STAGES"):
+        monkeypatch.delenv(k, raising=False)
+    ref = build(fsb, f1, f2, "3xbf16")._state.pyramid.clone()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = build(fsb, f1, f2, "3xbf16")._state.pyramid
+    lv_ref = fsb.ops.level_padded(ref, B, H, W, 4)
+    lv_got = fsb.ops.level_padded(got, B, H, W, 4)
+    for l in range(4):
+        assert torch.equal(lv_ref[l], lv_got[l]), (env, l)
