@@ -107,3 +107,25 @@ def test_run_sharded_world2_gloo(n_items):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, n_items, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def test_multiply_shift_division_formula_is_exact():
+    """fc_lookup.cuh::split_query replaces gq / N by (umulhi(m, gq) + gq) >> s with the Granlund-Montgomery round-up
+    multiplier of fill_params.  The formula must be exact for every query index the library accepts (gq < 2^31 - 32)
+    and every token count; checked here in integer arithmetic on edge values and a random sample."""
+    import random
+    rng = random.Random(0)
+    Ns = [1, 2, 3, 7, 96, 255, 256, 257, 2852, 4416, 6912, 7040, 7332, 32640, 65535, 65536, 1 << 20, (1 << 24) + 1]
+    for N in Ns:
+        s = 0
+        while (1 << s) < N:
+            s += 1
+        m = ((1 << 32) * ((1 << s) - N)) // N + 1
+        assert m < (1 << 32)
+        edge = [0, 1, N - 1, N, N + 1, 2 * N - 1, 2 * N, (1 << 31) - 33, (1 << 31) - 1 - 32]
+        edge += [k * N + d for k in (3, 1000, ((1 << 31) - 64) // N) for d in (-1, 0, 1) if 0 <= k * N + d < (1 << 31) - 32]
+        sample = edge + [rng.randrange(0, (1 << 31) - 32) for _ in range(2000)]
+        for gq in sample:
+            t = (m * gq) >> 32
+            assert t + gq < (1 << 32)                       # the 32-bit add in the kernel cannot wrap
+            assert (t + gq) >> s == gq // N, (N, gq)
