@@ -129,3 +129,32 @@ def test_multiply_shift_division_formula_is_exact():
             t = (m * gq) >> 32
             assert t + gq < (1 << 32)                       # the 32-bit add in the kernel cannot wrap
             assert (t + gq) >> s == gq // N, (N, gq)
+
+
+def test_build_schedule_covers_every_unit_once():
+    """fc_build_tc.cu: a CTA pair takes whole pair-tiles c, c + n, c + 2n, ... and the left-over pair-tiles are dealt
+    out unit by unit (unit_of / u_end in the kernel).  Mirror of that arithmetic: every unit exactly once, for any
+    number of pair-tiles, groups and resident CTA pairs; the busiest pair gets at most one unit more than the mean
+    rounded up plus the groups of an unfinished round."""
+    for n_pt in (1, 2, 3, 27, 28, 73, 74, 75, 147, 148, 224, 513):
+        for groups in (1, 2, 7, 17):
+            for n_clusters in (1, 2, 37, 74):
+                units = n_pt * groups
+                if n_clusters > units:
+                    continue
+                full = n_pt // n_clusters
+                tail_units = (n_pt - full * n_clusters) * groups
+                seen = []
+                most = 0
+                for c in range(n_clusters):
+                    n_local = full * groups + ((tail_units - c + n_clusters - 1) // n_clusters if tail_units > c else 0)
+                    most = max(most, n_local)
+                    for j in range(n_local):
+                        k = j // groups
+                        if k < full:
+                            u = (c + k * n_clusters) * groups + (j - k * groups)
+                        else:
+                            u = full * n_clusters * groups + c + (j - full * groups) * n_clusters
+                        seen.append(u)
+                assert sorted(seen) == list(range(units)), (n_pt, groups, n_clusters)
+                assert most <= -(-units // n_clusters) + (groups if tail_units else 0)
