@@ -234,7 +234,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
         if (lane == 0) {
-            int it = 0, a_use = 0, cur_am = -1, slot = 0;
+            int a_use = 0, cur_am = -1, slot = 0;
             uint32_t phase = 0;                                // ring position: stage `slot`, use parity `phase`
             for (int u = u_begin; u < u_end; ++u) {
                 int b, m0, t0, t1;
@@ -256,7 +256,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     const int ncols = h ? P.NT2 : P.NT;            // each CTA streams its half of the tile's targets
                     const int row0 = b * P.NP + rp * 2 * P.Wp + h * P.NT + (int)rank * (ncols >> 1);
                     for (int kb = 0; kb < KB; ++kb)
-                        for (int part = 0; part < n_parts; ++part, ++it) {
+                        for (int part = 0; part < n_parts; ++part) {
                             const int s = slot;
                             const uint32_t ph = phase;
                             if (++slot == P.stages) { slot = 0; phase ^= 1u; }
@@ -276,7 +276,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // ================= MMA issuer (leader CTA only) =================
         if (lane == 0 && leader) {
             const uint32_t idesc0 = umma_idesc_bf16(2 * TC_BM, P.NT), idesc1 = umma_idesc_bf16(2 * TC_BM, P.NT2 > 0 ? P.NT2 : P.NT);
-            int it = 0, tc = 0, a_use = 0, cur_am = -1, slot = 0;
+            int tc = 0, a_use = 0, cur_am = -1, slot = 0;
             uint32_t phase = 0;
             for (int u = u_begin; u < u_end; ++u) {
                 int b, m0, t0, t1;
@@ -295,7 +295,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     tc_fence_after();
                     const uint32_t d_addr = tmem_base + (uint32_t)(buf * 256);
                     for (int kb = 0; kb < KB; ++kb)
-                        for (int part = 0; part < n_parts; ++part, ++it) {
+                        for (int part = 0; part < n_parts; ++part) {
                             const int s = slot;
                             const uint32_t ph = phase;
                             if (++slot == P.stages) { slot = 0; phase ^= 1u; }

@@ -84,7 +84,7 @@ template <int RADIUS, int CM, int WI>
 __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams& P, int n_tiles, int g, int lane,
                                         uint32_t gbase) {
     using T = LbTile<RADIUS, WI>;
-    constexpr int R = T::R, C_LO = T::C_LO, C_HI = T::C_HI;
+    constexpr int R = T::R, C_LO = T::C_LO;
     const int tg = WI * 32 + lane;                                       // thread index inside the group
     const int n_groups = gridDim.x * LB_GROUPS;
     int tile = blockIdx.x * LB_GROUPS + g;

@@ -158,7 +158,7 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
     constexpr int R = 2 * RADIUS + 1;
     constexpr int APW = (R + LF_GWARPS - 1) / LF_GWARPS;             // x-offsets per warp
     constexpr bool EVEN = (R % APW) == 0;                            // every warp owns APW valid x-offsets
-    const int level = q.level, gq = q.gq;
+    const int level = q.level;
 
     // tap arithmetic overlaps the loads in flight
     int y0[R]; float wy0[R], wy1[R];
