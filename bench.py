@@ -32,6 +32,15 @@ if ROOT not in sys.path:
 
 LEVELS, RADIUS, DIM = 4, 4, 256
 K_CH = LEVELS * (2 * RADIUS + 1) ** 2
+METRIC = "RAFT corr-path pairs/s @436x1024 (12 iters)"
+
+
+def workload_config(args, H, W):
+    """The part of ``config`` both arms share (identical keys and values in both JSON lines)."""
+    return {"workload": f"CorrBlock build + {args.iters} lookups per pair, {args.height}x{args.width} px "
+                        f"-> {H}x{W} tokens, D={DIM}, L={LEVELS}, r={RADIUS}, batch {args.batch}/GPU",
+            "volume": "f32", "coords": "grid + N(0,5^2) 1/8-px flow",
+            "l2": "inputs larger than L2 (pyramid 2.1 GB/GPU vs 126 MB)"}
 
 
 def parse():
@@ -173,42 +182,62 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------ CPU arms
-def cpu_path_rate(H, W, iters, batch, budget_s, threads):
-    """The reference's CPU CorrBlock path (oracle/corr_torch.py: the same torch library
-    calls as corr.py) on the host cores: pairs/s over a bounded sample."""
+def reference_block():
+    """-> (CorrBlock class, kind, description).  The reference's OWN class
+    (/root/reference/pytorch/core/corr.py, installed verbatim into git-ignored baseline/_ref by
+    baseline/install_ref.py, which travels to the GPU box) when it is there -> kind "reference";
+    otherwise the library-call port oracle/corr_torch.py (bit-exact to it on CPU) -> kind "port"."""
+    try:
+        from baseline import install_ref
+        p = install_ref.install()
+        if p:
+            if p not in sys.path:
+                sys.path.insert(0, p)
+            from core.corr import CorrBlock as RefCorrBlock
+            return RefCorrBlock, "reference", "baseline/_ref/pytorch/core/corr.py (unmodified reference CorrBlock)"
+    except Exception:                               # noqa: BLE001
+        pass
     from oracle import corr_torch
+    return corr_torch.TorchCorrBlock, "port", "oracle/corr_torch.py (library-call port of corr.py)"
+
+
+def cpu_path_rate(H, W, iters, batch, budget_s, threads):
+    """The reference's CPU CorrBlock path on the host cores: pairs/s over a bounded sample."""
+    Block, kind, what = reference_block()
     torch.set_num_threads(threads)
     f1, f2, coords = synth(batch, H, W, iters, seed=0)
     def one():
-        blk = corr_torch.TorchCorrBlock(f1, f2, LEVELS, RADIUS)
+        blk = Block(f1, f2, LEVELS, RADIUS)
         for t in range(iters):
             out = blk(coords[t])
         return out
-    one()
-    reps, t0 = 0, time.perf_counter()
-    while True:
-        one(); reps += 1
-        el = time.perf_counter() - t0
-        if el >= budget_s:
-            break
-    return batch * reps / el, reps, el
+    with torch.no_grad():
+        one()
+        reps, t0 = 0, time.perf_counter()
+        while True:
+            one(); reps += 1
+            el = time.perf_counter() - t0
+            if el >= budget_s:
+                break
+    return batch * reps / el, reps, el, kind, what
 
 
 def run_reference(args, H, W):
-    """--impl reference: the reference's own CPU implementation of the path (library-call
-    port in oracle/corr_torch.py; the reference itself is Python and does not travel to
-    the GPU box).  Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path -- its unmodified
+    ``core.corr.CorrBlock`` from baseline/_ref (else the oracle port) -- on all host cores, on a
+    bounded sample of the workload per step.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    from oracle import corr_torch
+    Block, kind, what = reference_block()
     sample_b = 2
     f1, f2, coords = synth(sample_b, H, W, args.iters, seed=0)
     def step():
-        blk = corr_torch.TorchCorrBlock(f1, f2, LEVELS, RADIUS)
-        for t in range(args.iters):
-            blk(coords[t])
+        with torch.no_grad():
+            blk = Block(f1, f2, LEVELS, RADIUS)
+            for t in range(args.iters):
+                blk(coords[t])
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -217,17 +246,16 @@ def run_reference(args, H, W):
     el = time.perf_counter() - t0
     v = sample_b * args.steps / el
     line = {
-        "impl": "reference", "metric": "RAFT corr-path pairs/s @436x1024 (12 iters)", "value": v,
+        "impl": "reference", "metric": METRIC, "value": v,
         "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CorrBlock build + {args.iters} lookups per pair, {args.height}x{args.width} px "
-                               f"-> {H}x{W} tokens, D={DIM}, L={LEVELS}, r={RADIUS}, batch {args.batch}/GPU",
-                   "math": "fp32 (torch CPU ops)", "volume": "f32",
-                   "sample": f"{sample_b} pairs per step on the host cores (bounded sample of the {args.batch}-pair batch)",
-                   "coords": "grid + N(0,5^2) 1/8-px flow"},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps x {sample_b} pairs, torch {torch.__version__} CPU ops"},
+        "config": workload_config(args, H, W),
+        "reference_arm": {"math": "fp32 (torch CPU ops)", "what": what,
+                          "sample": f"{sample_b} pairs per step on the host cores (bounded sample of the "
+                                    f"{args.batch}-pair batch), normalised to pairs/s"},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind,
+                         "sample": f"{args.steps} steps x {sample_b} pairs, {what}, torch {torch.__version__} CPU ops"},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -406,16 +434,14 @@ def main():
         bld.update({"bound": which, **bld[which]})
         dominant, other = (look, bld) if look["share_of_step"] >= bld["share_of_step"] else (bld, look)
         line = {
-            "metric": "RAFT corr-path pairs/s @436x1024 (12 iters)", "value": value, "unit": "pairs/s",
+            "metric": METRIC, "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"CorrBlock build + {iters} lookups per pair, {args.height}x{args.width} px "
-                                   f"-> {H}x{W} tokens, D={DIM}, L={LEVELS}, r={RADIUS}, batch {B}/GPU",
-                       "math": args.math, "volume": "f32", "parallelism": f"batch-sharded x{world}, no collective",
-                       "l2": f"inputs larger than L2 (pyramid {pyr_bytes / 1e9:.2f} GB/GPU)",
-                       "coords": "grid + N(0,5^2) 1/8-px flow",
-                       "kernel_events": f"per-kernel CUDA events on every {EV_STRIDE}th timed step"},
+            "config": workload_config(args, H, W),
+            "arm": {"math": args.math, "parallelism": f"batch-sharded x{world}, no collective",
+                    "l2": f"inputs larger than L2 (pyramid {pyr_bytes / 1e9:.2f} GB/GPU, L2 126 MB): no flush needed",
+                    "kernel_events": f"per-kernel CUDA events on every {EV_STRIDE}th timed step"},
             "lookups_per_s": world * B * N * iters * args.steps / (elapsed_ms * 1e-3),
             "wall_s": wall,
             "roofline": dominant, "roofline_other": other,
@@ -424,7 +450,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if not args.no_rows:
+        if not args.no_rows and world == 1:
             # the other rows of SURVEY.md section 8 (lookup / build backward at config 3, on-demand at
             # config 5 next to the compiled reference kernel when oracle/_ref holds it): auxiliary,
             # measured after the timed regions above (tools/bench_rows.py states the work per row)
@@ -434,12 +460,13 @@ def main():
                 line["rows"] = bench_rows.collect(reps=5, ref_kernel=False)   # no oracle/ here
             except Exception as e:                      # noqa: BLE001
                 line["rows"] = {"error": repr(e)}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
+            # N=1 only: at N>1 the other ranks would spin in the closing barrier on the host cores being timed
             threads = os.cpu_count() or 1
-            rate, reps, el = cpu_path_rate(H, W, iters, batch=1, budget_s=12.0, threads=threads)
-            line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port",
+            rate, reps, el, kind, what = cpu_path_rate(H, W, iters, batch=1, budget_s=12.0, threads=threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": kind,
                                     "sample": f"{reps} x 1 pair (build + {iters} lookups) in {el:.1f} s, "
-                                              f"oracle/corr_torch.py on torch {torch.__version__} CPU ops"}
+                                              f"{what}, torch {torch.__version__} CPU ops"}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -1,0 +1,234 @@
+"""GPU: the UNMODIFIED reference models (baseline/_ref = /root/reference/pytorch/core, copied by
+baseline/install_ref.py) with the drop-in classes bound in through ``patch_reference()``,
+against the same models with the reference's own CorrBlock on the same GPU.
+
+One test per configuration of BASELINE.json:
+  cfg 1  RAFT 368x496, 12 iterations                       (raft.py:104-107,124)
+  cfg 2  RAFT 436x1024 (padded 440x1024), 12 iterations
+  cfg 3  L2L semi-supervised step: 368x768 crops + 432x1024 frames, 24 iterations, sequence
+         loss, two backward passes                          (l2l.py:52-57,82-113; train.py:270-277)
+  cfg 4  RAFTGMA 375x1242 (padded 376x1248)                 (gma_network.py:90,109)
+  cfg 5  RAFT(alternate_corr=True) 1088x1920, batch 2, vs the reference's own compiled
+         alt_cuda_corr kernel (oracle/_ref)                 (raft.py:104-105, corr.py:63-91)
+Tolerances (north_star): final flow <= 0.01 px mean EPE after 12 iterations; gradients <= 2e-3
+of the largest gradient of the tensor.
+"""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+import refmodels as rm  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def core():
+    return rm.core()
+
+
+def _run_both(model, *inputs, **kw):
+    """-> (reference arm, drop-in arm) outputs of the same model object."""
+    with torch.no_grad():
+        ref = model(*inputs, **kw)
+        with rm.patched() as names:
+            assert names, "patch_reference() found no import site"
+            ours = model(*inputs, **kw)
+    return ref, ours
+
+
+def test_cfg1_raft_368x496(core):
+    torch.manual_seed(1234)
+    model = core.raft.RAFT(rm.raft_args()).eval().cuda()
+    im1, im2 = (t.cuda() for t in rm.synth_pair(368, 496))
+    with rm.strict_fp32():
+        (low_r, up_r), (low_o, up_o) = _run_both(model, im1, im2, iters=12, test_mode=True)
+    assert tuple(up_o.shape) == (1, 2, 368, 496) and torch.isfinite(up_o).all()
+    assert float(up_r.abs().mean()) > 0.05            # a non-trivial flow, not two zero fields
+    assert rm.epe(up_o, up_r) <= 0.01, rm.epe(up_o, up_r)
+    assert float((low_o - low_r).abs().max()) <= 0.02
+
+
+def test_cfg2_raft_sintel_size_batch2(core):
+    torch.manual_seed(1234)
+    model = core.raft.RAFT(rm.raft_args()).eval().cuda()
+    im1, im2 = (t.cuda() for t in rm.synth_pair(440, 1024, seed=3, batch=2))
+    with rm.strict_fp32():
+        (_, up_r), (_, up_o) = _run_both(model, im1, im2, iters=12, test_mode=True)
+    assert rm.epe(up_o, up_r) <= 0.01, rm.epe(up_o, up_r)
+
+
+def test_cfg2_raft_32_iterations(core):
+    """configs[1] names 32 iterations; the parity bar is stated at 12, so this only has to stay close."""
+    torch.manual_seed(1234)
+    model = core.raft.RAFT(rm.raft_args()).eval().cuda()
+    im1, im2 = (t.cuda() for t in rm.synth_pair(440, 1024, seed=4))
+    with rm.strict_fp32():
+        (_, up_r), (_, up_o) = _run_both(model, im1, im2, iters=32, test_mode=True)
+    assert rm.epe(up_o, up_r) <= 0.03, rm.epe(up_o, up_r)
+
+
+def test_cfg4_raftgma_kitti_size(core):
+    torch.manual_seed(1234)
+    model = core.gma_network.RAFTGMA(rm.gma_args()).eval().cuda()
+    im1, im2 = (t.cuda() for t in rm.synth_pair(376, 1248, seed=5))
+    with rm.strict_fp32():
+        (_, up_r), (_, up_o) = _run_both(model, im1, im2, iters=12, test_mode=True)
+    assert tuple(up_o.shape) == (1, 2, 376, 1248)
+    assert rm.epe(up_o, up_r) <= 0.01, rm.epe(up_o, up_r)
+
+
+def test_cfg4_gmal2l_test_mode(core):
+    """GMAL2L (gma_l2l.py:56,75) in test mode: the student half through the GMA update block."""
+    torch.manual_seed(1234)
+    model = core.gma_l2l.GMAL2L(rm.gma_args()).eval().cuda()
+    im1, im2 = (t.cuda() for t in rm.synth_pair(184, 320, seed=6))
+    with rm.strict_fp32():
+        (_, up_r), (_, up_o) = _run_both(model, im1, im2, iters=12, test_mode=True)
+    assert rm.epe(up_o, up_r) <= 0.01, rm.epe(up_o, up_r)
+
+
+def _l2l_step(model, batch, n_iters=24):
+    """train.py:270-277: supervised call + backward, unsupervised call + backward (gradients
+    accumulate), no optimizer step."""
+    c1, c2, f1, f2, ox, oy, gt, valid = batch
+    model.zero_grad(set_to_none=True)
+    preds = model(c1, c2, f1, f2, ox, oy, iters=n_iters)
+    loss = rm.sequence_loss(preds, gt, valid)
+    loss.backward()
+    preds_u = model(c1.flip(0), c2.flip(0), f1.flip(0), f2.flip(0), ox, oy, iters=n_iters)
+    loss_u = rm.sequence_loss_unsup(preds_u)
+    loss_u.backward()
+    return float(loss), float(loss_u), [p.detach() for p in preds]
+
+
+@pytest.mark.parametrize("batch", [2])
+def test_cfg3_l2l_semi_supervised_step(core, batch):
+    torch.manual_seed(1234)
+    model = core.l2l.L2L(rm.raft_args()).cuda().train()
+    model.freeze_bn()                                                   # train.py:201-202
+    data = rm.l2l_batch(batch)
+    with rm.strict_fp32():
+        loss_r, lossu_r, preds_r = _l2l_step(model, data)
+        g_ref = rm.grad_dict(model)
+        with rm.patched():
+            loss_o, lossu_o, preds_o = _l2l_step(model, data)
+            g_our = rm.grad_dict(model)
+    model.zero_grad(set_to_none=True)
+    assert len(preds_o) == 24 and tuple(preds_o[-1].shape) == (batch, 2, 368, 768)
+    assert abs(loss_o - loss_r) <= 1e-3 * abs(loss_r) and abs(lossu_o - lossu_r) <= 1e-3 * max(abs(lossu_r), 1e-3)
+    assert rm.epe(preds_o[11], preds_r[11]) <= 0.01                      # student's last prediction
+    assert rm.epe(preds_o[-1], preds_r[-1]) <= 0.02                      # teacher's last prediction (24 iterations)
+    assert any(k.startswith("fnet.") for k in g_ref) and any(k.startswith("grad_update_block.") for k in g_ref)
+    worst = rm.compare_grads(g_our, g_ref, rel=5e-3)
+    print(f"cfg3 B={batch}: loss {loss_o:.6f}/{loss_r:.6f}  worst gradient deviation {worst:.2e}")
+
+
+def test_cfg3_l2l_data_parallel_replicas_match_single_gpu(core):
+    """train.py:183 wraps L2L in nn.DataParallel: the constructor of the block runs in worker
+    threads, one per device.  Needs 2 GPUs (skipped on a 1-GPU box)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    torch.manual_seed(1234)
+    model = core.l2l.L2L(rm.raft_args()).cuda().train()
+    model.freeze_bn()
+    dp = torch.nn.DataParallel(model, device_ids=[0, 1])
+    c1, c2, f1, f2, ox, oy, gt, valid = rm.l2l_batch(2)
+    with rm.strict_fp32(), rm.patched():
+        model.zero_grad(set_to_none=True)
+        preds = model(c1, c2, f1, f2, ox, oy, iters=8)
+        rm.sequence_loss(preds, gt, valid).backward()
+        g_one = rm.grad_dict(model)
+        model.zero_grad(set_to_none=True)
+        preds_dp = dp(c1, c2, f1, f2, ox, oy, iters=8)
+        rm.sequence_loss(preds_dp, gt, valid).backward()
+        g_dp = rm.grad_dict(model)
+    assert rm.epe(preds_dp[-1], preds[-1]) <= 1e-3
+    rm.compare_grads(g_dp, g_one, rel=5e-3)
+
+
+def test_cfg5_alternate_corr_full_size_vs_compiled_reference(core):
+    """RAFT(alternate_corr=True) at 1088x1920, batch 2: the reference arm runs its own
+    AlternateCorrBlock over its own compiled alt_cuda_corr kernel (oracle/_ref); ours runs the
+    drop-in AlternateCorrBlock (route 'auto' -> materialise on a 180 GB device) and, separately,
+    the on-demand route."""
+    from oracle import ref_ext
+    if not ref_ext.available():
+        pytest.skip("oracle/_ref/alt_cuda_corr_ref.so not built")
+    import flow_supervisor_b200 as fsb
+    torch.manual_seed(1234)
+    model = core.raft.RAFT(rm.raft_args(alternate_corr=True)).eval().cuda()
+    im1, im2 = (t.cuda() for t in rm.synth_pair(1088, 1920, seed=7, batch=2))
+    core.corr.alt_cuda_corr = ref_ext.load()                      # what `import alt_cuda_corr` (corr.py:5-9) would bind
+    iters = 4                                                      # the reference kernel needs ~0.1 s per lookup here
+    with rm.strict_fp32(), torch.no_grad():
+        low_r, up_r = model(im1, im2, iters=iters, test_mode=True)
+        outs = {}
+        for route in ("auto", "ondemand"):
+            fsb.AlternateCorrBlock.route = route
+            try:
+                with rm.patched():
+                    outs[route] = model(im1, im2, iters=iters, test_mode=True)
+            finally:
+                fsb.AlternateCorrBlock.route = "auto"
+    assert float(up_r.abs().mean()) > 0.05
+    for route, (low_o, up_o) in outs.items():
+        assert tuple(up_o.shape) == (2, 2, 1088, 1920)
+        assert rm.epe(up_o, up_r) <= 0.01, (route, rm.epe(up_o, up_r))
+
+
+def test_cfg5_alternate_block_values_full_size_vs_compiled_reference(core):
+    """Value-level comparison at 136x240 tokens, batch 2, D=256: drop-in AlternateCorrBlock (both
+    routes) vs the reference's AlternateCorrBlock over its compiled kernel.  Summation orders
+    differ (the reference accumulates 32-channel chunks with global +=), so the outputs are close,
+    not identical."""
+    from oracle import ref_ext
+    if not ref_ext.available():
+        pytest.skip("oracle/_ref/alt_cuda_corr_ref.so not built")
+    import flow_supervisor_b200 as fsb
+    g = torch.Generator().manual_seed(11)
+    B, D, H, W = 2, 256, 136, 240
+    f1 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
+    f2 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
+    coords = (fsb.coords_grid(B, H, W) + 6.0 * torch.randn(B, 2, H, W, generator=g)).cuda()
+    core.corr.alt_cuda_corr = ref_ext.load()
+    ref = core.corr.AlternateCorrBlock(f1, f2, num_levels=4, radius=4)(coords)
+    scale = float(ref.abs().max())
+    diffs = {}
+    for route in ("materialise", "ondemand"):
+        fsb.AlternateCorrBlock.route = route
+        try:
+            out = fsb.AlternateCorrBlock(f1, f2, num_levels=4, radius=4)(coords)
+        finally:
+            fsb.AlternateCorrBlock.route = "auto"
+        diffs[route] = float((out - ref).abs().max()) / scale
+        assert torch.equal(out == 0, ref == 0) or float(((out == 0) != (ref == 0)).float().mean()) < 1e-6
+    print("cfg5 max rel diff vs compiled reference kernel:", diffs)
+    assert all(d <= 1e-4 for d in diffs.values()), diffs
+    assert any(d > 0 for d in diffs.values()), "bit-identical outputs across different summation orders: comparing a tensor with itself?"
+
+
+def test_cfg3_l2l_ddp_two_gpus_equals_single_gpu_on_the_concatenated_batch(core, tmp_path):
+    """The only exchange of training is DDP's gradient all-reduce (NCCL): a 2-rank step on half
+    batches gives the gradients of the 1-GPU step on the whole batch.  Needs 2 GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    n_iters, world = 8, 2
+    out = str(tmp_path / "ddp_grads.pt")
+    mp.spawn(rm.ddp_l2l_worker, args=(world, 29531, out, n_iters), nprocs=world, join=True)
+    g_ddp = {k: v.cuda() for k, v in torch.load(out).items()}
+    torch.manual_seed(1234)
+    model = core.l2l.L2L(rm.raft_args()).cuda().train()
+    model.freeze_bn()
+    c1, c2, f1, f2, ox, oy, gt, valid = rm.l2l_batch(world)
+    with rm.strict_fp32(), rm.patched():
+        preds = model(c1, c2, f1, f2, ox, oy, iters=n_iters)
+        rm.sequence_loss(preds, gt, valid).backward()
+    rm.compare_grads(g_ddp, rm.grad_dict(model), rel=5e-3)
