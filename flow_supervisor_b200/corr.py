@@ -15,13 +15,16 @@ Modes (class attributes, or environment variables read at import):
                           '3xbf16' tensor-core parity mode when the shape allows it
                           (D % 64 == 0, D <= 256, W <= 256 tokens), else 'fp32' CUDA-core mode;
                           both are this library's own kernels and both meet the 1e-4 contract)
-    CorrBlock.volume     'f32'  | 'bf16'              (FLOWCORR_VOLUME)
+    CorrBlock.volume     'f32'  | 'bf16'              (FLOWCORR_VOLUME; 'bf16' = inference-only bf16 VOLUME written by the
+                          tensor-core build, read by the same lookup kernel at half the bytes; values within 2^-8
+                          of the fp32-volume lookup, final flow within 0.05 px -- stated separately from the fp32 contract)
     CorrBlock.coord_mode 'cuda' | 'cpu'               (FLOWCORR_COORD; which device's
                           rounding of utils.py:61-62 to reproduce; default 'cuda')
 """
 from __future__ import annotations
 
 import os
+import sys
 
 import torch
 
@@ -32,9 +35,18 @@ _VOL = {"f32": _lib.VOL_F32, "bf16": _lib.VOL_BF16}
 _COORD = {"cuda": _lib.COORD_CUDA, "cpu": _lib.COORD_CPU}
 
 
+_noted = set()
+
+
 def resolve_math(name: str, D: int, W: int) -> int:
     if name == "auto":
-        name = "3xbf16" if (D % 64 == 0 and D <= 256 and (W + 7) // 8 * 8 <= 256) else "fp32"
+        # tensor-core kernel: D a multiple of 64 up to 256, 16 <= padded width <= 256 tokens (a tile of two
+        # target rows is one UMMA N, 32..256); everything else runs the CUDA-core fp32 mode
+        name = "3xbf16" if (D % 64 == 0 and D <= 256 and 16 <= (W + 7) // 8 * 8 <= 256) else "fp32"
+        if name == "fp32" and (D, W) not in _noted and os.environ.get("FLOWCORR_VERBOSE", "1") != "0":
+            _noted.add((D, W))
+            print(f"[flowcorr] CorrBlock: D={D}, {W} tokens wide is outside the tensor-core build's range "
+                  "(D % 64 == 0, D <= 256, 9..256 tokens): using the fp32 CUDA-core mode", file=sys.stderr)
     return _MATH[name]
 
 

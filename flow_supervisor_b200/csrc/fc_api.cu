@@ -4,6 +4,11 @@
 #include <cstdio>
 #include <cmath>
 #include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <set>
+#include <string>
 
 #include "fc_tma.cuh"
 
@@ -53,6 +58,98 @@ EncodeTiledFn tensor_map_encoder() {
         return reinterpret_cast<EncodeTiledFn>(p);
     }();
     return fn;
+}
+
+const Tunables& tunables() {
+    static const Tunables t = []() {
+        Tunables v{};
+        auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+#ifdef FC_PROBES
+        v.probe = geti("FLOWCORR_PROBE", 0);
+#endif
+        v.build_sched = geti("FLOWCORR_BUILD_SCHED", 1);
+        v.build_stages = geti("FLOWCORR_BUILD_STAGES", 0);
+        v.build_epi_warps = geti("FLOWCORR_BUILD_EPI_WARPS", 4) == 8 ? 8 : 4;
+        v.no_fuse = getenv("FLOWCORR_NO_FUSE") != nullptr;
+        v.verbose = geti("FLOWCORR_VERBOSE", 1);
+        return v;
+    }();
+    return t;
+}
+
+int sm_count_cached() {
+    static thread_local int cached_dev = -1, cached_sm = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) { cached_sm = n; cached_dev = dev; }
+    }
+    return cached_sm;
+}
+
+void note_once(const char* key, const char* fmt, ...) {
+    if (!tunables().verbose) return;
+    static std::mutex mu;
+    static std::set<std::string> seen;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (!seen.insert(key).second) return;
+    }
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "[flowcorr] %s\n", buf);
+}
+
+// ---- memoised tensor-map encoder
+namespace {
+struct EncKey {
+    const void* base; int dtype, rank, swizzle, l2;
+    cuuint64_t dims[5], strides[4]; cuuint32_t box[5];
+    bool operator==(const EncKey& o) const { return memcmp(this, &o, sizeof(EncKey)) == 0; }
+};
+constexpr int ENC_CACHE = 1024;               // direct-mapped by a hash of the key
+std::mutex g_enc_mutex;
+EncKey g_enc_keys[ENC_CACHE];
+CUtensorMap g_enc_vals[ENC_CACHE];
+bool g_enc_valid[ENC_CACHE];
+unsigned enc_hash(const EncKey& k) {
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(&k);
+    unsigned long long h = 1469598103934665603ull;                       // FNV-1a
+    for (size_t i = 0; i < sizeof(EncKey); ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return (unsigned)(h ^ (h >> 32)) % ENC_CACHE;
+}
+}  // namespace
+
+int encode_tiled_cached(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* base,
+                        const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                        CUtensorMapSwizzle swizzle, CUtensorMapL2promotion l2) {
+    EncKey k;
+    memset(&k, 0, sizeof(k));
+    k.base = base; k.dtype = (int)dtype; k.rank = rank; k.swizzle = (int)swizzle; k.l2 = (int)l2;
+    for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) k.strides[i] = strides_bytes[i];
+    const unsigned slot = enc_hash(k);
+    {
+        std::lock_guard<std::mutex> g(g_enc_mutex);
+        if (g_enc_valid[slot] && g_enc_keys[slot] == k) { *out = g_enc_vals[slot]; return FC_OK; }
+    }
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FC_ECUDA; }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank %d, dims %llu x %llu, box %u x %u", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 1), box[0], rank > 1 ? box[1] : 1u);
+        return FC_ECUDA;
+    }
+    std::lock_guard<std::mutex> g(g_enc_mutex);
+    g_enc_keys[slot] = k; g_enc_vals[slot] = *out; g_enc_valid[slot] = true;
+    return FC_OK;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -135,6 +232,9 @@ extern "C" int fc_build_bwd(float* grad_pyramid, const float* fmap1, const float
     // tensor-core kernel does not take (fc_build_bwd_workspace_bytes == 0) run the fp32 mode
     if (math != FC_MATH_FP32 && tc_bwd_supported(D, H, W))
         return tc_build_bwd(grad_pyramid, fmap1, fmap2, dfmap1, dfmap2, pyr, D, H, W, math, workspace, workspace_bytes, s);
+    if (math != FC_MATH_FP32)
+        note_once("build_bwd_simt", "fc_build_bwd: D=%d, %dx%d tokens is outside the tensor-core backward's range "
+                  "(D %% 64 == 0, D <= 256, padded map <= 16384 targets): running the fp32 CUDA-core contractions", D, H, W);
     if (int e = simt_fold(grad_pyramid, pyr, s)) return e;
     return simt_build_bwd(grad_pyramid, fmap1, fmap2, dfmap1, dfmap2, pyr, D, H, W, s);
 }

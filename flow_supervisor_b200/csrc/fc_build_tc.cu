@@ -23,8 +23,9 @@
 // warps (TMEM lane quarter = warp_id % 4): warps 2-5, or warps 4-11 with two warps per quarter
 // splitting the tile's columns.
 //
-// Diagnostic switches (read per call, none needed in production): FLOWCORR_PROBE (stage probes, results are
-// garbage), FLOWCORR_BUILD_EPI_WARPS=4|8, FLOWCORR_BUILD_STAGES=1..4, FLOWCORR_BUILD_SCHED=0|1, FLOWCORR_NO_FUSE.
+// Diagnostic switches (fc::tunables(): read from the environment once per process, none needed in production):
+// FLOWCORR_BUILD_EPI_WARPS=4|8, FLOWCORR_BUILD_STAGES=1..4, FLOWCORR_BUILD_SCHED=0|1, FLOWCORR_NO_FUSE; the stage probes
+// (FLOWCORR_PROBE, results are garbage) exist only in a library compiled with -DFC_PROBES.
 #include <cstdlib>
 
 #include "fc_umma.cuh"
@@ -124,16 +125,34 @@ __device__ __forceinline__ void st_v8(float* dst, const float* v) {
                  : "memory");
 }
 
+// 8 / 4 consecutive volume elements from fp32 registers: fp32 volume = 32 / 16 bytes, bf16 volume = 16 / 8 bytes (RN)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 v(__float2bfloat16_rn(lo), __float2bfloat16_rn(hi));
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ void vol_store8(float* dst, const float* v) { st_v8(dst, v); }
+__device__ __forceinline__ void vol_store8(__nv_bfloat16* dst, const float* v) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                                pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void vol_store4(float* dst, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(dst) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void vol_store4(__nv_bfloat16* dst, float a, float b, float c, float d) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+}
+template <int VB> struct VolT { using type = float; };
+template <> struct VolT<1> { using type = __nv_bfloat16; };
+
 struct TcStoreMaps {
     CUtensorMap l0_c32, l0_c16;    // level 0 as {NP, N, B}: boxes of 32 queries x 32 / 16 columns
 };
 
 struct TcParams {
-    float* lvl[4];         // fused pyramid: level base pointers (level 0 == vol0)
+    void* lvl[4];          // fused pyramid: level base pointers (level 0 == vol0), fp32 or bf16 elements
     int lvH[4], lvW[4], lvWp[4], lvHp[4];
     int n_fused;           // levels written by the epilogue (1 = level 0 only)
     int W;                 // valid target columns of level 0
-    float* vol0;           // level 0: (B*N, NP)
     int N, NP, H, Wp;      // queries per sample, padded targets per sample
     int halves;            // tiles per row pair: 1 (2 * Wp <= 256) or 2 (tile 0 = first NT targets of the row pair in patch
                            // order = both rows x columns [0, NT / 2); tile 1 = the remaining 2 * Wp - NT)
@@ -152,7 +171,7 @@ struct TcParams {
                            // 5 = pooled-level stores off, 6 = level-0 stores off, 7 = no target-operand loads
 };
 
-template <int KB, int EW>   // KB = D / 64 k-blocks, EW = epilogue warps (4 or 8)
+template <int KB, int EW, int VB>   // KB = D / 64 k-blocks, EW = epilogue warps (4 or 8), VB = 1: bf16 volume
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc_threads(EW), 1)
 tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -261,7 +280,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             const uint32_t ph = phase;
                             if (++slot == P.stages) { slot = 0; phase ^= 1u; }
                             mbar_wait(b_empty + s, ph ^ 1u);
-                            if (P.probe == 7) {                // no target loads (stage probe)
+                            if (FC_PROBE_VAL(P) == 7) {                // no target loads (stage probe)
                                 if (leader) mbar_arrive(b_full + s);
                                 continue;
                             }
@@ -306,7 +325,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             const uint32_t al_addr = smem_u32(a_lo + kb * TC_ABLK_BYTES);
 #pragma unroll
                             for (int k = 0; k < TC_BK / 16; ++k) {
-                                if (P.probe == 2) break;
+                                if (FC_PROBE_VAL(P) == 2) break;
                                 const uint64_t bd = umma_desc_sw128(b_addr + k * 32);
                                 // part 0: B = hi -> A_hi*B_hi (+ A_lo*B_hi); part 1: B = lo -> A_hi*B_lo
                                 umma2_bf16(d_addr, umma_desc_sw128(ah_addr + k * 32), bd, idesc, (kb | part | k) != 0 ? 1u : 0u);
@@ -334,6 +353,10 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         constexpr int NH = EW / 4;                             // warps per TMEM lane quarter
         constexpr int CMAX = 8 / NH;                           // chunk slots per warp
         constexpr int NBUF = 8 / EW;                           // staging boxes per warp
+        using vol_t = typename VolT<VB>::type;
+        vol_t* const lv1 = static_cast<vol_t*>(P.lvl[1]);
+        vol_t* const lv2 = static_cast<vol_t*>(P.lvl[2]);
+        vol_t* const lv3 = static_cast<vol_t*>(P.lvl[3]);
         const int ew = warp - tc_first_epi_warp(EW);
         const int quarter = warp & 3, half_id = ew >> 2;
         float* sbuf0 = stg + ew * NBUF * TC_STG_FLOATS;        // this warp's 4 KB staging box(es)
@@ -373,7 +396,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const int c_lo = NH == 1 ? 0 : ((n_chunks > 2 || half_id == 0) ? half_id * CH : 8);
             auto chunk_of = [&](int cc) { return ilv ? ((cc >> 1) * 4 + half_id * 2 + (cc & 1)) : (c_lo + cc); };
             float l2[CMAX][4];
-            if (P.probe != 3) {
+            if (FC_PROBE_VAL(P) != 3) {
 #pragma unroll
               for (int cc = 0; cc < CMAX; ++cc) {
                 const int c = chunk_of(cc);                    // chunk inside the tile
@@ -392,7 +415,23 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     ++use;
                     if (lane == 0) tma_wait_group_read<NBUF - 1>();   // the store that last read this box is done
                     __syncwarp();
-                    if (rem >= 32) {
+                    if (VB) {
+                        // bf16 volume: rows of 64 bytes (SWIZZLE_64B box of 32 columns) or 32 bytes (plain box of 16)
+                        uint4* sb = reinterpret_cast<uint4*>(sbuf);
+                        if (rem >= 32) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                sb[lane * 4 + (k ^ ((lane >> 1) & 3))] =
+                                    make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                                               pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                sb[lane * 2 + k] =
+                                    make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                                               pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+                        }
+                    } else if (rem >= 32) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
                             *reinterpret_cast<float4*>(sbuf + lane * 32 + ((k ^ (lane & 7)) << 2)) =
@@ -405,7 +444,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0 && rows_valid > 0 && P.probe != 1 && P.probe != 6) {
+                    if (lane == 0 && rows_valid > 0 && FC_PROBE_VAL(P) != 1 && FC_PROBE_VAL(P) != 6) {
                         tma_store_3d(rem >= 32 ? &SM.l0_c32 : &SM.l0_c16, smem_u32(sbuf), q0 + c * 32, row0, b);
                         tma_commit_group();
                     }
@@ -421,8 +460,8 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                                                                     v[16 * pp + 8 + 2 * j]), v[16 * pp + 8 + 2 * j + 1]);
                                 l1[4 * pp + j] = (8 * gc + 4 * pp + j < W1) ? a * 0.25f : 0.f;
                             }
-                        if (rp < P.lvH[1] && 8 * gc < P.lvWp[1] && mine && P.probe != 1 && P.probe != 5)
-                            st_v8(P.lvl[1] + qrow * ms1 + (long long)(rp >> 1) * 2 * P.lvWp[1] + gc * 16 + (rp & 1) * 8, l1);
+                        if (rp < P.lvH[1] && 8 * gc < P.lvWp[1] && mine && FC_PROBE_VAL(P) != 1 && FC_PROBE_VAL(P) != 5)
+                            vol_store8(lv1 + qrow * ms1 + (long long)(rp >> 1) * 2 * P.lvWp[1] + gc * 16 + (rp & 1) * 8, l1);
                         if (P.n_fused > 2) {
                             if ((rp & 1) == 0) {
 #pragma unroll
@@ -447,17 +486,17 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(t_empty + buf, 0);
 
-            if (P.n_fused > 2 && (rp & 1) && P.probe != 3) {
+            if (P.n_fused > 2 && (rp & 1) && FC_PROBE_VAL(P) != 3) {
                 // ---- level 2: row y2 = rp / 2, columns [4 gc, 4 gc + 4) per chunk -> 32-byte runs per chunk pair
                 const int y2 = rp >> 1;
-                const bool st = mine && P.probe != 1 && P.probe != 5;
+                const bool st = mine && FC_PROBE_VAL(P) != 1 && FC_PROBE_VAL(P) != 5;
 #pragma unroll
                 for (int cp = 0; cp < CMAX / 2; ++cp) {
                     const int gc = H * (P.NT >> 5) + chunk_of(2 * cp);
                     if (2 * cp < CH && y2 < P.lvH[2] && 4 * gc < P.lvWp[2] && st) {
                         const float o[8] = {l2[2 * cp][0], l2[2 * cp][1], l2[2 * cp][2], l2[2 * cp][3],
                                             l2[2 * cp + 1][0], l2[2 * cp + 1][1], l2[2 * cp + 1][2], l2[2 * cp + 1][3]};
-                        st_v8(P.lvl[2] + qrow * ms2 + (long long)(y2 >> 1) * 2 * P.lvWp[2] + (gc >> 1) * 16 + (y2 & 1) * 8, o);
+                        vol_store8(lv2 + qrow * ms2 + (long long)(y2 >> 1) * 2 * P.lvWp[2] + (gc >> 1) * 16 + (y2 & 1) * 8, o);
                     }
                 }
                 if (P.n_fused > 3) {
@@ -483,22 +522,21 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             // (narrow tiles: the one active warp also writes the zero pad columns 4..7 of the patch)
                             // (a warp that owns whole level-3 patches completes them: 4 chunks = 8 columns, zeros past the map)
                             if ((2 * cp < (NH == 1 ? ((CH + 3) & ~3) : CH) || n_chunks <= 2) && y3 < P.lvH[3] && 2 * gc < P.lvWp[3] && st)
-                                *reinterpret_cast<float4*>(P.lvl[3] + qrow * ms3 + (long long)(y3 >> 1) * 2 * P.lvWp[3] +
-                                                           (gc >> 2) * 16 + (y3 & 1) * 8 + ((gc >> 1) & 1) * 4) =
-                                    make_float4(o[0], o[1], o[2], o[3]);
+                                vol_store4(lv3 + qrow * ms3 + (long long)(y3 >> 1) * 2 * P.lvWp[3] +
+                                               (gc >> 2) * 16 + (y3 & 1) * 8 + ((gc >> 1) & 1) * 4, o[0], o[1], o[2], o[3]);
                         }
                     }
                 }
             }
-            if (fused && rp == P.n_rp - 1 && H == P.halves - 1 && mine && P.probe != 1 && P.probe != 5) {
+            if (fused && rp == P.n_rp - 1 && H == P.halves - 1 && mine && FC_PROBE_VAL(P) != 1 && FC_PROBE_VAL(P) != 5) {
                 // pad row (y = Hl, Hl odd) of every pooled level: the lookup's TMA boxes read whole
                 // row pairs, so it must hold zeros (the tile loop itself never produces it)
                 const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 for (int l = 1; l < P.n_fused; ++l)
                     if (P.lvHp[l] > P.lvH[l]) {
                         const int y = P.lvH[l], wp = P.lvWp[l];
-                        float* rowp = P.lvl[l] + qrow * ((long long)P.lvHp[l] * wp) + (long long)(y >> 1) * 2 * wp + (y & 1) * 8;
-                        for (int g = half_id; g * 8 < wp; g += NH) st_v8(rowp + g * 16, z);
+                        vol_t* rowp = static_cast<vol_t*>(P.lvl[l]) + qrow * ((long long)P.lvHp[l] * wp) + (long long)(y >> 1) * 2 * wp + (y & 1) * 8;
+                        for (int g = half_id; g * 8 < wp; g += NH) vol_store8(rowp + g * 16, z);
                     }
             }
             ++tc;
@@ -531,31 +569,19 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 // 2-D bf16 row-major [rows][cols] tensor, box {box_cols, box_rows}; box_cols = 64 -> 128-byte
 // swizzle (query operand), 32 -> 64-byte swizzle (target operand stages)
 static int make_map(CUtensorMap* map, const void* base, long long rows, int cols, int box_rows, int box_cols) {
-    EncodeTiledFn enc = tensor_map_encoder();
-    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FC_ECUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return FC_ECUDA; }
-    return FC_OK;
+    return encode_tiled_cached(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box,
+                               box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
-// fp32 tensor of `rank` dims (dim 0 contiguous): the epilogue's store boxes
-static int make_f32_map(CUtensorMap* map, float* base, int rank, const cuuint64_t* dims,
+// volume tensor (fp32 or bf16 elements) of `rank` dims (dim 0 contiguous): the epilogue's store boxes
+static int make_vol_map(CUtensorMap* map, void* base, bool bf16, int rank, const cuuint64_t* dims,
                         const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
-    EncodeTiledFn enc = tensor_map_encoder();
-    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FC_ECUDA; }
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (store map, rank %d) failed (%d)", rank, (int)r); return FC_ECUDA; }
-    return FC_OK;
+    return encode_tiled_cached(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, base, dims,
+                               strides_bytes, box, swizzle, CU_TENSOR_MAP_L2_PROMOTION_NONE);
 }
 
 struct TcLayout { size_t a_hi, a_lo, b_hi, b_lo, total; long long NP; };
@@ -578,35 +604,46 @@ size_t tc_build_workspace_bytes(int B, int D, int H, int W, int, int) {
     return tc_layout(B, D, H, W).total + 1024;   // slack to align the base to 1 KB
 }
 
-template <int KB, int EW>
+template <int KB, int EW, int VB>
 static int launch_tc(const CUtensorMap* maps, const TcStoreMaps& SM, const TcParams& P, int B, cudaStream_t s) {
     const size_t smem = 1024 + 2 * KB * TC_ABLK_BYTES + TC_STAGES * TC_STAGE_BYTES + TC_STG_BYTES + 256;
-    FC_CUDA(cudaFuncSetAttribute(tc_build_kernel<KB, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // persistent: one CTA pair (cluster 2x1x1) per co-resident SM pair
-    int n_clusters = 0;
-    {
+    FC_SMEM_ATTR_ONCE((tc_build_kernel<KB, EW, VB>), smem);
+    // persistent: one CTA pair (cluster 2x1x1) per co-resident SM pair; the occupancy query runs once per
+    // (kernel instantiation, device)
+    static std::atomic<int> clusters_of[64];
+    int dev = 0, n_clusters = 0;
+    FC_CUDA(cudaGetDevice(&dev));
+    n_clusters = clusters_of[dev & 63].load(std::memory_order_acquire);
+    if (n_clusters == 0) {
+        int n_sm = 0;
+        FC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(tc_threads(EW)); cfg.dynamicSmemBytes = smem;
+        cfg.gridDim = dim3(n_sm & ~1); cfg.blockDim = dim3(tc_threads(EW)); cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute attr;
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr; cfg.numAttrs = 1;
-        FC_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, tc_build_kernel<KB, EW>, &cfg));
+        FC_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, tc_build_kernel<KB, EW, VB>, &cfg));
+        clusters_of[dev & 63].store(n_clusters, std::memory_order_release);
     }
     if (n_clusters < 1) { set_error("fc_build: no CTA pair of the tensor-core kernel fits on this device"); return FC_ECUDA; }
     if (n_clusters > P.units) n_clusters = P.units;
     dim3 grid(2 * n_clusters);
-    tc_build_kernel<KB, EW><<<grid, tc_threads(EW), smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], SM, P);
+    tc_build_kernel<KB, EW, VB><<<grid, tc_threads(EW), smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], SM, P);
     FC_LAUNCH_CHECK("tc_build_kernel");
     return FC_OK;
 }
 
 int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr, int D, int H, int W,
              int vol_dtype, int math, void* ws, size_t ws_bytes, cudaStream_t s) {
-    FC_REQUIRE(vol_dtype == FC_VOL_F32, "fc_build: tensor-core modes write an fp32 volume (bf16 volume not built yet)");
+    FC_REQUIRE(vol_dtype == FC_VOL_F32 || vol_dtype == FC_VOL_BF16, "fc_build: unknown vol_dtype %d", vol_dtype);
+    const bool vb = vol_dtype == FC_VOL_BF16;
+    const size_t es = vb ? 2 : 4;
+    FC_REQUIRE(!vb || (pyr.L <= 4 && !tunables().no_fuse),
+               "fc_build: the bf16 volume is written by the fused epilogue only (num_levels <= 4, got %d)", pyr.L);
     FC_REQUIRE(D % 64 == 0 && D <= 256, "fc_build: tensor-core modes need D %% 64 == 0 and D <= 256 (got %d); use FC_MATH_FP32", D);
     const int Wp = pyr.lv[0].Wp;
-    FC_REQUIRE(Wp <= 256, "fc_build: tensor-core modes need W <= 256 tokens (got %d); use FC_MATH_FP32", W);
+    FC_REQUIRE(Wp >= 16 && Wp <= 256, "fc_build: tensor-core modes need 9 <= W <= 256 tokens (got %d); use FC_MATH_FP32", W);
     const int B = pyr.B;
     const TcLayout L = tc_layout(B, D, H, W);
     if (!ws || ws_bytes < L.total) { set_error("fc_build: workspace %zu < %zu bytes", ws_bytes, L.total); return FC_EWORKSPACE; }
@@ -641,13 +678,13 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     }
 
     TcParams P{};
-    P.vol0 = static_cast<float*>(pyramid) + pyr.lv[0].offset;
     P.W = W;
     // the epilogue produces the pyramid itself when a tile holds two whole target rows
-    const bool fuse = pyr.L >= 2 && getenv("FLOWCORR_NO_FUSE") == nullptr;
+    const Tunables& T = tunables();
+    const bool fuse = pyr.L >= 2 && !T.no_fuse;
     P.n_fused = fuse ? (pyr.L < 4 ? pyr.L : 4) : 1;
     for (int l = 0; l < 4 && l < pyr.L; ++l) {
-        P.lvl[l] = static_cast<float*>(pyramid) + pyr.lv[l].offset;
+        P.lvl[l] = static_cast<uint8_t*>(pyramid) + (size_t)pyr.lv[l].offset * es;
         P.lvH[l] = pyr.lv[l].H; P.lvW[l] = pyr.lv[l].W; P.lvWp[l] = pyr.lv[l].Wp; P.lvHp[l] = pyr.lv[l].Hp;
     }
     P.N = N; P.NP = (int)NP; P.H = H; P.Wp = Wp;
@@ -663,10 +700,10 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     P.units = B * P.mp * P.groups;
     P.three_pass = three ? 1 : 0;
     P.stages = TC_STAGES;
-    { const char* sc = getenv("FLOWCORR_BUILD_SCHED"); P.sched = sc ? atoi(sc) : 1; }
-    if (const char* st = getenv("FLOWCORR_BUILD_STAGES")) { const int v = atoi(st); if (v >= 1 && v <= TC_STAGES) P.stages = v; }
+    P.sched = T.build_sched;
+    if (T.build_stages >= 1 && T.build_stages <= TC_STAGES) P.stages = T.build_stages;
     P.scale = fold_scale ? 1.0f : inv_sqrt_d;
-    { const char* pr = getenv("FLOWCORR_PROBE"); P.probe = pr ? atoi(pr) : 0; }
+    P.probe = T.probe;
 
     CUtensorMap maps[6];
     if (int e = make_map(&maps[0], a_hi, (long long)B * N, D, TC_BM, TC_BK)) return e;
@@ -680,28 +717,29 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     // store maps (see the epilogue)
     TcStoreMaps SM;
     {
-        float* l0 = static_cast<float*>(pyramid) + pyr.lv[0].offset;
+        void* l0 = P.lvl[0];
         cuuint64_t dims[3] = {(cuuint64_t)NP, (cuuint64_t)N, (cuuint64_t)B};
-        cuuint64_t str[2] = {(cuuint64_t)NP * 4, (cuuint64_t)N * NP * 4};
+        cuuint64_t str[2] = {(cuuint64_t)NP * es, (cuuint64_t)N * NP * es};
         cuuint32_t box32[3] = {32, 32, 1}, box16[3] = {16, 32, 1};
-        if (int e = make_f32_map(&SM.l0_c32, l0, 3, dims, str, box32, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-        if (int e = make_f32_map(&SM.l0_c16, l0, 3, dims, str, box16, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+        // staging rows: fp32 128 / 64 bytes, bf16 64 / 32 bytes (see the epilogue)
+        if (int e = make_vol_map(&SM.l0_c32, l0, vb, 3, dims, str, box32, vb ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+        if (int e = make_vol_map(&SM.l0_c16, l0, vb, 3, dims, str, box16, vb ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B)) return e;
     }
 
     int e;
     // 4 epilogue warps measured 2.5 % faster than 8 in the three-pass mode at cfg 2 (same box, round robin:
     // profiles/r01j_build_epilogue_warps_ab.jsonl) and equal in single-pass mode; FLOWCORR_BUILD_EPI_WARPS=8 selects the other
-    int ewarps = 4;
-    if (const char* ev = getenv("FLOWCORR_BUILD_EPI_WARPS")) ewarps = atoi(ev) == 8 ? 8 : 4;
+    const int ewarps = T.build_epi_warps;
     const int kbs = D / 64;
-    if (ewarps == 8) {
-        e = kbs == 1 ? launch_tc<1, 8>(maps, SM, P, B, s) : kbs == 2 ? launch_tc<2, 8>(maps, SM, P, B, s)
-          : kbs == 3 ? launch_tc<3, 8>(maps, SM, P, B, s) : launch_tc<4, 8>(maps, SM, P, B, s);
-    } else {
-        e = kbs == 1 ? launch_tc<1, 4>(maps, SM, P, B, s) : kbs == 2 ? launch_tc<2, 4>(maps, SM, P, B, s)
-          : kbs == 3 ? launch_tc<3, 4>(maps, SM, P, B, s) : launch_tc<4, 4>(maps, SM, P, B, s);
-    }
+#define FC_TC_LAUNCH(EWV, VBV)                                                                           \
+    (kbs == 1 ? launch_tc<1, EWV, VBV>(maps, SM, P, B, s) : kbs == 2 ? launch_tc<2, EWV, VBV>(maps, SM, P, B, s) \
+   : kbs == 3 ? launch_tc<3, EWV, VBV>(maps, SM, P, B, s) : launch_tc<4, EWV, VBV>(maps, SM, P, B, s))
+    if (vb) e = FC_TC_LAUNCH(4, 1);                          // bf16 volume: half the store bytes, the 4-warp epilogue
+    else if (ewarps == 8) e = FC_TC_LAUNCH(8, 0);
+    else e = FC_TC_LAUNCH(4, 0);
+#undef FC_TC_LAUNCH
     if (e) return e;
+    if (vb) return FC_OK;                                    // (all levels fused: checked above)
     return simt_pool_levels(static_cast<float*>(pyramid), pyr, P.n_fused, s);
 }
 

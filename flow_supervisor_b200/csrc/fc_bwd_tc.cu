@@ -371,14 +371,8 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 // ---------------------------------------------------------------- host side
 static int encode_bf16(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
                        const cuuint64_t* strides_bytes, const cuuint32_t* box) {
-    EncodeTiledFn enc = tensor_map_encoder();
-    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FC_ECUDA; }
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (backward operand, rank %d) failed (%d)", rank, (int)r); return FC_ECUDA; }
-    return FC_OK;
+    return encode_tiled_cached(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides_bytes, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
 struct BwdLayout { size_t f1_hi, f1_lo, f2_hi, f2_lo, total; int N8, NPk; };
@@ -419,16 +413,20 @@ static int pick_ksplit(int m_units, int kb_total, int n_clusters) {
 template <int OP>
 static int launch_bwd_gemm(const CUtensorMap* maps, BwdParams P, int B, cudaStream_t s) {
     const size_t smem = 1024 + (size_t)BW_STAGES * BW_STAGE_BYTES + 256;
-    FC_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int n_clusters = 0;
-    {
+    FC_SMEM_ATTR_ONCE((tc_bwd_kernel<OP>), smem);
+    static std::atomic<int> clusters_of[64];                   // occupancy query once per (kernel instantiation, device)
+    int dev = 0;
+    FC_CUDA(cudaGetDevice(&dev));
+    int n_clusters = clusters_of[dev & 63].load(std::memory_order_acquire);
+    if (n_clusters == 0) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(BW_THREADS); cfg.dynamicSmemBytes = smem;
+        cfg.gridDim = dim3(sm_count_cached() & ~1); cfg.blockDim = dim3(BW_THREADS); cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute attr;
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr; cfg.numAttrs = 1;
         FC_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, tc_bwd_kernel<OP>, &cfg));
+        clusters_of[dev & 63].store(n_clusters, std::memory_order_release);
     }
     if (n_clusters < 1) { set_error("fc_build_bwd: no CTA pair of the tensor-core kernel fits on this device"); return FC_ECUDA; }
     P.ksplit = pick_ksplit(B * P.mp, P.kb_total, n_clusters);
@@ -469,7 +467,7 @@ int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float
         const dim3 grid((unsigned)((long long)B * N));
 #define FC_FOLD_CASE(LV)                                                                                              \
     case LV:                                                                                                          \
-        FC_CUDA(cudaFuncSetAttribute(bwd_fold_pack_kernel<LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        FC_SMEM_ATTR_ONCE((bwd_fold_pack_kernel<LV>), 227 * 1024);   /* the opt-in maximum: smem varies with the geometry */ \
         bwd_fold_pack_kernel<LV><<<grid, 256, smem, s>>>(F);                                                         \
         break;
         switch (pyr.L) {

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 
 #include "../../include/flowcorr.h"
 
@@ -34,6 +35,42 @@ void count_launch();          // fc_kernel_launches() instrumentation
         fc::count_launch();                                   \
         cudaError_t e__ = cudaPeekAtLastError();              \
         if (e__ != cudaSuccess) return fc::cuda_fail(e__, name); \
+    } while (0)
+
+// Stage probes (tools/probe_bounds.py) exist only in a library compiled with -DFC_PROBES; the shipped
+// library has no probe branches in its kernels and never reads FLOWCORR_PROBE.
+#ifdef FC_PROBES
+#define FC_PROBE_VAL(P) ((P).probe)
+#else
+#define FC_PROBE_VAL(P) 0
+#endif
+
+// Run-time switches, read from the environment ONCE per process (fc_api.cu).
+struct Tunables {
+    int probe;               // FLOWCORR_PROBE (FC_PROBES builds only, else 0)
+    int build_sched;         // FLOWCORR_BUILD_SCHED      0 | 1 (default 1: pair-tiles strided over the CTA pairs)
+    int build_stages;        // FLOWCORR_BUILD_STAGES     operand ring depth, 0 = kernel default
+    int build_epi_warps;     // FLOWCORR_BUILD_EPI_WARPS  4 | 8 (default 4)
+    int no_fuse;             // FLOWCORR_NO_FUSE          pyramid by separate pooling launches
+    int verbose;             // FLOWCORR_VERBOSE          log mode fall-backs (shape not taken by a tensor-core kernel) to stderr
+};
+const Tunables& tunables();
+// SM count of the current device (cached per host thread); 148 (B200) if the query fails
+int sm_count_cached();
+// one line on stderr the first time `key` is seen (FLOWCORR_VERBOSE=0 silences): fall-backs must not be silent
+void note_once(const char* key, const char* fmt, ...);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (call site = kernel instantiation, device)
+#define FC_SMEM_ATTR_ONCE(kernel, bytes)                                                                   \
+    do {                                                                                                   \
+        static std::atomic<unsigned long long> done__{0};                                                  \
+        int dev__ = 0;                                                                                     \
+        FC_CUDA(cudaGetDevice(&dev__));                                                                    \
+        const unsigned long long bit__ = 1ull << (dev__ & 63);                                             \
+        if (!(done__.load(std::memory_order_acquire) & bit__)) {                                           \
+            FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            done__.fetch_or(bit__, std::memory_order_release);                                             \
+        }                                                                                                  \
     } while (0)
 
 // ---------------------------------------------------------------- pyramid geometry

@@ -118,11 +118,12 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
         // footprint box as the forward sizes it, but clamped to non-negative tensor coordinates:
         // TMA loads zero-fill at negative coordinates, TMA stores / reductions TRAP there
         // (tools/probes/tma_reduce_probe.cu), while boxes overhanging the far edge are clipped
+        // ... and, like the forward's, clipped to the padded map at the far edge as well
         const int rp_lo = max(y0[0] >> 1, 0), pc_lo = max(x0a[0] >> 3, 0);
-        const int n_rp = ((y0[R - 1] + 1) >> 1) - rp_lo + 1;
-        const int n_pc = ((x0a[R - 1] + 1) >> 3) - pc_lo + 1;
-        const int sel = (n_rp > 5 ? 2 : 0) + (n_pc > 2 ? 1 : 0);
-        const int pitch = 64 * (n_pc > 2 ? 3 : 2);
+        const int n_rp = min(min((y0[R - 1] + 1) >> 1, P.nrp[level] - 1) - rp_lo + 1, 6);
+        const int n_pc = min(min((x0a[R - 1] + 1) >> 3, P.npc[level] - 1) - pc_lo + 1, 3);
+        const int sel = (n_rp > 0 && n_pc > 0) ? lk_shape(n_rp, n_pc) : 0;
+        const int pitch = 64 * n_pc;
         const int ybase = 2 * rp_lo, xbase = 8 * pc_lo;
         const int Hl = P.H[level], Wl = P.W[level];
         // some part of the window lies inside the map
@@ -195,8 +196,8 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
         group_sync(g);
         // every warp holds every query's box geometry: the 32 reduce-adds of the tile (one per lane, serialised
         // by the hardware's uniform-operand issue) are dealt out over the group's three warps
-        if (touches && P.probe != 1 && (lane % LB_GWARPS) == WI) {
-            if (P.probe == 2) tma_store_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, cur.gq);
+        if (touches && FC_PROBE_VAL(P) != 1 && (lane % LB_GWARPS) == WI) {
+            if (FC_PROBE_VAL(P) == 2) tma_store_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, cur.gq);
             else tma_reduce_add_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, cur.gq);
         }
         tma_commit_group();
@@ -225,10 +226,10 @@ static int launch_bwd(const LookupMaps& M, const LookupParams& P, int n_tiles, i
     const int want = (n_tiles + LB_GROUPS - 1) / LB_GROUPS;
     const int grid = want < n_sm ? want : n_sm;
     if (coord_mode == FC_COORD_CUDA) {
-        FC_CUDA(cudaFuncSetAttribute(lookup_bwd_kernel<RADIUS, FC_COORD_CUDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FC_SMEM_ATTR_ONCE((lookup_bwd_kernel<RADIUS, FC_COORD_CUDA>), smem);
         lookup_bwd_kernel<RADIUS, FC_COORD_CUDA><<<grid, LB_THREADS, smem, s>>>(M, P, n_tiles);
     } else {
-        FC_CUDA(cudaFuncSetAttribute(lookup_bwd_kernel<RADIUS, FC_COORD_CPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FC_SMEM_ATTR_ONCE((lookup_bwd_kernel<RADIUS, FC_COORD_CPU>), smem);
         lookup_bwd_kernel<RADIUS, FC_COORD_CPU><<<grid, LB_THREADS, smem, s>>>(M, P, n_tiles);
     }
     FC_LAUNCH_CHECK("lookup_bwd_kernel");
@@ -246,13 +247,15 @@ extern "C" int fc_lookup_bwd(const float* grad_out, const float* coords, float* 
     FC_REQUIRE((reinterpret_cast<uintptr_t>(grad_pyramid) & 15u) == 0, "fc_lookup_bwd: grad_pyramid must be 16-byte aligned");
     Pyramid pyr;
     FC_REQUIRE(make_pyramid(pyr, B, H, W, num_levels), "fc_lookup_bwd: bad geometry B=%d H=%d W=%d L=%d", B, H, W, num_levels);
+    FC_REQUIRE(coord_mode == FC_COORD_CUDA || coord_mode == FC_COORD_CPU,
+               "fc_lookup_bwd: coord_mode %d has no backward (AlternateCorrBlock is inference-only, corr.py:86)", coord_mode);
     if (int e = check_lookup_common(pyr, radius, coord_mode)) return e;
     LookupParams P{};
     fill_params(P, pyr, radius);
     P.pyr = nullptr; P.coords = coords;
     P.io = const_cast<float*>(grad_out); P.gpyr = grad_pyramid;
     LookupMaps M;
-    if (int e = get_level_maps(M, grad_pyramid, pyr, H, W)) return e;
+    if (int e = get_level_maps(M, grad_pyramid, pyr, H, W, 0)) return e;
     int n_sm = 0;
     if (int e = sm_count(n_sm)) return e;
     const int n_tiles = ((P.Q + QT - 1) / QT) * pyr.L;

@@ -20,23 +20,28 @@ struct LookupParams {
     int H[FC_MAX_LEVELS], W[FC_MAX_LEVELS], Wp[FC_MAX_LEVELS];
     int msize[FC_MAX_LEVELS];   // elements per query map (Hp * Wp)
     AxisConst ax[FC_MAX_LEVELS], ay[FC_MAX_LEVELS];
+    int nrp[FC_MAX_LEVELS], npc[FC_MAX_LEVELS];   // row pairs (Hp / 2) and 8-column patches (Wp / 8) per map
     float inv_scale[FC_MAX_LEVELS];
-    int probe;              // 0 in production; FLOWCORR_PROBE=n switches one pipeline stage off so that
-                            // tools/probe_bounds.py can time the others (results are then garbage)
+    int probe;              // always 0 unless the library is compiled with -DFC_PROBES (stage probes of tools/probe_bounds.py:
+                            // FLOWCORR_PROBE=n switches one pipeline stage off, results are then garbage)
     uint32_t div_m, div_s;  // gq / N without a division: (__umulhi(div_m, gq) + gq) >> div_s   (gq < 2^31)
     int32_t* dbg_x0;
     int32_t* dbg_y0;
     uint8_t* dbg_mask;
 };
 
-// Per level, four TMA views of the (gradient) pyramid as a 3-D tensor [query][row pair][2*Wp floats]
-// over the 2x8-patch layout: boxes of {2|3 patches, 5|6 row pairs, 1 query}.  Shared by the
-// forward (footprint loads) and the backward (footprint reduce-adds).  Memoised per
-// (pointer, geometry) in fc_lookup_fwd.cu.
+// Per level, 18 TMA views of the (gradient) pyramid as a 3-D tensor [query][row pair][2*Wp floats]
+// over the 2x8-patch layout: boxes of {1..3 patches, 1..6 row pairs, 1 query}.  A footprint box is CLIPPED to the
+// query's map in software: the TMA unit fetches every byte of a box from L2 / DRAM, also the parts it then
+// zero-fills because they lie outside the tensor (ncu, profiles/r02a: 168.4 MB of TMA load traffic per launch
+// = exactly the unclipped boxes, against 117.5 MB inside the maps).  Shared by the forward (footprint loads)
+// and the backward (footprint reduce-adds).  Memoised per (pointer, geometry) in fc_lookup_fwd.cu.
+constexpr int LK_SHAPES = 18;
+__host__ __device__ __forceinline__ int lk_shape(int n_rp, int n_pc) { return (n_rp - 1) * 3 + (n_pc - 1); }
 struct LookupMaps {
-    CUtensorMap m[FC_MAX_LEVELS][4];      // [level][(6 row pairs ? 2 : 0) + (3 patches ? 1 : 0)]
+    CUtensorMap m[FC_MAX_LEVELS][LK_SHAPES];      // [level][lk_shape(row pairs, patches)]
 };
-int get_level_maps(LookupMaps& M, const float* pyramid, const Pyramid& pyr, int H, int W);
+int get_level_maps(LookupMaps& M, const void* pyramid, const Pyramid& pyr, int H, int W, int vb);
 int sm_count(int& n_sm);
 
 #ifdef __CUDACC__
@@ -68,8 +73,12 @@ struct TileIt {
 inline void fill_params(LookupParams& P, const Pyramid& pyr, int radius) {
     P.Q = pyr.B * pyr.N;
     P.N = pyr.N; P.L = pyr.L;
+#ifdef FC_PROBES
     const char* pr = getenv("FLOWCORR_PROBE");
     P.probe = pr ? atoi(pr) : 0;
+#else
+    P.probe = 0;
+#endif
     // Granlund-Montgomery round-up multiplier for the divisor N
     P.div_s = 0;
     while ((1ull << P.div_s) < (unsigned long long)pyr.N) ++P.div_s;
@@ -80,6 +89,7 @@ inline void fill_params(LookupParams& P, const Pyramid& pyr, int radius) {
         P.off[l] = pyr.lv[l].offset;
         P.H[l] = pyr.lv[l].H; P.W[l] = pyr.lv[l].W; P.Wp[l] = pyr.lv[l].Wp;
         P.msize[l] = pyr.lv[l].Hp * pyr.lv[l].Wp;
+        P.nrp[l] = pyr.lv[l].Hp / 2; P.npc[l] = pyr.lv[l].Wp / 8;
         P.ax[l] = make_axis(pyr.lv[l].W);
         P.ay[l] = make_axis(pyr.lv[l].H);
         P.inv_scale[l] = 1.0f / (float)(1 << l);
@@ -89,8 +99,9 @@ inline void fill_params(LookupParams& P, const Pyramid& pyr, int radius) {
 inline int check_lookup_common(const Pyramid& pyr, int radius, int coord_mode) {
     FC_REQUIRE((long long)pyr.B * pyr.N < (1LL << 31) - QT, "B*H*W = %lld queries exceed 2^31", (long long)pyr.B * pyr.N);
     FC_REQUIRE(radius >= 1 && radius <= FC_MAX_RADIUS, "radius %d unsupported (1..%d)", radius, FC_MAX_RADIUS);
-    FC_REQUIRE(coord_mode == FC_COORD_CUDA || coord_mode == FC_COORD_CPU, "bad coord_mode %d", coord_mode);
-    for (int l = 0; l < pyr.L; ++l)
+    FC_REQUIRE(coord_mode == FC_COORD_CUDA || coord_mode == FC_COORD_CPU || coord_mode == FC_COORD_RAW, "bad coord_mode %d", coord_mode);
+    // FC_COORD_RAW (AlternateCorrBlock's indexing) never divides by (size - 1): unit dimensions are fine there
+    for (int l = 0; l < pyr.L && coord_mode != FC_COORD_RAW; ++l)
         FC_REQUIRE(pyr.lv[l].H >= 2 && pyr.lv[l].W >= 2,
                    "pyramid level %d is %dx%d: a unit dimension makes the reference divide by zero "
                    "(utils.py:61-62); inputs must be at least %d px on a side",

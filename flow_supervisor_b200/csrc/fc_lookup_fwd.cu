@@ -5,12 +5,13 @@
 // the level of a tile rotates with its query block so that every CTA sees all levels.
 // A query's footprint is ONE TMA tensor load: the level is described to the TMA unit as a
 // 3-D tensor [query][row pair][2*Wp floats] over the 2x8-patch layout (include/flowcorr.h),
-// and a box of {2|3 patches, 5|6 row pairs, 1 query} at signed coordinates lands the
-// (2r+2)^2 footprint (+1 guard row/column for floor flips of the normalise/un-normalise
-// round trip) in shared memory.  Everything outside the padded map is zero-filled by the
-// TMA unit itself -- that IS the reference's padding_mode='zeros'; pad rows/columns inside
-// the map hold zeros by the pyramid invariant.  Four box shapes per level keep the DRAM
-// traffic at the 64-byte patches the footprint really touches.
+// and a box of {1..3 patches, 1..6 row pairs, 1 query} lands the (2r+2)^2 footprint (+1 guard
+// row/column for floor flips of the normalise/un-normalise round trip) in shared memory.
+// The box is CLIPPED to the padded map in software (the TMA unit fetches every byte of a box,
+// also the part outside the tensor that it then zero-fills); taps outside the box get weight
+// zero and a clamped address -- that is the reference's padding_mode='zeros'; pad rows/columns
+// inside the map hold zeros by the pyramid invariant.  18 box shapes per level keep the DRAM
+// traffic at the 64-byte patches of the map the footprint really touches.
 //
 // A 6-stage mbarrier ring decouples three producer warps (tile k -> producer k % 3: coordinate
 // prefetch, footprint arithmetic, one TMA issue per lane) from three consumer groups of
@@ -18,6 +19,7 @@
 // x-offsets, so every store of the (B, K, H, W) output is a coalesced
 // 128-byte row; one horizontally interpolated column of R+1 rows serves all R outputs of an
 // x-offset.  The integer part (fc::axis_tap) is bit-exact to the reference's op sequence.
+#include <cstring>
 #include <mutex>
 
 #include "fc_lookup.cuh"
@@ -35,15 +37,17 @@ constexpr int LF_STAGES = 6;
 // a ring stage must always be filled by the same producer and drained by the same group:
 // an mbarrier parity wait may run at most one phase ahead of the barrier
 static_assert(LF_STAGES % LF_PTEAMS == 0 && LF_STAGES % LF_GROUPS == 0, "stage ownership");
-constexpr int LF_WIN_FLOATS = 6 * 3 * 16;                     // 6 row pairs x 3 patches x 16 floats
-constexpr int LF_WIN_BYTES = LF_WIN_FLOATS * 4;               // 1152
-constexpr int LF_STAGE_BYTES = QT * LF_WIN_BYTES;             // 36 864 B per stage
+// VB = 0: fp32 volume, VB = 1: bf16 volume (same element indexing, half the bytes)
+__host__ __device__ constexpr int lf_es(int vb) { return vb ? 2 : 4; }                       // element size
+// window = 6 row pairs x 3 patches x 16 elements, rounded up to the 128-byte alignment of a TMA destination
+__host__ __device__ constexpr int lf_win_bytes(int vb) { return (6 * 3 * 16 * lf_es(vb) + 127) / 128 * 128; }   // 1152 / 640
+__host__ __device__ constexpr int lf_stage_bytes(int vb) { return QT * lf_win_bytes(vb); }   // 36 864 / 20 480 B per stage
 
 struct alignas(16) QueryDesc {           // producer -> consumers, per stage and lane
     int ybase;                            // first window row    (2 * first row pair; may be negative)
     int xbase;                            // first window column (8 * first patch;    may be negative)
-    int pitch;                            // BYTES per window row pair (128 or 192)
-    int valid;                            // 0: dead or far query -> all outputs are exact zeros
+    int pitch;                            // BYTES per window row pair (16 elements * patches in the box)
+    int valid;                            // rows in the box (2 * row pairs); 0: dead, far or fully outside -> exact zeros
 };
 
 struct LfShared {
@@ -56,6 +60,16 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr));
     return v;
+}
+// one volume element from shared memory as fp32 (bf16 -> fp32 is a 16-bit shift)
+template <int VB>
+__device__ __forceinline__ float lds_vol(uint32_t addr) {
+    if (VB) {
+        uint16_t h;
+        asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(h) : "r"(addr));
+        return __uint_as_float((uint32_t)h << 16);
+    }
+    return lds_f32(addr);
 }
 
 struct LfQuery { int level, gq, b, p; bool live, near_; float cx, cy; };
@@ -85,12 +99,13 @@ __device__ __forceinline__ void lf_finish_query(const LookupParams& P, LfQuery& 
 }
 
 // Producer: one warp issues the 32 footprint loads of a tile into ring stage `stage`.
-template <int RADIUS, int CM>
+template <int RADIUS, int CM, int VB>
 __device__ __forceinline__ void lf_produce(const LookupParams& P, const LookupMaps& M, LfShared& sh,
                                            uint32_t win, const LfQuery& q, int stage, int lane, int member,
                                            bool wait_empty, uint32_t empty_parity) {
     constexpr int R = 2 * RADIUS + 1;
-    QueryDesc d{0, 0, 128, 0};
+    constexpr int ES = lf_es(VB), LF_WIN_BYTES = lf_win_bytes(VB), LF_STAGE_BYTES = lf_stage_bytes(VB);
+    QueryDesc d{0, 0, 32 * ES, 0};
     uint32_t bytes = 0;
     int sel = 0, c0 = 0, c1 = 0;
     const bool mine = (lane / (32 / LF_PSPLIT)) == member;          // this warp's share of the tile's queries
@@ -101,18 +116,21 @@ __device__ __forceinline__ void lf_produce(const LookupParams& P, const LookupMa
         axis_tap<CM>(q.cx, R - 1 - RADIUS, P.ax[level], xh, t0, t1);
         axis_tap<CM>(q.cy, -RADIUS, P.ay[level], yl, t0, t1);
         axis_tap<CM>(q.cy, R - 1 - RADIUS, P.ay[level], yh, t0, t1);
-        const int rp0 = yl >> 1, pc0 = xl >> 3;                       // arithmetic shifts: floor
-        const int n_rp = ((yh + 1) >> 1) - rp0 + 1;                   // <= 6 (taps are monotone, span <= R)
-        const int n_pc = ((xh + 1) >> 3) - pc0 + 1;                   // <= 3
-        sel = (n_rp > 5 ? 2 : 0) + (n_pc > 2 ? 1 : 0);
-        const int box_rp = n_rp > 5 ? 6 : 5, box_pc = n_pc > 2 ? 3 : 2;
-        d.ybase = 2 * rp0; d.xbase = 8 * pc0; d.pitch = 64 * box_pc; d.valid = 1;
-        bytes = (uint32_t)(box_rp * box_pc * 64);
-        c0 = 16 * pc0; c1 = rp0;
+        // clip the box to the padded map: [rp_lo, rp_hi] x [pc_lo, pc_hi] (arithmetic shifts: floor)
+        const int rp_lo = max(yl >> 1, 0), rp_hi = min((yh + 1) >> 1, P.nrp[level] - 1);
+        const int pc_lo = max(xl >> 3, 0), pc_hi = min((xh + 1) >> 3, P.npc[level] - 1);
+        const int n_rp = min(rp_hi - rp_lo + 1, 6);                   // <= 6 anyway (taps are monotone, span <= R)
+        const int n_pc = min(pc_hi - pc_lo + 1, 3);                   // <= 3 anyway
+        if (n_rp > 0 && n_pc > 0) {
+            sel = lk_shape(n_rp, n_pc);
+            d.ybase = 2 * rp_lo; d.xbase = 8 * pc_lo; d.pitch = 16 * ES * n_pc; d.valid = 2 * n_rp;
+            bytes = (uint32_t)(n_rp * n_pc * 16 * ES);
+            c0 = 16 * pc_lo; c1 = rp_lo;
+        }
     }
     // the footprint arithmetic above ran while the stage was still being drained
     if (wait_empty) mbar_wait(&sh.empty[stage], empty_parity);
-    if (P.probe & 2) bytes = 0;                                      // stage probe: no loads
+    if (FC_PROBE_VAL(P) & 2) bytes = 0;                                      // stage probe: no loads
     if (bytes)
         tma_load_3d(win + stage * LF_STAGE_BYTES + lane * LF_WIN_BYTES, &M.m[q.level][sel], smem_u32(&sh.full[stage]),
                     c0, c1, q.gq);
@@ -152,12 +170,13 @@ __device__ __forceinline__ void lf_debug_out(const LookupParams& P, const LfQuer
 }
 
 // Consumer: warp `w` of a group interpolates x-offsets [w*APW, w*APW + APW) of the tile.
-template <int RADIUS, int CM, bool DBG>
+template <int RADIUS, int CM, bool DBG, int VB>
 __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, uint32_t win, const LfQuery& q,
                                            int stage, uint32_t parity, int lane, int w) {
     constexpr int R = 2 * RADIUS + 1;
     constexpr int APW = (R + LF_GWARPS - 1) / LF_GWARPS;             // x-offsets per warp
     constexpr bool EVEN = (R % APW) == 0;                            // every warp owns APW valid x-offsets
+    constexpr int ES = lf_es(VB), LF_WIN_BYTES = lf_win_bytes(VB), LF_STAGE_BYTES = lf_stage_bytes(VB);
     const int level = q.level;
 
     // tap arithmetic overlaps the loads in flight
@@ -188,29 +207,41 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
     // when no lane needs the per-tap slow path, the ring stage is handed back as soon as the
     // sub-windows sit in registers: a stage is then busy for the loads only, not for the
     // arithmetic and the stores
-    const bool early = !__any_sync(0xffffffffu, q.live && d.valid && !regular) && !(P.probe & 1);   // FLOWCORR_PROBE=1: late release (stage probe)
+    const bool early = !__any_sync(0xffffffffu, q.live && d.valid && !regular) && !(FC_PROBE_VAL(P) & 1);   // FLOWCORR_PROBE=1: late release (stage probe)
 
     // horizontally interpolated (R + 1) x APW sub-window of a regular lane
     float h[R + 1][APW];
     if (fast) {
-        // byte addresses of window columns x0[0] .. x0[0]+APW (a patch jump every 8 columns)
+        // byte addresses of window columns x0[0] .. x0[0]+APW (a patch jump every 8 columns); a column outside the
+        // (clipped) box is outside the padded map: its address is clamped into the box and its weight set to zero
+        const int ncols = pitch / (2 * ES), nrows = d.valid;
         uint32_t col[APW + 1];
+        bool okc[APW + 1];
 #pragma unroll
         for (int i = 0; i <= APW; ++i) {
-            const int xr = min(max(x0[0] + i - d.xbase, 0), 23);
-            col[i] = wq + 4u * (uint32_t)(xr + (xr & ~7));
+            const int xr = x0[0] + i - d.xbase;
+            okc[i] = (unsigned)xr < (unsigned)ncols;
+            const int xc = min(max(xr, 0), ncols - 1);
+            col[i] = wq + (uint32_t)ES * (uint32_t)(xc + (xc & ~7));
         }
-        // footprint row n = y0[0] - ybase + r sits at (n >> 1) * pitch + (n & 1) * 32 bytes
-        const int n0 = min(max(y0[0] - d.ybase, 0), 1);
-        uint32_t rofs = 32u * n0;
-        uint32_t step = n0 ? (uint32_t)pitch - 32u : 32u;             // n even -> +32, n odd -> +pitch-32
+#pragma unroll
+        for (int aa = 0; aa < APW; ++aa) {
+            wx0[aa] = okc[aa] ? wx0[aa] : 0.f;
+            wx1[aa] = okc[aa + 1] ? wx1[aa] : 0.f;
+        }
+        // footprint row n sits at (m >> 1) * pitch + (m & 1) * 32 bytes, m = y0[0] - ybase + n clamped into the box
         float v[R + 1][APW + 1];
+        const int m0 = y0[0] - d.ybase;
 #pragma unroll
         for (int n = 0; n <= R; ++n) {
+            const int m = m0 + n;
+            const bool okr = (unsigned)m < (unsigned)nrows;
+            const int mc = min(max(m, 0), nrows - 1);
+            const uint32_t rofs = (uint32_t)((mc >> 1) * pitch + (mc & 1) * (8 * ES));
 #pragma unroll
-            for (int i = 0; i <= APW; ++i) v[n][i] = lds_f32(col[i] + rofs);
-            rofs += step;
-            step = (uint32_t)pitch - step;
+            for (int i = 0; i <= APW; ++i) v[n][i] = lds_vol<VB>(col[i] + rofs);
+            if (n < R) wy0[n] = okr ? wy0[n] : 0.f;
+            if (n > 0) wy1[n - 1] = okr ? wy1[n - 1] : 0.f;
         }
 #pragma unroll
         for (int n = 0; n <= R; ++n)
@@ -247,20 +278,27 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
             }
         } else {
             // floor flips among the taps (lattice coordinates): every tap addressed on its own
+            const int ncols = pitch / (2 * ES), nrows = d.valid;
 #pragma unroll
             for (int aa = 0; aa < APW; ++aa) {
                 if (w * APW + aa >= R) break;
-                const int xa = min(max(x0[aa] - d.xbase, 0), 22), xb = xa + 1;
-                const uint32_t ca = wq + 4u * (uint32_t)(xa + (xa & ~7)), cb = wq + 4u * (uint32_t)(xb + (xb & ~7));
+                const int xa = x0[aa] - d.xbase, xb = xa + 1;
+                const float wa = (unsigned)xa < (unsigned)ncols ? wx0[aa] : 0.f;
+                const float wb = (unsigned)xb < (unsigned)ncols ? wx1[aa] : 0.f;
+                const int xac = min(max(xa, 0), ncols - 1), xbc = min(max(xb, 0), ncols - 1);
+                const uint32_t ca = wq + (uint32_t)ES * (uint32_t)(xac + (xac & ~7)), cb = wq + (uint32_t)ES * (uint32_t)(xbc + (xbc & ~7));
                 float* oa = outq + aa * R * N;
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
-                    const int ya = min(max(y0[j] - d.ybase, 0), 10), yb = ya + 1;
-                    const uint32_t ra = (uint32_t)((ya >> 1) * pitch + (ya & 1) * 32);
-                    const uint32_t rb = (uint32_t)((yb >> 1) * pitch + (yb & 1) * 32);
-                    const float top = fmaf(wx1[aa], lds_f32(cb + ra), wx0[aa] * lds_f32(ca + ra));
-                    const float bot = fmaf(wx1[aa], lds_f32(cb + rb), wx0[aa] * lds_f32(ca + rb));
-                    *oa = fmaf(wy1[j], bot, wy0[j] * top);
+                    const int ya = y0[j] - d.ybase, yb = ya + 1;
+                    const float wt = (unsigned)ya < (unsigned)nrows ? wy0[j] : 0.f;
+                    const float wu = (unsigned)yb < (unsigned)nrows ? wy1[j] : 0.f;
+                    const int yac = min(max(ya, 0), nrows - 1), ybc = min(max(yb, 0), nrows - 1);
+                    const uint32_t ra = (uint32_t)((yac >> 1) * pitch + (yac & 1) * (8 * ES));
+                    const uint32_t rb = (uint32_t)((ybc >> 1) * pitch + (ybc & 1) * (8 * ES));
+                    const float top = fmaf(wb, lds_vol<VB>(cb + ra), wa * lds_vol<VB>(ca + ra));
+                    const float bot = fmaf(wb, lds_vol<VB>(cb + rb), wa * lds_vol<VB>(ca + rb));
+                    *oa = fmaf(wu, bot, wt * top);
                     oa += N;
                 }
             }
@@ -273,9 +311,10 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
     }
 }
 
-template <int RADIUS, int CM, bool DBG>
+template <int RADIUS, int CM, bool DBG, int VB>
 __global__ void __launch_bounds__(LF_THREADS, 1)
 lookup_fwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, int n_tiles) {
+    constexpr int LF_STAGE_BYTES = lf_stage_bytes(VB);
     extern __shared__ __align__(1024) uint8_t lf_smem[];
     const uint32_t win = smem_u32(lf_smem);                          // [stage][query][6 x 3 x 16 floats]
     LfShared& sh = *reinterpret_cast<LfShared*>(lf_smem + LF_STAGES * LF_STAGE_BYTES);
@@ -311,9 +350,9 @@ lookup_fwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, in
         const uint32_t round = (uint32_t)(k / LF_STAGES);
         lf_finish_query(P, q);
         if (producer) {
-            lf_produce<RADIUS, CM>(P, M, sh, win, q, s, lane, sub, k >= LF_STAGES, (round & 1u) ^ 1u);
+            lf_produce<RADIUS, CM, VB>(P, M, sh, win, q, s, lane, sub, k >= LF_STAGES, (round & 1u) ^ 1u);
         } else {
-            lf_consume<RADIUS, CM, DBG>(P, sh, win, q, s, round & 1u, lane, sub);
+            lf_consume<RADIUS, CM, DBG, VB>(P, sh, win, q, s, round & 1u, lane, sub);
         }
         if (kn >= n_local) break;
         k = kn; q = qn;
@@ -324,8 +363,8 @@ lookup_fwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, in
 // Tensor maps are a pure function of (pyramid pointer, geometry): memoised so that the
 // per-iteration call does not pay 4 * L driver encodes.
 struct MapKey {
-    const void* ptr; int B, H, W, L;
-    bool operator==(const MapKey& o) const { return ptr == o.ptr && B == o.B && H == o.H && W == o.W && L == o.L; }
+    const void* ptr; int B, H, W, L, vb;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && B == o.B && H == o.H && W == o.W && L == o.L && vb == o.vb; }
 };
 static std::mutex g_map_mutex;
 static constexpr int MAP_CACHE = 16;
@@ -333,38 +372,44 @@ static MapKey g_map_keys[MAP_CACHE];
 static LookupMaps g_map_vals[MAP_CACHE];
 static int g_map_next = 0, g_map_used = 0;
 
-static int encode_level_maps(LookupMaps& M, const float* pyramid, const Pyramid& pyr) {
+static int encode_level_maps(LookupMaps& M, const void* pyramid, const Pyramid& pyr, int vb) {
+    const size_t es = (size_t)lf_es(vb);
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FC_ECUDA; }
     const long long Q = (long long)pyr.B * pyr.N;
+    memset(&M, 0, sizeof(M));
     for (int l = 0; l < pyr.L; ++l) {
         const Level& lv = pyr.lv[l];
         cuuint64_t dims[3] = {(cuuint64_t)(2 * lv.Wp), (cuuint64_t)(lv.Hp / 2), (cuuint64_t)Q};
-        cuuint64_t strides[2] = {(cuuint64_t)(2 * lv.Wp) * 4, (cuuint64_t)lv.Hp * lv.Wp * 4};
+        cuuint64_t strides[2] = {(cuuint64_t)(2 * lv.Wp) * es, (cuuint64_t)lv.Hp * lv.Wp * es};
         cuuint32_t estr[3] = {1, 1, 1};
-        for (int sel = 0; sel < 4; ++sel) {
-            cuuint32_t box[3] = {(cuuint32_t)((sel & 1) ? 48 : 32), (cuuint32_t)((sel & 2) ? 6 : 5), 1};
-            CUresult r = enc(&M.m[l][sel], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
-                             const_cast<float*>(pyramid + lv.offset), dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) {
-                set_error("cuTensorMapEncodeTiled failed (%d) for level %d (%dx%d, pitch %d)", (int)r, l, lv.H, lv.W, lv.Wp);
-                return FC_ECUDA;
+        void* base = const_cast<uint8_t*>(static_cast<const uint8_t*>(pyramid)) + (size_t)lv.offset * es;
+        // shapes a clipped footprint can take on this level: at most the whole map
+        for (int n_rp = 1; n_rp <= 6 && n_rp <= lv.Hp / 2; ++n_rp)
+            for (int n_pc = 1; n_pc <= 3 && n_pc <= lv.Wp / 8; ++n_pc) {
+                cuuint32_t box[3] = {(cuuint32_t)(16 * n_pc), (cuuint32_t)n_rp, 1};
+                CUresult r = enc(&M.m[l][lk_shape(n_rp, n_pc)],
+                                 vb ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) {
+                    set_error("cuTensorMapEncodeTiled failed (%d) for level %d (%dx%d, pitch %d), box %dx%d", (int)r, l, lv.H,
+                              lv.W, lv.Wp, n_rp, n_pc);
+                    return FC_ECUDA;
+                }
             }
-        }
     }
     return FC_OK;
 }
 
-int get_level_maps(LookupMaps& M, const float* pyramid, const Pyramid& pyr, int H, int W) {
-    const MapKey key{pyramid, pyr.B, H, W, pyr.L};
+int get_level_maps(LookupMaps& M, const void* pyramid, const Pyramid& pyr, int H, int W, int vb) {
+    const MapKey key{pyramid, pyr.B, H, W, pyr.L, vb};
     {
         std::lock_guard<std::mutex> g(g_map_mutex);
         for (int i = 0; i < g_map_used; ++i)
             if (g_map_keys[i] == key) { M = g_map_vals[i]; return FC_OK; }
     }
-    if (int e = encode_level_maps(M, pyramid, pyr)) return e;
+    if (int e = encode_level_maps(M, pyramid, pyr, vb)) return e;
     std::lock_guard<std::mutex> g(g_map_mutex);
     g_map_keys[g_map_next] = key; g_map_vals[g_map_next] = M;
     g_map_next = (g_map_next + 1) % MAP_CACHE;
@@ -372,25 +417,29 @@ int get_level_maps(LookupMaps& M, const float* pyramid, const Pyramid& pyr, int 
     return FC_OK;
 }
 
-template <int RADIUS, int CM, bool DBG>
-static int launch_fwd3(const LookupMaps& M, const LookupParams& P, int n_tiles, int n_sm, cudaStream_t s) {
-    const size_t smem = (size_t)LF_STAGES * LF_STAGE_BYTES + sizeof(LfShared);
-    FC_CUDA(cudaFuncSetAttribute(lookup_fwd_kernel<RADIUS, CM, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int RADIUS, int CM, bool DBG, int VB>
+static int launch_fwd4(const LookupMaps& M, const LookupParams& P, int n_tiles, int n_sm, cudaStream_t s) {
+    const size_t smem = (size_t)LF_STAGES * lf_stage_bytes(VB) + sizeof(LfShared);
+    FC_SMEM_ATTR_ONCE((lookup_fwd_kernel<RADIUS, CM, DBG, VB>), smem);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-    lookup_fwd_kernel<RADIUS, CM, DBG><<<grid, LF_THREADS, smem, s>>>(M, P, n_tiles);
+    lookup_fwd_kernel<RADIUS, CM, DBG, VB><<<grid, LF_THREADS, smem, s>>>(M, P, n_tiles);
     FC_LAUNCH_CHECK("lookup_fwd_kernel");
     return FC_OK;
 }
+template <int RADIUS, int CM, bool DBG>
+static int launch_fwd3(const LookupMaps& M, const LookupParams& P, int n_tiles, int n_sm, int vb, cudaStream_t s) {
+    return vb ? launch_fwd4<RADIUS, CM, DBG, 1>(M, P, n_tiles, n_sm, s) : launch_fwd4<RADIUS, CM, DBG, 0>(M, P, n_tiles, n_sm, s);
+}
 template <int RADIUS>
-static int launch_fwd2(const LookupMaps& M, const LookupParams& P, int n_tiles, int n_sm, int coord_mode, bool dbg, cudaStream_t s) {
+static int launch_fwd2(const LookupMaps& M, const LookupParams& P, int n_tiles, int n_sm, int coord_mode, bool dbg, int vb, cudaStream_t s) {
     if (coord_mode == FC_COORD_CUDA)
-        return dbg ? launch_fwd3<RADIUS, FC_COORD_CUDA, true>(M, P, n_tiles, n_sm, s)
-                   : launch_fwd3<RADIUS, FC_COORD_CUDA, false>(M, P, n_tiles, n_sm, s);
+        return dbg ? launch_fwd3<RADIUS, FC_COORD_CUDA, true>(M, P, n_tiles, n_sm, vb, s)
+                   : launch_fwd3<RADIUS, FC_COORD_CUDA, false>(M, P, n_tiles, n_sm, vb, s);
     if (coord_mode == FC_COORD_RAW)
-        return dbg ? launch_fwd3<RADIUS, FC_COORD_RAW, true>(M, P, n_tiles, n_sm, s)
-                   : launch_fwd3<RADIUS, FC_COORD_RAW, false>(M, P, n_tiles, n_sm, s);
-    return dbg ? launch_fwd3<RADIUS, FC_COORD_CPU, true>(M, P, n_tiles, n_sm, s)
-               : launch_fwd3<RADIUS, FC_COORD_CPU, false>(M, P, n_tiles, n_sm, s);
+        return dbg ? launch_fwd3<RADIUS, FC_COORD_RAW, true>(M, P, n_tiles, n_sm, vb, s)
+                   : launch_fwd3<RADIUS, FC_COORD_RAW, false>(M, P, n_tiles, n_sm, vb, s);
+    return dbg ? launch_fwd3<RADIUS, FC_COORD_CPU, true>(M, P, n_tiles, n_sm, vb, s)
+               : launch_fwd3<RADIUS, FC_COORD_CPU, false>(M, P, n_tiles, n_sm, vb, s);
 }
 
 int sm_count(int& n_sm) {
@@ -414,10 +463,11 @@ extern "C" int fc_lookup_fwd(const void* pyramid, const float* coords, float* ou
                              int vol_dtype, int coord_mode,
                              int32_t* dbg_x0, int32_t* dbg_y0, uint8_t* dbg_mask, void* stream) {
     FC_REQUIRE(pyramid && coords && out, "fc_lookup_fwd: null pointer");
-    FC_REQUIRE(vol_dtype == FC_VOL_F32, "fc_lookup_fwd: vol_dtype %d not supported yet", vol_dtype);
+    FC_REQUIRE(vol_dtype == FC_VOL_F32 || vol_dtype == FC_VOL_BF16, "fc_lookup_fwd: unknown vol_dtype %d", vol_dtype);
+    const int vb = vol_dtype == FC_VOL_BF16 ? 1 : 0;
     Pyramid pyr;
     FC_REQUIRE(make_pyramid(pyr, B, H, W, num_levels), "fc_lookup_fwd: bad geometry B=%d H=%d W=%d L=%d", B, H, W, num_levels);
-    if (int e = check_lookup_common(pyr, radius, coord_mode == FC_COORD_RAW ? FC_COORD_CUDA : coord_mode)) return e;
+    if (int e = check_lookup_common(pyr, radius, coord_mode)) return e;
     FC_REQUIRE((reinterpret_cast<uintptr_t>(pyramid) & 15u) == 0, "fc_lookup_fwd: pyramid must be 16-byte aligned");
     LookupParams P{};
     fill_params(P, pyr, radius);
@@ -425,16 +475,16 @@ extern "C" int fc_lookup_fwd(const void* pyramid, const float* coords, float* ou
     P.coords = coords; P.io = out; P.gpyr = nullptr;
     P.dbg_x0 = dbg_x0; P.dbg_y0 = dbg_y0; P.dbg_mask = dbg_mask;
     LookupMaps M;
-    if (int e = get_level_maps(M, P.pyr, pyr, H, W)) return e;
+    if (int e = get_level_maps(M, pyramid, pyr, H, W, vb)) return e;
     int n_sm = 0;
     if (int e = sm_count(n_sm)) return e;
     const int n_tiles = ((P.Q + QT - 1) / QT) * pyr.L;
     const bool dbg = dbg_x0 || dbg_y0 || dbg_mask;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (radius) {
-        case 1: return launch_fwd2<1>(M, P, n_tiles, n_sm, coord_mode, dbg, s);
-        case 2: return launch_fwd2<2>(M, P, n_tiles, n_sm, coord_mode, dbg, s);
-        case 3: return launch_fwd2<3>(M, P, n_tiles, n_sm, coord_mode, dbg, s);
-        default: return launch_fwd2<4>(M, P, n_tiles, n_sm, coord_mode, dbg, s);
+        case 1: return launch_fwd2<1>(M, P, n_tiles, n_sm, coord_mode, dbg, vb, s);
+        case 2: return launch_fwd2<2>(M, P, n_tiles, n_sm, coord_mode, dbg, vb, s);
+        case 3: return launch_fwd2<3>(M, P, n_tiles, n_sm, coord_mode, dbg, vb, s);
+        default: return launch_fwd2<4>(M, P, n_tiles, n_sm, coord_mode, dbg, vb, s);
     }
 }

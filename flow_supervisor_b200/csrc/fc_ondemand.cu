@@ -233,7 +233,7 @@ ondemand_bwd_kernel(const OdParams P) {
 
 static inline unsigned grid1d(long long total, int threads) {
     long long g = (total + threads - 1) / threads;
-    const long long cap = 148LL * 32;
+    const long long cap = (long long)sm_count_cached() * 32;
     return (unsigned)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 

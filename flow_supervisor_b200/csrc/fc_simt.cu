@@ -204,7 +204,7 @@ __global__ void fold_level_kernel(const float* __restrict__ parent, float* __res
 
 static inline unsigned grid_for(long long total, int threads) {
     long long g = (total + threads - 1) / threads;
-    const long long cap = 148LL * 32;
+    const long long cap = (long long)sm_count_cached() * 32;
     return (unsigned)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 

@@ -109,4 +109,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn tensor_map_encoder();     // fc_api.cu; nullptr if the driver entry point is missing
 
+// cuTensorMapEncodeTiled behind a process-wide memo (mutex-guarded ring of recent encodings keyed by every
+// argument): a tensor map is a pure function of (base pointer, geometry, box), and the same buffers recur from
+// step to step under a caching allocator, so steady-state calls pay a table lookup instead of a driver call.
+// interleave NONE, OOB fill NONE (zeros), element strides 1.  Returns FC_OK / FC_ECUDA (fc_last_error set).
+int encode_tiled_cached(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* base,
+                        const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                        CUtensorMapSwizzle swizzle, CUtensorMapL2promotion l2);
+
 }  // namespace fc

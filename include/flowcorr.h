@@ -15,8 +15,10 @@
  *     allocates nothing and never synchronises (CUDA-graph capturable);
  *   - return 0 on success, a negative FC_E* code otherwise; fc_last_error() gives
  *     a thread-local human readable message.  Nothing throws or aborts;
- *   - no global mutable state: safe to call concurrently from several host
- *     threads / devices (nn.DataParallel replicas, pytorch/train.py:192).
+ *   - thread safe: results depend on the arguments only.  The process-wide state is a set of
+ *     mutex-guarded memo caches (tensor-map encodings keyed by pointer + geometry, per-device
+ *     kernel attributes, the environment switches read once), so concurrent calls from several
+ *     host threads / devices are fine (nn.DataParallel replicas, pytorch/train.py:183).
  *
  * Correlation pyramid layout (internal to this library; the reference keeps a list
  * of (B*N, 1, Hl, Wl) tensors, corr.py:14-27, which nothing outside corr.py reads):
@@ -25,7 +27,10 @@
  *   like avg_pool2d), Wp_l = round_up(Wl, 8), Hp_l = round_up(Hl, 2), stored in 64-byte
  *   patches of 2 rows x 8 columns (the DRAM access granule), patches of a row pair left
  *   to right:  offset(y, x) = (y/2)*(2*Wp_l) + (x/8)*16 + (y%2)*8 + x%8.
- *   Pad columns of level 0 hold zeros; other pads are never read.
+ *   INVARIANT: every pad row (y >= Hl) and pad column (x >= Wl) of EVERY level holds exact zeros.
+ *   fc_build establishes it; the lookup kernels read whole patches / row pairs and rely on it for the
+ *   reference's padding_mode='zeros' at the right / bottom edge.  A caller filling a pyramid itself must
+ *   zero the pads.
  *   Element type: fp32 (FC_VOL_F32) or bf16 (FC_VOL_BF16).
  */
 #ifndef FLOWCORR_H_

@@ -232,3 +232,18 @@ def test_cfg3_l2l_ddp_two_gpus_equals_single_gpu_on_the_concatenated_batch(core,
         preds = model(c1, c2, f1, f2, ox, oy, iters=n_iters)
         rm.sequence_loss(preds, gt, valid).backward()
     rm.compare_grads(g_ddp, rm.grad_dict(model), rel=5e-3)
+
+
+def test_bf16_volume_mode_epe_stated_separately(core):
+    """bf16 VOLUME (CorrBlock.volume='bf16'): tolerance 0.05 px mean EPE after 12 iterations."""
+    import flow_supervisor_b200 as fsb
+    torch.manual_seed(1234)
+    model = core.raft.RAFT(rm.raft_args()).eval().cuda()
+    im1, im2 = (t.cuda() for t in rm.synth_pair(440, 1024, seed=3))
+    fsb.CorrBlock.volume = "bf16"
+    try:
+        with rm.strict_fp32():
+            (_, up_r), (_, up_o) = _run_both(model, im1, im2, iters=12, test_mode=True)
+    finally:
+        fsb.CorrBlock.volume = "f32"
+    assert rm.epe(up_o, up_r) <= 0.05, rm.epe(up_o, up_r)
