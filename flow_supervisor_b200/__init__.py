@@ -8,5 +8,6 @@ All arithmetic runs in hand-written CUDA kernels behind the C ABI of
 from . import ops  # noqa: F401
 from .corr import AlternateCorrBlock, CorrBlock, coords_grid  # noqa: F401
 from .patch import patch_reference, unpatch_reference  # noqa: F401
+from .runner import RaftRunner  # noqa: F401
 
-__all__ = ["CorrBlock", "AlternateCorrBlock", "coords_grid", "patch_reference", "unpatch_reference"]
+__all__ = ["CorrBlock", "AlternateCorrBlock", "coords_grid", "patch_reference", "unpatch_reference", "RaftRunner"]

@@ -40,6 +40,7 @@ SIGNATURES = {
     "fc_ondemand_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "fc_altcorr_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "fc_altcorr_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "fc_upsample_flow": (_i, [_p, _p, _p, _i, _i, _i, _p]),
 }
 
 _lock = threading.Lock()

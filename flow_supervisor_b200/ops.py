@@ -261,3 +261,25 @@ def altcorr_bwd(fmap1: Tensor, fmap2: Tensor, coords: Tensor, corr_grad: Tensor,
 @altcorr_bwd.register_fake
 def _(fmap1, fmap2, coords, corr_grad, radius):
     return torch.empty_like(fmap1), torch.empty_like(fmap2)
+
+
+# ----------------------------------------------------------------------------- adjacent components (section 8 f)
+@custom_op("flowcorr::upsample_flow", mutates_args=())
+def upsample_flow(flow: Tensor, mask: Tensor) -> Tensor:
+    """RAFT.upsample_flow (raft.py:72-83): (B,2,H,W) flow + (B,576,H,W) mask -> (B,2,8H,8W).  Forward only."""
+    _need_cuda(flow, mask)
+    f, m = _f32c(flow), _f32c(mask)
+    B, _, H, W = f.shape
+    if tuple(m.shape) != (B, 576, H, W):
+        raise ValueError(f"mask must be ({B}, 576, {H}, {W}); got {tuple(m.shape)}")
+    with torch.cuda.device(f.device):
+        out = torch.empty(B, 2, 8 * H, 8 * W, dtype=torch.float32, device=f.device)
+        _lib.check(_lib.load().fc_upsample_flow(f.data_ptr(), m.data_ptr(), out.data_ptr(), B, H, W, _stream()),
+                   "fc_upsample_flow")
+    return out
+
+
+@upsample_flow.register_fake
+def _(flow, mask):
+    B, _, H, W = flow.shape
+    return flow.new_empty(B, 2, 8 * H, 8 * W, dtype=torch.float32)

@@ -1,0 +1,113 @@
+"""Opt-in inference driver around an UNMODIFIED reference model.
+
+``RaftRunner(model)`` runs the arithmetic of ``model.forward(image1, image2, iters, test_mode=True)``
+(/root/reference/pytorch/core/raft.py:86-144; gma_network.py:74-129) with the model's own
+sub-modules (``fnet``, ``cnet``, ``update_block``, ``att``) and weights, restructured for the GPU:
+
+* the correlation block is this package's ``CorrBlock`` (build + one lookup launch per iteration);
+* the whole forward -- encoders, volume build, every GRU iteration (lookup, update block,
+  ``coords1 += delta``, raft.py:122-132) and the final upsampling -- is captured ONCE per input shape
+  in a CUDA graph and replayed: the reference issues ~60 small kernels and 4 host-to-device copies per
+  iteration from Python (corr.py:29-50), here an iteration is a fixed chain of launches with no host
+  work in between (row f2);
+* in test mode only the LAST iteration's upsampled flow is returned (raft.py:141-142), so the convex
+  upsampling (raft.py:72-83, a 576-channel softmax per iteration in the reference) runs once, through
+  ``fc_upsample_flow`` (row f4; ``fused_upsample=False`` keeps the model's own method).
+
+Graph on / off is bit-identical (same kernels, same order); against the reference forward the result
+is within the flow tolerance of the drop-in block (tests/test_gpu_runner.py).  Inference only: the
+reference's training path keeps running unchanged through ``patch_reference()``.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .corr import CorrBlock, coords_grid
+
+
+class RaftRunner:
+    def __init__(self, model, iters: int = 12, graph: bool = True, fused_upsample: bool = True,
+                 corr_block=CorrBlock):
+        self.model = model
+        self.iters = int(iters)
+        self.use_graph = bool(graph)
+        self.fused_upsample = bool(fused_upsample)
+        self.corr_block = corr_block
+        self._graphs = {}            # (shape, dtype, device, flow_init?) -> (graph, static inputs, static outputs)
+
+    # ------------------------------------------------------------------ the forward itself
+    def _autocast(self):
+        return torch.autocast("cuda", enabled=bool(getattr(self.model.args, "mixed_precision", False)))
+
+    def forward_eager(self, image1, image2, flow_init=None):
+        m = self.model
+        hdim, cdim = m.hidden_dim, m.context_dim
+        image1 = (2 * (image1 / 255.0) - 1.0).contiguous()                   # raft.py:89-93
+        image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
+        with self._autocast():
+            fmap1, fmap2 = m.fnet([image1, image2])                          # raft.py:99-100
+        corr_fn = self.corr_block(fmap1.float(), fmap2.float(), radius=m.args.corr_radius)
+        with self._autocast():
+            cnet = m.cnet(image1)                                            # raft.py:110-114
+            net, inp = torch.split(cnet, [hdim, cdim], dim=1)
+            net, inp = torch.tanh(net), torch.relu(inp)
+            attention = m.att(inp) if hasattr(m, "att") else None            # gma_network.py:100
+        B, _, H, W = image1.shape
+        coords0 = coords_grid(B, H // 8, W // 8, device=image1.device)
+        coords1 = coords0.clone()
+        if flow_init is not None:
+            coords1 = coords1 + flow_init
+        up_mask = None
+        for _ in range(self.iters):                                          # raft.py:122-132
+            corr = corr_fn(coords1)
+            flow = coords1 - coords0
+            with self._autocast():
+                if attention is None:
+                    net, up_mask, delta = m.update_block(net, inp, corr, flow)
+                else:
+                    net, up_mask, delta = m.update_block(net, inp, corr, flow, attention)
+            coords1 = coords1 + delta
+        flow_low = coords1 - coords0
+        if up_mask is None:                                                  # small model: bilinear x8 (utils.py:80-82)
+            flow_up = 8 * torch.nn.functional.interpolate(flow_low, scale_factor=8, mode="bilinear", align_corners=True)
+        elif self.fused_upsample:
+            flow_up = ops.upsample_flow(flow_low.float(), up_mask.float())
+        else:
+            flow_up = m.upsample_flow(flow_low, up_mask)
+        return flow_low, flow_up
+
+    # ------------------------------------------------------------------ graph capture / replay
+    def _capture(self, image1, image2, flow_init):
+        s_im1, s_im2 = torch.empty_like(image1), torch.empty_like(image2)
+        s_init = torch.empty_like(flow_init) if flow_init is not None else None
+        s_im1.copy_(image1); s_im2.copy_(image2)
+        if s_init is not None:
+            s_init.copy_(flow_init)
+        side = torch.cuda.Stream(device=image1.device)
+        side.wait_stream(torch.cuda.current_stream(image1.device))
+        with torch.cuda.stream(side):                                        # warm-up: lazy inits, cuDNN plans, caches
+            for _ in range(2):
+                self.forward_eager(s_im1, s_im2, s_init)
+        torch.cuda.current_stream(image1.device).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self.forward_eager(s_im1, s_im2, s_init)
+        return g, (s_im1, s_im2, s_init), out
+
+    @torch.no_grad()
+    def __call__(self, image1, image2, flow_init=None):
+        if not image1.is_cuda:
+            raise RuntimeError("RaftRunner needs CUDA images: this package has no CPU fallback")
+        if not self.use_graph:
+            return self.forward_eager(image1, image2, flow_init)
+        key = (tuple(image1.shape), image1.dtype, image1.device, flow_init is not None, self.iters,
+               self.fused_upsample)
+        if key not in self._graphs:
+            self._graphs[key] = self._capture(image1, image2, flow_init)
+        g, (s_im1, s_im2, s_init), (flow_low, flow_up) = self._graphs[key]
+        s_im1.copy_(image1); s_im2.copy_(image2)
+        if s_init is not None:
+            s_init.copy_(flow_init)
+        g.replay()
+        return flow_low.clone(), flow_up.clone()

@@ -162,6 +162,13 @@ int fc_altcorr_bwd(const float* fmap1, const float* fmap2, const float* coords,
                    const float* corr_grad, float* fmap1_grad, float* fmap2_grad,
                    int B, int H1, int W1, int H2, int W2, int C, int radius, void* stream);
 
+/* ---- adjacent components: opt-in, the reference scripts run without them ---- */
+
+/* RAFT.upsample_flow (pytorch/core/raft.py:72-83; gma_network.py:60-72): convex 8x upsampling,
+ *   out[b,c,8h+i,8w+j] = sum_k softmax_k(mask[b, k*64+i*8+j, h, w]) * 8 * flow[b,c,h+k/3-1,w+k%3-1]  (zero padded)
+ * flow (B,2,H,W), mask (B,576,H,W), out (B,2,8H,8W), all fp32 contiguous.  One pass over the mask. */
+int fc_upsample_flow(const float* flow, const float* mask, float* out, int B, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,98 @@
+"""GPU: the opt-in pieces next to the correlation path:
+``fc_upsample_flow`` against RAFT.upsample_flow's torch ops, and ``RaftRunner`` (whole forward in one
+CUDA graph) against its own eager path (bit-identical) and against the unmodified reference forward."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import refmodels as rm  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_upsample(flow, mask):
+    """raft.py:72-83, verbatim arithmetic."""
+    N, _, H, W = flow.shape
+    mask = mask.view(N, 1, 9, 8, 8, H, W)
+    mask = torch.softmax(mask, dim=2)
+    up = F.unfold(8 * flow, [3, 3], padding=1).view(N, 2, 9, 1, 1, H, W)
+    up = torch.sum(mask * up, dim=2).permute(0, 1, 4, 2, 5, 3)
+    return up.reshape(N, 2, 8 * H, 8 * W)
+
+
+@pytest.mark.parametrize("shape", [(1, 46, 62), (2, 55, 128), (1, 7, 5), (3, 16, 33), (1, 1, 1)])
+def test_upsample_flow_matches_reference_ops(shape):
+    import flow_supervisor_b200 as fsb
+    B, H, W = shape
+    g = torch.Generator().manual_seed(3)
+    flow = (4.0 * torch.randn(B, 2, H, W, generator=g)).cuda()
+    mask = (3.0 * torch.randn(B, 576, H, W, generator=g)).cuda()
+    out = fsb.ops.upsample_flow(flow, mask)
+    ref = ref_upsample(flow, mask)
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+    # a peaked mask selects one neighbour exactly; the border reads zeros (unfold padding)
+    mask2 = torch.full_like(mask, -1e4)
+    mask2[:, 0 * 64:1 * 64] = 0.0                                          # k = 0: neighbour (h-1, w-1)
+    out2 = fsb.ops.upsample_flow(flow, mask2)
+    assert torch.equal(out2, ref_upsample(flow, mask2))
+    assert not out2[:, :, :8].any() and not out2[:, :, :, :8].any()
+
+
+def test_upsample_flow_rejects_bad_input():
+    import flow_supervisor_b200 as fsb
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fsb.ops.upsample_flow(torch.zeros(1, 2, 4, 4), torch.zeros(1, 576, 4, 4))
+    with pytest.raises(ValueError):
+        fsb.ops.upsample_flow(torch.zeros(1, 2, 4, 4).cuda(), torch.zeros(1, 64, 4, 4).cuda())
+
+
+@pytest.fixture(scope="module")
+def core():
+    return rm.core()
+
+
+@pytest.mark.parametrize("kind,size", [("raft", (368, 496)), ("raft", (440, 1024)), ("gma", (376, 1248))])
+def test_runner_graph_is_bit_identical_and_matches_the_reference_forward(core, kind, size):
+    import flow_supervisor_b200 as fsb
+    torch.manual_seed(1234)
+    model = (core.raft.RAFT(rm.raft_args()) if kind == "raft" else core.gma_network.RAFTGMA(rm.gma_args())).eval().cuda()
+    im1, im2 = (t.cuda() for t in rm.synth_pair(size[0], size[1], seed=9, batch=2))
+    with rm.strict_fp32(), torch.no_grad():
+        low_r, up_r = model(im1, im2, iters=12, test_mode=True)              # reference block, reference forward
+        with rm.patched():
+            low_p, up_p = model(im1, im2, iters=12, test_mode=True)          # drop-in block, reference forward
+        eager = fsb.RaftRunner(model, iters=12, graph=False, fused_upsample=False)
+        low_e, up_e = eager(im1, im2)
+        graphed = fsb.RaftRunner(model, iters=12, graph=True, fused_upsample=False)
+        low_g, up_g = graphed(im1, im2)
+        low_g2, up_g2 = graphed(im1.flip(0), im2.flip(0))                     # replay with new inputs
+        fused = fsb.RaftRunner(model, iters=12, graph=True, fused_upsample=True)
+        low_f, up_f = fused(im1, im2)
+    # same launches in the same order: the runner reproduces the patched reference forward exactly
+    assert torch.equal(low_e, low_p) and torch.equal(up_e, up_p)
+    # graph on / off: bit-identical flow
+    assert torch.equal(low_g, low_e) and torch.equal(up_g, up_e)
+    assert torch.equal(low_g2, low_e.flip(0)) and torch.equal(up_g2, up_e.flip(0))
+    # fused upsampling: same low-resolution flow, upsampled flow to rounding
+    assert torch.equal(low_f, low_e)
+    assert float((up_f - up_e).abs().max()) <= 1e-4
+    # and the whole thing against the reference's own block
+    assert rm.epe(up_f, up_r) <= 0.01, rm.epe(up_f, up_r)
+
+
+def test_runner_flow_init_and_mixed_precision(core):
+    import flow_supervisor_b200 as fsb
+    torch.manual_seed(1234)
+    model = core.raft.RAFT(rm.raft_args(mixed_precision=True)).eval().cuda()
+    im1, im2 = (t.cuda() for t in rm.synth_pair(368, 496, seed=10))
+    init = torch.randn(1, 2, 46, 62, device="cuda")
+    with torch.no_grad():
+        with rm.patched():
+            low_p, up_p = model(im1, im2, iters=6, flow_init=init, test_mode=True)
+        low_g, up_g = fsb.RaftRunner(model, iters=6, graph=True, fused_upsample=False)(im1, im2, flow_init=init)
+    assert torch.equal(low_g, low_p) and torch.equal(up_g, up_p)
