@@ -263,6 +263,54 @@ def run_reference(args, H, W):
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def model_e2e(args, B, iters, barrier):
+    """-> (dict for the JSON line or None, ms per step on this rank)."""
+    import flow_supervisor_b200 as fsb
+    try:
+        from baseline import install_ref
+        p = install_ref.install()
+        if p is None:
+            return {"unavailable": "baseline/_ref not installed"}, 0.0
+        if p not in sys.path:
+            sys.path.insert(0, p)
+        from core.raft import RAFT
+        torch.manual_seed(1234)
+        model = RAFT(argparse.Namespace(small=False, mixed_precision=False, alternate_corr=False)).eval().cuda()
+        Hp, Wp = (args.height + 7) // 8 * 8, (args.width + 7) // 8 * 8
+        gen = torch.Generator().manual_seed(7)
+        im1_h = (torch.rand(B, 3, Hp, Wp, generator=gen) * 255.0).pin_memory()
+        im2_h = (torch.rand(B, 3, Hp, Wp, generator=gen) * 255.0).pin_memory()
+        flow_h = torch.empty(B, 2, Hp, Wp).pin_memory()
+        runner = fsb.RaftRunner(model, iters=iters, graph=True)
+
+        def step():
+            a = im1_h.cuda(non_blocking=True)
+            b = im2_h.cuda(non_blocking=True)
+            _, up = runner(a, b)
+            flow_h.copy_(up, non_blocking=True)
+
+        for _ in range(3):
+            step()
+        barrier()
+        n = max(3, min(args.steps, 5))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / n
+        info = {"unit": "pairs/s", "what": "images (pinned host) -> RaftRunner(reference RAFT, drop-in block, one CUDA graph) "
+                                           f"-> flow (pinned host), {iters} iterations, {args.height}x{args.width}, batch {B}/GPU, "
+                                           "torch default conv math",
+                "h2d_bytes_per_step": 2 * im1_h.numel() * 4, "d2h_bytes_per_step": flow_h.numel() * 4}
+        del runner, model
+        torch.cuda.empty_cache()
+        return info, ms
+    except Exception as e:                              # noqa: BLE001
+        return {"unavailable": repr(e)}, 0.0
+
+
 def main():
     args = parse()
     H, W = token_grid(args.height, args.width)
@@ -388,13 +436,21 @@ def main():
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / n_e2e
+    if sampler: sampler.pause()
+
+    # ---- model-level end to end (the metric BASELINE.json names): images in pinned host memory -> RaftRunner over
+    # the unmodified reference RAFT (baseline/_ref, random init) with the drop-in block, whole forward in one CUDA
+    # graph -> full-resolution flow back in pinned host memory.  H2D and D2H inside the timed region, every step.
+    e2e_model, model_ms = model_e2e(args, B, iters, barrier)
     clocks = sampler.stop() if sampler else None
 
     # ---- max over ranks
-    t = torch.tensor([elapsed_ms, e2e_ms, build_ms, look_ms], device="cuda", dtype=torch.float64)
+    t = torch.tensor([elapsed_ms, e2e_ms, build_ms, look_ms, model_ms], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms, build_ms, look_ms = t.tolist()
+    elapsed_ms, e2e_ms, build_ms, look_ms, model_ms = t.tolist()
+    if e2e_model is not None and model_ms > 0:
+        e2e_model.update({"value": world * B / (model_ms * 1e-3), "ms_per_step": model_ms})
 
     if rank == 0:
         hbm, tf_burst, tf_sust, peak_src = peaks()
@@ -447,6 +503,7 @@ def main():
             "roofline": dominant, "roofline_other": other,
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e_model": e2e_model,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -457,7 +514,9 @@ def main():
             try:
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import bench_rows
-                line["rows"] = bench_rows.collect(reps=5, ref_kernel=False)   # no oracle/ here
+                # (the compiled reference kernel of oracle/_ref is timed as a comparison column of the on-demand
+                # rows, after and outside every timed region of the product path)
+                line["rows"] = bench_rows.collect(reps=5, ref_kernel=True)
             except Exception as e:                      # noqa: BLE001
                 line["rows"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:

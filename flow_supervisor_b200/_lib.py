@@ -26,6 +26,7 @@ _p, _i, _z = C.c_void_p, C.c_int, C.c_size_t
 SIGNATURES = {
     "fc_abi_version": (_i, []),
     "fc_last_error": (C.c_char_p, []),
+    "fc_tunable_set": (_i, [C.c_char_p, _i]),
     "fc_kernel_launches": (C.c_ulonglong, []),
     "fc_level_dims": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "fc_pyramid_bytes": (_z, [_i, _i, _i, _i, _i, C.POINTER(_z)]),

@@ -60,8 +60,8 @@ EncodeTiledFn tensor_map_encoder() {
     return fn;
 }
 
-const Tunables& tunables() {
-    static const Tunables t = []() {
+static Tunables& tunables_mut() {
+    static Tunables t = []() {
         Tunables v{};
         auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
 #ifdef FC_PROBES
@@ -71,11 +71,13 @@ const Tunables& tunables() {
         v.build_stages = geti("FLOWCORR_BUILD_STAGES", 0);
         v.build_epi_warps = geti("FLOWCORR_BUILD_EPI_WARPS", 4) == 8 ? 8 : 4;
         v.no_fuse = getenv("FLOWCORR_NO_FUSE") != nullptr;
+        v.l2_fetch = geti("FLOWCORR_L2_FETCH", 0);
         v.verbose = geti("FLOWCORR_VERBOSE", 1);
         return v;
     }();
     return t;
 }
+const Tunables& tunables() { return tunables_mut(); }
 
 int sm_count_cached() {
     static thread_local int cached_dev = -1, cached_sm = 148;
@@ -159,6 +161,23 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 using namespace fc;
 
 extern "C" int fc_abi_version(void) { return FC_ABI_VERSION; }
+
+extern "C" int fc_tunable_set(const char* name, int value) {
+    FC_REQUIRE(name != nullptr, "fc_tunable_set: null name");
+    Tunables& t = tunables_mut();
+    const std::string n(name);
+    if (n == "build_sched") t.build_sched = value;
+    else if (n == "build_stages") t.build_stages = value;
+    else if (n == "build_epi_warps") t.build_epi_warps = value == 8 ? 8 : 4;
+    else if (n == "no_fuse") t.no_fuse = value != 0;
+    else if (n == "verbose") t.verbose = value;
+    else if (n == "l2_fetch") t.l2_fetch = value;
+#ifdef FC_PROBES
+    else if (n == "probe") t.probe = value;
+#endif
+    else { set_error("fc_tunable_set: unknown switch '%s'", name); return FC_EINVAL; }
+    return FC_OK;
+}
 
 extern "C" const char* fc_last_error(void) { return g_err; }
 

@@ -467,7 +467,7 @@ int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float
         const dim3 grid((unsigned)((long long)B * N));
 #define FC_FOLD_CASE(LV)                                                                                              \
     case LV:                                                                                                          \
-        FC_SMEM_ATTR_ONCE((bwd_fold_pack_kernel<LV>), 227 * 1024);   /* the opt-in maximum: smem varies with the geometry */ \
+        FC_SMEM_ATTR_GROW((bwd_fold_pack_kernel<LV>), smem);   /* smem varies with the geometry */ \
         bwd_fold_pack_kernel<LV><<<grid, 256, smem, s>>>(F);                                                         \
         break;
         switch (pyr.L) {

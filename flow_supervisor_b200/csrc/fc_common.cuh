@@ -27,13 +27,13 @@ void count_launch();          // fc_kernel_launches() instrumentation
 #define FC_CUDA(call)                                         \
     do {                                                      \
         cudaError_t e__ = (call);                             \
-        if (e__ != cudaSuccess) return fc::cuda_fail(e__, #call); \
+        if (e__ != cudaSuccess) { (void)cudaGetLastError(); return fc::cuda_fail(e__, #call); } \
     } while (0)
 
 #define FC_LAUNCH_CHECK(name)                                 \
     do {                                                      \
         fc::count_launch();                                   \
-        cudaError_t e__ = cudaPeekAtLastError();              \
+        cudaError_t e__ = cudaGetLastError();   /* clears a non-sticky error: a later call must not inherit it */ \
         if (e__ != cudaSuccess) return fc::cuda_fail(e__, name); \
     } while (0)
 
@@ -52,6 +52,7 @@ struct Tunables {
     int build_stages;        // FLOWCORR_BUILD_STAGES     operand ring depth, 0 = kernel default
     int build_epi_warps;     // FLOWCORR_BUILD_EPI_WARPS  4 | 8 (default 4)
     int no_fuse;             // FLOWCORR_NO_FUSE          pyramid by separate pooling launches
+    int l2_fetch;            // FLOWCORR_L2_FETCH         32 | 64 | 128: cudaLimitMaxL2FetchGranularity set at the first lookup (0 = leave)
     int verbose;             // FLOWCORR_VERBOSE          log mode fall-backs (shape not taken by a tensor-core kernel) to stderr
 };
 const Tunables& tunables();
@@ -70,6 +71,18 @@ void note_once(const char* key, const char* fmt, ...);
         if (!(done__.load(std::memory_order_acquire) & bit__)) {                                           \
             FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
             done__.fetch_or(bit__, std::memory_order_release);                                             \
+        }                                                                                                  \
+    } while (0)
+
+// the same for a kernel whose dynamic shared memory varies with the geometry: the attribute only ever grows
+#define FC_SMEM_ATTR_GROW(kernel, bytes)                                                                   \
+    do {                                                                                                   \
+        static std::atomic<int> cur__[64];                                                                 \
+        int dev__ = 0;                                                                                     \
+        FC_CUDA(cudaGetDevice(&dev__));                                                                    \
+        if ((int)(bytes) > cur__[dev__ & 63].load(std::memory_order_acquire)) {                            \
+            FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            cur__[dev__ & 63].store((int)(bytes), std::memory_order_release);                              \
         }                                                                                                  \
     } while (0)
 

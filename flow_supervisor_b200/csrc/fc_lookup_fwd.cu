@@ -33,7 +33,10 @@ constexpr int LF_PRODUCERS = LF_PTEAMS * LF_PSPLIT;           // warps issuing T
 constexpr int LF_GROUPS = 3;                                  // consumer groups (tile k -> group k % 3)
 constexpr int LF_GWARPS = 3;                                  // warps per group (x-offset thirds)
 constexpr int LF_THREADS = 32 * (LF_PRODUCERS + LF_GROUPS * LF_GWARPS);   // 352
-constexpr int LF_STAGES = 6;
+#ifndef FC_LF_STAGES
+#define FC_LF_STAGES 6
+#endif
+constexpr int LF_STAGES = FC_LF_STAGES;
 // a ring stage must always be filled by the same producer and drained by the same group:
 // an mbarrier parity wait may run at most one phase ahead of the barrier
 static_assert(LF_STAGES % LF_PTEAMS == 0 && LF_STAGES % LF_GROUPS == 0, "stage ownership");
@@ -420,8 +423,8 @@ int get_level_maps(LookupMaps& M, const void* pyramid, const Pyramid& pyr, int H
 template <int RADIUS, int CM, bool DBG, int VB>
 static int launch_fwd4(const LookupMaps& M, const LookupParams& P, int n_tiles, int n_sm, cudaStream_t s) {
     const size_t smem = (size_t)LF_STAGES * lf_stage_bytes(VB) + sizeof(LfShared);
-    FC_SMEM_ATTR_ONCE((lookup_fwd_kernel<RADIUS, CM, DBG, VB>), smem);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    FC_SMEM_ATTR_ONCE((lookup_fwd_kernel<RADIUS, CM, DBG, VB>), smem);
     lookup_fwd_kernel<RADIUS, CM, DBG, VB><<<grid, LF_THREADS, smem, s>>>(M, P, n_tiles);
     FC_LAUNCH_CHECK("lookup_fwd_kernel");
     return FC_OK;
@@ -474,6 +477,18 @@ extern "C" int fc_lookup_fwd(const void* pyramid, const float* coords, float* ou
     P.pyr = static_cast<const float*>(pyramid);
     P.coords = coords; P.io = out; P.gpyr = nullptr;
     P.dbg_x0 = dbg_x0; P.dbg_y0 = dbg_y0; P.dbg_mask = dbg_mask;
+    if (tunables().l2_fetch) {                               // experiment switch (profiles/r02): DRAM fetch granularity of L2 misses
+        static std::atomic<int> applied{0};
+        if (!applied.exchange(1)) {
+            size_t before = 0;
+            cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+            cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)tunables().l2_fetch);
+            size_t after = 0;
+            cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+            note_once("l2_fetch", "cudaLimitMaxL2FetchGranularity %zu -> %zu (%s)", before, after, cudaGetErrorName(e));
+            (void)cudaGetLastError();
+        }
+    }
     LookupMaps M;
     if (int e = get_level_maps(M, pyramid, pyr, H, W, vb)) return e;
     int n_sm = 0;

@@ -74,6 +74,12 @@ extern "C" {
 int fc_abi_version(void);
 const char* fc_last_error(void);
 
+/* Diagnostic switches.  They are read from the environment ONCE per process (FLOWCORR_BUILD_SCHED,
+ * FLOWCORR_BUILD_STAGES, FLOWCORR_BUILD_EPI_WARPS, FLOWCORR_NO_FUSE, FLOWCORR_VERBOSE, FLOWCORR_L2_FETCH); this call
+ * overrides one at run time (names: build_sched, build_stages, build_epi_warps, no_fuse, verbose, l2_fetch).
+ * None changes results -- only which kernel variant computes them (tests/test_gpu_tensorcore.py). */
+int fc_tunable_set(const char* name, int value);
+
 /* Number of CUDA kernels this library has launched in the calling process so far
  * (monotonic; instrumentation for benchmarks: bench.py's gpu_launches). */
 unsigned long long fc_kernel_launches(void);

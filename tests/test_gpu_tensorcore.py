@@ -131,6 +131,34 @@ def test_tc_backward_matches_fp32_mode(fsb, shape, L, r, math, tol):
     assert e1 < tol and e2 < tol, (e1, e2)
 
 
+@pytest.mark.parametrize("shape", [(1, 256, 46, 96), (1, 256, 54, 128), (2, 128, 23, 50)])
+def test_tc_backward_matches_torch_autograd_of_the_reference_ops(fsb, shape):
+    """The tcgen05 backward (lookup_bwd + fold + two GEMMs, 3xbf16) against torch autograd through the reference's
+    own library calls (matmul / avg_pool2d / grid_sample, oracle/corr_torch.py) on the same GPU, at the configuration-3
+    geometries (46x96 student crop, 54x128 teacher frame, D = 256), three accumulated lookups (an independent
+    implementation, not this library's fp32 mode).  Tolerance 1e-4 of the gradient's max magnitude."""
+    from oracle import corr_torch
+    B, D, H, W = shape
+    gen = torch.Generator().manual_seed(71)
+    f1 = (1.57 * torch.randn(B, D, H, W, generator=gen)).cuda()
+    f2 = (1.57 * torch.randn(B, D, H, W, generator=gen)).cuda()
+    cs = [(fsb.coords_grid(B, H, W) + 3.0 * torch.randn(B, 2, H, W, generator=gen)).cuda() for _ in range(3)]
+    gs = [torch.randn(B, 324, H, W, generator=gen).cuda() for _ in range(3)]
+    d1, d2 = _grads(fsb, "3xbf16", f1, f2, cs, gs)
+    a, b = f1.clone().requires_grad_(), f2.clone().requires_grad_()
+    keep = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        blk = corr_torch.TorchCorrBlock(a, b, 4, 4)
+        loss = sum((blk(c) * g).sum() for c, g in zip(cs, gs))
+        loss.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = keep
+    e1 = float((d1 - a.grad).abs().max() / a.grad.abs().max())
+    e2 = float((d2 - b.grad).abs().max() / b.grad.abs().max())
+    assert e1 < 1e-4 and e2 < 1e-4, (e1, e2)
+
+
 def test_tc_backward_matches_oracle(fsb):
     """... and against the numpy oracle's adjoint (oracle/corr_spec.py), fp64-free path."""
     B, D, H, W = 1, 64, 18, 26
@@ -146,23 +174,32 @@ def test_tc_backward_matches_oracle(fsb):
     assert float(np.abs(d2.cpu().numpy() - w2).max() / np.abs(w2).max()) < 1e-4
 
 
-@pytest.mark.parametrize("env", [{"FLOWCORR_BUILD_EPI_WARPS": "8"}, {"FLOWCORR_BUILD_SCHED": "0"},
-                                 {"FLOWCORR_BUILD_STAGES": "2"}, {"FLOWCORR_BUILD_EPI_WARPS": "8", "FLOWCORR_BUILD_SCHED": "0"}])
+DEFAULTS = {"build_epi_warps": 4, "build_sched": 1, "build_stages": 0, "no_fuse": 0}
+
+
+@pytest.mark.parametrize("env", [{"build_epi_warps": 8}, {"build_sched": 0}, {"build_stages": 2},
+                                 {"build_epi_warps": 8, "build_sched": 0}, {"no_fuse": 1}])
 @pytest.mark.parametrize("shape", [(2, 256, 55, 128), (1, 128, 21, 156), (3, 64, 17, 23)])
-def test_tc_build_variants_are_bit_identical(fsb, monkeypatch, env, shape):
-    """The alternative epilogue width, unit schedule and ring depth (diagnostic switches of fc_build_tc.cu) change
-    who computes a tile and when, never the arithmetic: the pyramid must come out bit for bit the same."""
-    import os
+def test_tc_build_variants_are_bit_identical(fsb, env, shape):
+    """The alternative epilogue width, unit schedule, ring depth and the unfused pooling launches (diagnostic switches,
+    fc_tunable_set) change who computes a tile and when, never the arithmetic: the pyramid must come out bit for bit
+    the same."""
+    from flow_supervisor_b200 import _lib
+    lib = _lib.load()
     B, D, H, W = shape
     gen = torch.Generator().manual_seed(7)
     f1 = (1.57 * torch.randn(B, D, H, W, generator=gen)).cuda()
     f2 = (1.57 * torch.randn(B, D, H, W, generator=gen)).cuda()
-    for k in ("FLOWCORR_BUILD_EPI_WARPS", "FLOWCORR_BUILD_SCHED", "FLOWCORR_BUILD_STAGES"):
-        monkeypatch.delenv(k, raising=False)
+    for k, v in DEFAULTS.items():
+        _lib.check(lib.fc_tunable_set(k.encode(), v), "fc_tunable_set")
     ref = build(fsb, f1, f2, "3xbf16")._state.pyramid.clone()
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    got = build(fsb, f1, f2, "3xbf16")._state.pyramid
+    try:
+        for k, v in env.items():
+            _lib.check(lib.fc_tunable_set(k.encode(), v), "fc_tunable_set")
+        got = build(fsb, f1, f2, "3xbf16")._state.pyramid
+    finally:
+        for k, v in DEFAULTS.items():
+            lib.fc_tunable_set(k.encode(), v)
     lv_ref = fsb.ops.level_padded(ref, B, H, W, 4)
     lv_got = fsb.ops.level_padded(got, B, H, W, 4)
     for l in range(4):

@@ -73,7 +73,7 @@ def emit(**kw):
         print(json.dumps(kw), flush=True)
 
 
-def collect(reps=5, ref_kernel=True):
+def collect(reps=5, ref_kernel=True, model=True):
     """All rows as a list of dicts: what bench.py embeds under "rows"."""
     global USE_REF
     USE_REF = ref_kernel
@@ -81,7 +81,79 @@ def collect(reps=5, ref_kernel=True):
     row_backward(6, 46, 96, reps)
     row_backward(6, 54, 128, reps)
     row_ondemand(2, 136, 240, reps)
+    row_bf16_volume(8, 55, 128, reps)
+    if model:
+        row_model(8, 436, 1024, max(2, reps // 2))
     return list(ROWS)
+
+
+def row_bf16_volume(B, H, W, reps, iters=12):
+    """bf16 VOLUME mode (FC_VOL_BF16) next to the fp32 volume, same arithmetic (3xbf16 contraction)."""
+    g = torch.Generator().manual_seed(0)
+    f1 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
+    f2 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
+    c = (fsb.coords_grid(B, H, W) + 5.0 * torch.randn(B, 2, H, W, generator=g)).cuda()
+    keep = fsb.CorrBlock.math, fsb.CorrBlock.volume
+    out = {}
+    try:
+        fsb.CorrBlock.math = "3xbf16"
+        for vol in ("f32", "bf16"):
+            fsb.CorrBlock.volume = vol
+            ms_b = timed(lambda: fsb.CorrBlock(f1, f2, L, R), reps)
+            blk = fsb.CorrBlock(f1, f2, L, R)
+            ms_l = timed(lambda: blk(c), reps)
+            out[vol] = {"build_ms": ms_b, "lookup_ms": ms_l, "step_ms": ms_b + iters * ms_l,
+                        "pyramid_gb": blk._state.pyramid.numel() * blk._state.pyramid.element_size() / 1e9}
+            if vol == "f32":
+                ref = blk(c)
+            else:
+                out["max_rel_diff_vs_f32_volume"] = float((blk(c) - ref).abs().max() / ref.abs().max())
+            del blk
+    finally:
+        fsb.CorrBlock.math, fsb.CorrBlock.volume = keep
+    emit(row="bf16 volume mode (build + lookups), stated tolerance 2^-8 of max / 0.05 px EPE", geometry=f"B={B} {H}x{W}", **out)
+
+
+def row_model(B, Himg, Wimg, reps, iters=12):
+    """BASELINE.json's metric itself: RAFT pairs/s at Sintel resolution, the UNMODIFIED reference model
+    (baseline/_ref, random init, stock torch settings) on this GPU with (1) its own CorrBlock, (2) the drop-in block
+    through patch_reference(), (3) RaftRunner eager, (4) RaftRunner with the whole forward in one CUDA graph."""
+    try:
+        from baseline import install_ref
+        p = install_ref.install()
+        if p is None:
+            raise FileNotFoundError("baseline/_ref not installed")
+        if p not in sys.path:
+            sys.path.insert(0, p)
+        import argparse as _ap
+        from core.raft import RAFT
+    except Exception as e:                                    # noqa: BLE001
+        emit(row="RAFT forward pairs/s (reference model)", unavailable=repr(e))
+        return
+    Hp, Wp = (Himg + 7) // 8 * 8, (Wimg + 7) // 8 * 8
+    torch.manual_seed(1234)
+    model = RAFT(_ap.Namespace(small=False, mixed_precision=False, alternate_corr=False)).eval().cuda()
+    g = torch.Generator().manual_seed(0)
+    im1 = (torch.rand(B, 3, Hp, Wp, generator=g) * 255.0).cuda()
+    im2 = (torch.rand(B, 3, Hp, Wp, generator=g) * 255.0).cuda()
+    res = {}
+    with torch.no_grad():
+        res["reference_block_ms"] = timed(lambda: model(im1, im2, iters=iters, test_mode=True), reps, warm=2)
+        fsb.patch_reference()
+        try:
+            res["dropin_block_ms"] = timed(lambda: model(im1, im2, iters=iters, test_mode=True), reps, warm=2)
+        finally:
+            fsb.unpatch_reference()
+        eager = fsb.RaftRunner(model, iters=iters, graph=False)
+        res["runner_eager_ms"] = timed(lambda: eager(im1, im2), reps, warm=2)
+        graphed = fsb.RaftRunner(model, iters=iters, graph=True)
+        res["runner_graph_ms"] = timed(lambda: graphed(im1, im2), reps, warm=2)
+    emit(row="RAFT forward pairs/s @436x1024, 12 iterations: unmodified reference model, same GPU",
+         geometry=f"B={B} {Hp}x{Wp} px", conv_math="torch defaults (cuDNN TF32 convolutions)", **res,
+         pairs_per_s={k[:-3]: B / v * 1e3 for k, v in res.items()},
+         speedup_vs_reference_block={k[:-3]: res["reference_block_ms"] / v for k, v in res.items()})
+    del model, eager, graphed
+    torch.cuda.empty_cache()
 
 
 USE_REF = True

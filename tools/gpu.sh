@@ -16,7 +16,7 @@ run_one() {
   case "$task" in
     tests)
       if [ $# -eq 0 ]; then set -- tests -m gpu -x -q; fi
-      timeout 1500 python -m pytest "$@" 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log ;;
+      timeout 1500 python -m pytest -p no:cacheprovider --timeout 300 "$@" 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log ;;
     smoke)
       timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/smoke.log ;;
     bench)

@@ -12,6 +12,9 @@ One JSON line per measurement."""
 import json
 import os
 import sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _switch import set_switch  # noqa: E402
+import sys
 
 import torch
 
@@ -60,12 +63,12 @@ def main():
         for probe, what in ((0, "real"), (1, "epilogue without global stores"), (2, "no MMAs issued"),
                             (3, "epilogue neither reads TMEM nor stores"), (5, "pooled-level stores off"),
                             (6, "level-0 stores off"), (0, "real again")):
-            os.environ["FLOWCORR_PROBE"] = str(probe)
+            set_switch("FLOWCORR_PROBE", str(probe))
             print(json.dumps({"kernel": "build (pack + tc_build)", "math": mname, "geometry": f"B={B} {H}x{W}",
                               "probe": probe, "what": what,
                               "us": 1e3 * timed(lambda: ops.build(f1, f2, L, math, _lib.VOL_F32), reps=10, warm=3)}),
                   flush=True)
-    os.environ["FLOWCORR_PROBE"] = "0"
+    set_switch("FLOWCORR_PROBE", "0")
     pyr = ops.build(f1, f2, L, _lib.MATH_TC_3XBF16, _lib.VOL_F32)
     it = [0]
 
@@ -83,10 +86,10 @@ def main():
     gout = torch.randn(B, K, H, W, generator=g).cuda()
     gp = torch.zeros(ops.pyramid_numel(B, H, W, L), device="cuda")
     for probe, what in ((0, "real"), (1, "no reduce-add"), (2, "TMA store instead of reduce"), (0, "real again")):
-        os.environ["FLOWCORR_PROBE"] = str(probe)
+        set_switch("FLOWCORR_PROBE", str(probe))
         print(json.dumps({"kernel": "lookup_bwd", "geometry": f"B={B} {H}x{W}", "probe": probe, "what": what,
                           "us": 1e3 * timed(lambda: ops.lookup_bwd(gout, c, gp, L, R, _lib.COORD_CUDA))}), flush=True)
-    os.environ["FLOWCORR_PROBE"] = "0"
+    set_switch("FLOWCORR_PROBE", "0")
 
 
 if __name__ == "__main__":
