@@ -43,13 +43,21 @@ __host__ __device__ constexpr int tc_first_epi_warp(int ew) { return ew == 4 ? 2
 constexpr int TC_BM = 128;           // queries per CTA (UMMA M)
 constexpr int TC_BK = 64;            // bf16 elements per 128-byte swizzle row
 #ifndef FC_TC_STAGES
-#define FC_TC_STAGES 4
+#define FC_TC_STAGES 5
 #endif
-constexpr int TC_STAGES = FC_TC_STAGES;
+constexpr int TC_STAGES = FC_TC_STAGES;                   // operand ring depth (barrier arrays); the 8-warp epilogue keeps 8
+__host__ __device__ constexpr int tc_ring_stages(int ew) { return (ew == 8 && TC_STAGES > 4) ? 4 : TC_STAGES; }   // staging boxes -> 4
 constexpr int TC_STAGE_BYTES = 128 * TC_BK * 2;           // 16 KB: this CTA's half (<= 128 rows) of a target tile x 64 k
 constexpr int TC_ABLK_BYTES = TC_BM * TC_BK * 2;          // 16 KB per k-block of the query tile
 constexpr int TC_STG_FLOATS = 32 * 32;                    // one TMA-store box: [32 queries][32 floats] = 4 KB
-constexpr int TC_STG_BYTES = 8 * TC_STG_FLOATS * 4;       // 8 staging boxes (EW warps x 8 / EW buffers) = 32 KB
+#ifndef FC_TC_STG_BOXES
+#define FC_TC_STG_BOXES 4
+#endif
+// staging boxes per CTA: one per epilogue warp.  With EW = 4 that leaves room for a FIFTH ring stage next to the resident
+// query operand: same-box round robin (profiles/r02b_build_ring_ab.txt) 4 stages + 8 boxes 0.655 ms, 5 stages + 4 boxes
+// 0.628 ms; level-0 stores straight from registers (no staging, 5 or 6 stages) 0.69 ms.
+__host__ __device__ constexpr int tc_stg_boxes(int ew) { return ew == 8 ? 8 : FC_TC_STG_BOXES; }
+__host__ __device__ constexpr int tc_stg_bytes(int ew) { return tc_stg_boxes(ew) * TC_STG_FLOATS * 4; }
 
 
 // ---------------------------------------------------------------- pack pre-pass
@@ -183,8 +191,8 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     uint8_t* a_hi = smem;
     uint8_t* a_lo = a_hi + KB * TC_ABLK_BYTES;
     uint8_t* ring = a_lo + KB * TC_ABLK_BYTES;
-    float* stg = reinterpret_cast<float*>(ring + TC_STAGES * TC_STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg) + TC_STG_BYTES);
+    float* stg = reinterpret_cast<float*>(ring + tc_ring_stages(EW) * TC_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg) + tc_stg_bytes(EW));
     uint64_t* a_full = bars;                       // 1
     uint64_t* b_full = bars + 1;                   // TC_STAGES
     uint64_t* b_empty = b_full + TC_STAGES;        // TC_STAGES
@@ -352,7 +360,8 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // by the TMA unit.
         constexpr int NH = EW / 4;                             // warps per TMEM lane quarter
         constexpr int CMAX = 8 / NH;                           // chunk slots per warp
-        constexpr int NBUF = 8 / EW;                           // staging boxes per warp
+        constexpr int NBUF = tc_stg_boxes(EW) / EW;            // staging boxes per warp
+        static_assert((NBUF & (NBUF - 1)) == 0, "staging boxes per epilogue warp: a power of two (0 = stores from registers)");
         using vol_t = typename VolT<VB>::type;
         vol_t* const lv1 = static_cast<vol_t*>(P.lvl[1]);
         vol_t* const lv2 = static_cast<vol_t*>(P.lvl[2]);
@@ -409,44 +418,55 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] *= P.scale;
                     }
-                    // ---- level 0: staging (swizzled like the store map) -> TMA store
                     const int rem = ncols - c * 32;
-                    float* sbuf = sbuf0 + (use & (NBUF - 1)) * TC_STG_FLOATS;
-                    ++use;
-                    if (lane == 0) tma_wait_group_read<NBUF - 1>();   // the store that last read this box is done
-                    __syncwarp();
-                    if (VB) {
-                        // bf16 volume: rows of 64 bytes (SWIZZLE_64B box of 32 columns) or 32 bytes (plain box of 16)
-                        uint4* sb = reinterpret_cast<uint4*>(sbuf);
-                        if (rem >= 32) {
+                    if constexpr (NBUF == 0) {
+                        // ---- level 0 straight from registers: a thread owns 128 contiguous bytes (64 with a bf16 volume)
+                        // of its query's map; all of shared memory beyond the resident operand goes to the operand ring
+                        if (mine && FC_PROBE_VAL(P) != 1 && FC_PROBE_VAL(P) != 6) {
+                            vol_t* dst = static_cast<vol_t*>(P.lvl[0]) + qrow * (long long)P.NP + q0 + c * 32;
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                sb[lane * 4 + (k ^ ((lane >> 1) & 3))] =
-                                    make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
-                                               pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+                                if (k < 2 || rem >= 32) vol_store8(dst + 8 * k, v + 8 * k);
+                        }
+                    } else {
+                        // ---- level 0: staging (swizzled like the store map) -> TMA store
+                        float* sbuf = sbuf0 + (use & (NBUF - 1)) * TC_STG_FLOATS;
+                        ++use;
+                        if (lane == 0) tma_wait_group_read<NBUF - 1>();   // the store that last read this box is done
+                        __syncwarp();
+                        if (VB) {
+                            // bf16 volume: rows of 64 bytes (SWIZZLE_64B box of 32 columns) or 32 bytes (plain box of 16)
+                            uint4* sb = reinterpret_cast<uint4*>(sbuf);
+                            if (rem >= 32) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    sb[lane * 4 + (k ^ ((lane >> 1) & 3))] =
+                                        make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                                                   pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 2; ++k)
+                                    sb[lane * 2 + k] =
+                                        make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                                                   pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+                            }
+                        } else if (rem >= 32) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                *reinterpret_cast<float4*>(sbuf + lane * 32 + ((k ^ (lane & 7)) << 2)) =
+                                    make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                         } else {
 #pragma unroll
-                            for (int k = 0; k < 2; ++k)
-                                sb[lane * 2 + k] =
-                                    make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
-                                               pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+                            for (int k = 0; k < 4; ++k)
+                                *reinterpret_cast<float4*>(sbuf + lane * 16 + ((k ^ ((lane >> 1) & 3)) << 2)) =
+                                    make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                         }
-                    } else if (rem >= 32) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            *reinterpret_cast<float4*>(sbuf + lane * 32 + ((k ^ (lane & 7)) << 2)) =
-                                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            *reinterpret_cast<float4*>(sbuf + lane * 16 + ((k ^ ((lane >> 1) & 3)) << 2)) =
-                                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0 && rows_valid > 0 && FC_PROBE_VAL(P) != 1 && FC_PROBE_VAL(P) != 6) {
-                        tma_store_3d(rem >= 32 ? &SM.l0_c32 : &SM.l0_c16, smem_u32(sbuf), q0 + c * 32, row0, b);
-                        tma_commit_group();
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && rows_valid > 0 && FC_PROBE_VAL(P) != 1 && FC_PROBE_VAL(P) != 6) {
+                            tma_store_3d(rem >= 32 ? &SM.l0_c32 : &SM.l0_c16, smem_u32(sbuf), q0 + c * 32, row0, b);
+                            tma_commit_group();
+                        }
                     }
                     if (fused) {
                         // ---- level 1: row rp, columns [8 gc, 8 gc + 8); ((a + b) + c) + d, then * 0.25:
@@ -605,8 +625,10 @@ size_t tc_build_workspace_bytes(int B, int D, int H, int W, int, int) {
 }
 
 template <int KB, int EW, int VB>
-static int launch_tc(const CUtensorMap* maps, const TcStoreMaps& SM, const TcParams& P, int B, cudaStream_t s) {
-    const size_t smem = 1024 + 2 * KB * TC_ABLK_BYTES + TC_STAGES * TC_STAGE_BYTES + TC_STG_BYTES + 256;
+static int launch_tc(const CUtensorMap* maps, const TcStoreMaps& SM, const TcParams& P_in, int B, cudaStream_t s) {
+    const size_t smem = 1024 + 2 * KB * TC_ABLK_BYTES + tc_ring_stages(EW) * TC_STAGE_BYTES + tc_stg_bytes(EW) + 256;
+    TcParams P = P_in;
+    if (P.stages > tc_ring_stages(EW)) P.stages = tc_ring_stages(EW);
     FC_SMEM_ATTR_ONCE((tc_build_kernel<KB, EW, VB>), smem);
     // persistent: one CTA pair (cluster 2x1x1) per co-resident SM pair; the occupancy query runs once per
     // (kernel instantiation, device)

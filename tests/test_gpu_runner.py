@@ -71,13 +71,15 @@ def test_runner_graph_is_bit_identical_and_matches_the_reference_forward(core, k
         graphed = fsb.RaftRunner(model, iters=12, graph=True, fused_upsample=False)
         low_g, up_g = graphed(im1, im2)
         low_g2, up_g2 = graphed(im1.flip(0), im2.flip(0))                     # replay with new inputs
+        low_e2, up_e2 = eager(im1.flip(0), im2.flip(0))
         fused = fsb.RaftRunner(model, iters=12, graph=True, fused_upsample=True)
         low_f, up_f = fused(im1, im2)
     # same launches in the same order: the runner reproduces the patched reference forward exactly
     assert torch.equal(low_e, low_p) and torch.equal(up_e, up_p)
     # graph on / off: bit-identical flow
     assert torch.equal(low_g, low_e) and torch.equal(up_g, up_e)
-    assert torch.equal(low_g2, low_e.flip(0)) and torch.equal(up_g2, up_e.flip(0))
+    assert torch.equal(low_g2, low_e2) and torch.equal(up_g2, up_e2)
+    assert rm.epe(up_g2, up_e.flip(0)) <= 1e-3                             # (cuDNN results may depend on the batch position)
     # fused upsampling: same low-resolution flow, upsampled flow to rounding
     assert torch.equal(low_f, low_e)
     assert float((up_f - up_e).abs().max()) <= 1e-4
