@@ -36,7 +36,10 @@ def peaks():
         return 6650.0, 1400.0
 
 
-def timed(fn, reps, warm=3, setup=None):
+def timed(fn, reps, warm=3, setup=None, inner=1):
+    """Mean device time of fn() in ms.  inner > 1: that many back-to-back calls between one pair of events -- for
+    kernels of tens of microseconds a single call between two events mostly measures the host's dispatch gap
+    (custom-op + ctypes, ~30 us) during which the GPU idles."""
     for _ in range(warm):
         if setup: setup()
         fn()
@@ -45,9 +48,12 @@ def timed(fn, reps, warm=3, setup=None):
     for _ in range(reps):
         if setup: setup()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record()
+        e0.record()
+        for _ in range(inner):
+            fn()
+        e1.record()
         torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
+        tot += e0.elapsed_time(e1) / inner
     return tot / reps
 
 
@@ -101,7 +107,7 @@ def row_bf16_volume(B, H, W, reps, iters=12):
             fsb.CorrBlock.volume = vol
             ms_b = timed(lambda: fsb.CorrBlock(f1, f2, L, R), reps)
             blk = fsb.CorrBlock(f1, f2, L, R)
-            ms_l = timed(lambda: blk(c), reps)
+            ms_l = timed(lambda: blk(c), reps, inner=12)
             out[vol] = {"build_ms": ms_b, "lookup_ms": ms_l, "step_ms": ms_b + iters * ms_l,
                         "pyramid_gb": blk._state.pyramid.numel() * blk._state.pyramid.element_size() / 1e9}
             if vol == "f32":
@@ -170,7 +176,7 @@ def row_backward(B, H, W, reps):
     numel = ops.pyramid_numel(B, H, W, L)
     gp = torch.zeros(numel, device="cuda")
     foot = inbounds_footprint(c.cpu(), H, W)
-    ms = timed(lambda: ops.lookup_bwd(gout, c, gp, L, R, _lib.COORD_CUDA), reps)
+    ms = timed(lambda: ops.lookup_bwd(gout, c, gp, L, R, _lib.COORD_CUDA), reps, inner=12)   # 12 lookups per block
     byts = Q * (K * 4 + 2 * foot * 4 + 8)
     emit(row="a6 lookup_bwd", geometry=f"B={B} {H}x{W}", ms=ms, bytes_algorithmic=byts,
          gbs=byts / ms / 1e6, bound="hbm", peak=hbm, frac=byts / ms / 1e6 / hbm,
@@ -208,7 +214,7 @@ def row_ondemand(B, H, W, reps):
     try:
         ms_build = timed(lambda: fsb.AlternateCorrBlock(f1, f2, L, R), max(2, reps // 2), warm=1)
         mblk = fsb.AlternateCorrBlock(f1, f2, L, R)
-        ms_look = timed(lambda: mblk(c), reps)
+        ms_look = timed(lambda: mblk(c), reps, inner=12)
         diff = float((mblk(c) - blk(c)).abs().max() / blk(c).abs().max())
         N = H * W
         emit(row="a7 AlternateCorrBlock route=materialise (build once + FC_COORD_RAW lookups)",
