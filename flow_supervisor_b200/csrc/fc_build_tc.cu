@@ -254,7 +254,8 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
     }
     tc_fence_before();
-    cluster_sync_all();
+    __syncthreads();          // CTA-wide: orders tcgen05.alloc's write of the TMEM address before every read of it
+    cluster_sync_all();       // cluster-wide: the peer's barriers are initialised before anyone arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 

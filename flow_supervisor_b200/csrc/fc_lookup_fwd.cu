@@ -46,17 +46,19 @@ __host__ __device__ constexpr int lf_es(int vb) { return vb ? 2 : 4; }          
 __host__ __device__ constexpr int lf_win_bytes(int vb) { return (6 * 3 * 16 * lf_es(vb) + 127) / 128 * 128; }   // 1152 / 640
 __host__ __device__ constexpr int lf_stage_bytes(int vb) { return QT * lf_win_bytes(vb); }   // 36 864 / 20 480 B per stage
 
-struct alignas(16) QueryDesc {           // producer -> consumers, per stage and lane
-    int ybase;                            // first window row    (2 * first row pair; may be negative)
-    int xbase;                            // first window column (8 * first patch;    may be negative)
-    int pitch;                            // BYTES per window row pair (16 elements * patches in the box)
-    int valid;                            // rows in the box (2 * row pairs); 0: dead, far or fully outside -> exact zeros
+// The footprint box of one query on one level, clipped to the padded map.  Producer and consumers derive it from the
+// same coordinates with the same arithmetic (fc::axis_tap is deterministic), so nothing but the footprints themselves
+// travels through shared memory (an earlier version handed a descriptor over per lane: 14 racecheck hazards, waived
+// by a release/acquire argument -- now there is no such write).
+struct LfBox {
+    int ybase;                            // first window row    (2 * first row pair)
+    int xbase;                            // first window column (8 * first patch)
+    int n_rp, n_pc;                       // row pairs (<= 6) / patches (<= 3) in the box; n_rp == 0: nothing inside the map
 };
 
 struct LfShared {
     uint64_t full[LF_STAGES];
     uint64_t empty[LF_STAGES];
-    QueryDesc desc[LF_STAGES][QT];
 };
 
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
@@ -101,6 +103,19 @@ __device__ __forceinline__ void lf_finish_query(const LookupParams& P, LfQuery& 
     q.near_ = q.live && (fabsf(q.cx) < 1048576.f) && (fabsf(q.cy) < 1048576.f);
 }
 
+// xl / xh, yl / yh: floor indices of the first and last tap on each axis (taps are monotone, span <= R + 1)
+__device__ __forceinline__ LfBox lf_box(const LookupParams& P, int level, bool near_, int xl, int xh, int yl, int yh) {
+    LfBox bx{0, 0, 0, 0};
+    if (near_) {
+        // clip to the padded map: [rp_lo, rp_hi] x [pc_lo, pc_hi] (arithmetic shifts: floor)
+        const int rp_lo = max(yl >> 1, 0), rp_hi = min((yh + 1) >> 1, P.nrp[level] - 1);
+        const int pc_lo = max(xl >> 3, 0), pc_hi = min((xh + 1) >> 3, P.npc[level] - 1);
+        const int n_rp = min(rp_hi - rp_lo + 1, 6), n_pc = min(pc_hi - pc_lo + 1, 3);
+        if (n_rp > 0 && n_pc > 0) { bx.ybase = 2 * rp_lo; bx.xbase = 8 * pc_lo; bx.n_rp = n_rp; bx.n_pc = n_pc; }
+    }
+    return bx;
+}
+
 // Producer: one warp issues the 32 footprint loads of a tile into ring stage `stage`.
 template <int RADIUS, int CM, int VB>
 __device__ __forceinline__ void lf_produce(const LookupParams& P, const LookupMaps& M, LfShared& sh,
@@ -108,7 +123,6 @@ __device__ __forceinline__ void lf_produce(const LookupParams& P, const LookupMa
                                            bool wait_empty, uint32_t empty_parity) {
     constexpr int R = 2 * RADIUS + 1;
     constexpr int ES = lf_es(VB), LF_WIN_BYTES = lf_win_bytes(VB), LF_STAGE_BYTES = lf_stage_bytes(VB);
-    QueryDesc d{0, 0, 32 * ES, 0};
     uint32_t bytes = 0;
     int sel = 0, c0 = 0, c1 = 0;
     const bool mine = (lane / (32 / LF_PSPLIT)) == member;          // this warp's share of the tile's queries
@@ -119,16 +133,11 @@ __device__ __forceinline__ void lf_produce(const LookupParams& P, const LookupMa
         axis_tap<CM>(q.cx, R - 1 - RADIUS, P.ax[level], xh, t0, t1);
         axis_tap<CM>(q.cy, -RADIUS, P.ay[level], yl, t0, t1);
         axis_tap<CM>(q.cy, R - 1 - RADIUS, P.ay[level], yh, t0, t1);
-        // clip the box to the padded map: [rp_lo, rp_hi] x [pc_lo, pc_hi] (arithmetic shifts: floor)
-        const int rp_lo = max(yl >> 1, 0), rp_hi = min((yh + 1) >> 1, P.nrp[level] - 1);
-        const int pc_lo = max(xl >> 3, 0), pc_hi = min((xh + 1) >> 3, P.npc[level] - 1);
-        const int n_rp = min(rp_hi - rp_lo + 1, 6);                   // <= 6 anyway (taps are monotone, span <= R)
-        const int n_pc = min(pc_hi - pc_lo + 1, 3);                   // <= 3 anyway
-        if (n_rp > 0 && n_pc > 0) {
-            sel = lk_shape(n_rp, n_pc);
-            d.ybase = 2 * rp_lo; d.xbase = 8 * pc_lo; d.pitch = 16 * ES * n_pc; d.valid = 2 * n_rp;
-            bytes = (uint32_t)(n_rp * n_pc * 16 * ES);
-            c0 = 16 * pc_lo; c1 = rp_lo;
+        const LfBox bx = lf_box(P, level, true, xl, xh, yl, yh);
+        if (bx.n_rp > 0) {
+            sel = lk_shape(bx.n_rp, bx.n_pc);
+            bytes = (uint32_t)(bx.n_rp * bx.n_pc * 16 * ES);
+            c0 = 2 * bx.xbase; c1 = bx.ybase >> 1;
         }
     }
     // the footprint arithmetic above ran while the stage was still being drained
@@ -137,7 +146,6 @@ __device__ __forceinline__ void lf_produce(const LookupParams& P, const LookupMa
     if (bytes)
         tma_load_3d(win + stage * LF_STAGE_BYTES + lane * LF_WIN_BYTES, &M.m[q.level][sel], smem_u32(&sh.full[stage]),
                     c0, c1, q.gq);
-    if (mine) sh.desc[stage][lane] = d;
     const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
     __syncwarp();
     if (lane == 0) mbar_expect_tx(&sh.full[stage], total);
@@ -197,27 +205,37 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
     for (int j = 1; j < R; ++j) regular = regular && (y0[j] == y0[0] + j);
 #pragma unroll
     for (int aa = 1; aa < APW; ++aa) regular = regular && (x0[aa] == x0[0] + aa);
+    // the box the producer loaded for this lane (same arithmetic on the same coordinates)
+    int xl, xh;
+    {
+        float t0, t1;
+        axis_tap<CM>(q.cx, -RADIUS, P.ax[level], xl, t0, t1);
+        axis_tap<CM>(q.cx, R - 1 - RADIUS, P.ax[level], xh, t0, t1);
+    }
+    const LfBox d = lf_box(P, level, q.near_, xl, xh, y0[0], y0[R - 1]);
+    const bool valid = d.n_rp > 0;
+    const int pitch = 16 * ES * max(d.n_pc, 1);                      // bytes per window row pair
+    const int ncols = 8 * max(d.n_pc, 1), nrows = 2 * max(d.n_rp, 1);
 
     // outputs of this thread: out[b][level*R*R + (w*APW + aa)*R + j][p] = outq[(aa*R + j) * N]
     float* outq = P.io + ((long long)q.b * P.K + level * R * R + w * APW * R) * P.N + q.p;
     const int N = P.N;
 
     mbar_wait(&sh.full[stage], parity);
-    const QueryDesc d = sh.desc[stage][lane];
     const uint32_t wq = win + stage * LF_STAGE_BYTES + lane * LF_WIN_BYTES;
-    const int pitch = d.pitch;
-    const bool fast = q.live && d.valid && regular;                  // this lane reads its sub-window on the fast path
+    const bool fast = q.live && valid && regular;                    // this lane's outputs come from the fast path
     // when no lane needs the per-tap slow path, the ring stage is handed back as soon as the
     // sub-windows sit in registers: a stage is then busy for the loads only, not for the
     // arithmetic and the stores
-    const bool early = !__any_sync(0xffffffffu, q.live && d.valid && !regular) && !(FC_PROBE_VAL(P) & 1);   // FLOWCORR_PROBE=1: late release (stage probe)
+    const bool early = !__any_sync(0xffffffffu, q.live && valid && !regular) && !(FC_PROBE_VAL(P) & 1);   // FLOWCORR_PROBE=1: late release (stage probe)
 
-    // horizontally interpolated (R + 1) x APW sub-window of a regular lane
+    // horizontally interpolated (R + 1) x APW sub-window.  EVERY lane executes the loads (addresses are clamped into
+    // the lane's own window, so lanes without a footprint read stale bytes they never use): the stage release below
+    // can then depend on the last load through any lane's register.
     float h[R + 1][APW];
-    if (fast) {
+    {
         // byte addresses of window columns x0[0] .. x0[0]+APW (a patch jump every 8 columns); a column outside the
         // (clipped) box is outside the padded map: its address is clamped into the box and its weight set to zero
-        const int ncols = pitch / (2 * ES), nrows = d.valid;
         uint32_t col[APW + 1];
         bool okc[APW + 1];
 #pragma unroll
@@ -258,12 +276,12 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
         __syncwarp();
         if (lane == 0)
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];   // after %1\n" ::"r"(smem_u32(&sh.empty[stage])),
-                         "f"(fast ? h[R][APW - 1] : 0.f)
+                         "f"(h[R][APW - 1])
                          : "memory");
     }
 
     if (q.live) {
-        if (!d.valid) {
+        if (!valid) {
 #pragma unroll
             for (int aa = 0; aa < APW; ++aa)
                 if (EVEN || w * APW + aa < R) {
@@ -281,7 +299,15 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
             }
         } else {
             // floor flips among the taps (lattice coordinates): every tap addressed on its own
-            const int ncols = pitch / (2 * ES), nrows = d.valid;
+            // (the fast-path block above zeroed weights of this lane by ITS column / row pattern: recompute them)
+#pragma unroll
+            for (int j = 0; j < R; ++j) { int t; axis_tap<CM>(q.cy, j - RADIUS, P.ay[level], t, wy0[j], wy1[j]); }
+#pragma unroll
+            for (int aa = 0; aa < APW; ++aa) {
+                int t;
+                const int a = EVEN ? w * APW + aa : min(w * APW + aa, R - 1);
+                axis_tap<CM>(q.cx, a - RADIUS, P.ax[level], t, wx0[aa], wx1[aa]);
+            }
 #pragma unroll
             for (int aa = 0; aa < APW; ++aa) {
                 if (w * APW + aa >= R) break;
