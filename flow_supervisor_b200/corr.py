@@ -56,6 +56,11 @@ def coords_grid(batch, ht, wd, device=None):
     return torch.stack([xs, ys], dim=0).float()[None].repeat(batch, 1, 1, 1)
 
 
+def _lookup_fn():
+    """torch.ops.flowcorr.lookup while a compiler traces, else the plain function behind it (no dispatcher hop)."""
+    return ops.lookup if torch.compiler.is_compiling() else ops.lookup_direct
+
+
 class _BlockState:
     """Per-CorrBlock state shared by the autograd nodes: the volume itself (never an
     autograd leaf) and ONE lazily zeroed gradient pyramid that every lookup's backward
@@ -152,7 +157,7 @@ class CorrBlock:
             raise ValueError(f"coords must be ({st.B}, 2, {st.H}, {st.W}); got {tuple(coords.shape)}")
         if self._token is not None and torch.is_grad_enabled():
             return _Lookup.apply(self._token, coords.detach(), st)
-        return ops.lookup(st.pyramid, coords.detach(), st.L, st.radius, st.coord)
+        return _lookup_fn()(st.pyramid, coords.detach(), st.L, st.radius, st.coord)
 
     def lookup_debug(self, coords):
         """(out, x0, y0, corner_mask): the lookup plus its integer part, for parity tests."""
@@ -220,5 +225,5 @@ class AlternateCorrBlock:
     def __call__(self, coords):
         B, D, H, W = self._shape
         if self.materialised:
-            return ops.lookup(self._pyramid, coords.detach(), self.num_levels, self.radius, _lib.COORD_RAW)
+            return _lookup_fn()(self._pyramid, coords.detach(), self.num_levels, self.radius, _lib.COORD_RAW)
         return ops.ondemand_lookup(self._ws, coords.detach(), D, self.num_levels, self.radius)

@@ -67,6 +67,23 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _NoSwitch:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def _on(device):
+    """Context that makes `device` current -- a no-op object when it already is (the common case; torch.cuda.device()
+    costs several microseconds of host time per call, as much as a tenth of a lookup kernel)."""
+    return _NO_SWITCH if device.index is None or torch.cuda.current_device() == device.index else torch.cuda.device(device)
+
+
 # ----------------------------------------------------------------------------- build
 @custom_op("flowcorr::build", mutates_args=())
 def build(fmap1: Tensor, fmap2: Tensor, num_levels: int, math: int, vol_dtype: int) -> Tensor:
@@ -91,19 +108,23 @@ def _(fmap1, fmap2, num_levels, math, vol_dtype):
 
 
 # ----------------------------------------------------------------------------- lookup
-@custom_op("flowcorr::lookup", mutates_args=())
-def lookup(pyramid: Tensor, coords: Tensor, num_levels: int, radius: int, coord_mode: int) -> Tensor:
-    """CorrBlock.__call__ (corr.py:29-50): (B, 2, H, W) -> (B, L*(2r+1)^2, H, W) fp32."""
+def lookup_direct(pyramid: Tensor, coords: Tensor, num_levels: int, radius: int, coord_mode: int) -> Tensor:
+    """CorrBlock.__call__ (corr.py:29-50): (B, 2, H, W) -> (B, L*(2r+1)^2, H, W) fp32.
+    The plain function behind ``torch.ops.flowcorr.lookup``: the classes call it directly in eager inference (the
+    custom-op dispatcher costs more host time per call than the kernel runs on the GPU)."""
     _need_cuda(pyramid, coords)
     c = _f32c(coords)
     B, _, H, W = c.shape
     vol_dtype = _lib.VOL_F32 if pyramid.dtype == torch.float32 else _lib.VOL_BF16
-    with torch.cuda.device(c.device):
+    with _on(c.device):
         out = torch.empty(B, num_levels * (2 * radius + 1) ** 2, H, W, dtype=torch.float32, device=c.device)
         _lib.check(_lib.load().fc_lookup_fwd(pyramid.data_ptr(), c.data_ptr(), out.data_ptr(), B, H, W,
                                              num_levels, radius, vol_dtype, coord_mode,
                                              None, None, None, _stream()), "fc_lookup_fwd")
     return out
+
+
+lookup = custom_op("flowcorr::lookup", mutates_args=())(lookup_direct)
 
 
 @lookup.register_fake
