@@ -31,11 +31,10 @@ struct LookupParams {
 };
 
 // Per level, 18 TMA views of the (gradient) pyramid as a 3-D tensor [query][row pair][2*Wp floats]
-// over the 2x8-patch layout: boxes of {1..3 patches, 1..6 row pairs, 1 query}.  A footprint box is CLIPPED to the
-// query's map in software: the TMA unit fetches every byte of a box from L2 / DRAM, also the parts it then
-// zero-fills because they lie outside the tensor (ncu, profiles/r02a: 168.4 MB of TMA load traffic per launch
-// = exactly the unclipped boxes, against 117.5 MB inside the maps).  Shared by the forward (footprint loads)
-// and the backward (footprint reduce-adds).  Memoised per (pointer, geometry) in fc_lookup_fwd.cu.
+// over the 2x8-patch layout: boxes of {1..3 patches, 1..6 row pairs, 1 query}.  The forward (footprint loads) uses
+// {5|6} x {2|3} at signed coordinates and lets the TMA unit zero-fill what lies outside the map; the backward
+// (footprint reduce-adds, which trap at negative coordinates) clips its boxes to the map and takes any shape.
+// Memoised per (pointer, geometry) in fc_lookup_fwd.cu.
 constexpr int LK_SHAPES = 18;
 __host__ __device__ __forceinline__ int lk_shape(int n_rp, int n_pc) { return (n_rp - 1) * 3 + (n_pc - 1); }
 struct LookupMaps {

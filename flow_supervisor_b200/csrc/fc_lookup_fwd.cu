@@ -5,13 +5,15 @@
 // the level of a tile rotates with its query block so that every CTA sees all levels.
 // A query's footprint is ONE TMA tensor load: the level is described to the TMA unit as a
 // 3-D tensor [query][row pair][2*Wp floats] over the 2x8-patch layout (include/flowcorr.h),
-// and a box of {1..3 patches, 1..6 row pairs, 1 query} lands the (2r+2)^2 footprint (+1 guard
-// row/column for floor flips of the normalise/un-normalise round trip) in shared memory.
-// The box is CLIPPED to the padded map in software (the TMA unit fetches every byte of a box,
-// also the part outside the tensor that it then zero-fills); taps outside the box get weight
-// zero and a clamped address -- that is the reference's padding_mode='zeros'; pad rows/columns
-// inside the map hold zeros by the pyramid invariant.  18 box shapes per level keep the DRAM
-// traffic at the 64-byte patches of the map the footprint really touches.
+// and a box of {2|3 patches, 5|6 row pairs, 1 query} at signed coordinates lands the (2r+2)^2
+// footprint (+1 guard row/column for floor flips of the normalise/un-normalise round trip) in
+// shared memory.  Everything outside the padded map is zero-filled by the TMA unit itself --
+// that IS the reference's padding_mode='zeros'; pad rows/columns inside the map hold zeros by the
+// pyramid invariant.  Four box shapes per level follow the patches the footprint touches.
+// (Measured, profiles/r02a: the TMA unit requests every byte of a box from L2, also the part it then
+// zero-fills -- 168.4 MB per launch = exactly the unclipped boxes, 117.6 MB when the boxes are clipped
+// to the maps in software -- but L2 fills from DRAM in whole 128-byte lines either way: 166 MB read per
+// launch with and without clipping, and the clipped variant's extra masking made the kernel ~2 % slower.)
 //
 // A 6-stage mbarrier ring decouples three producer warps (tile k -> producer k % 3: coordinate
 // prefetch, footprint arithmetic, one TMA issue per lane) from three consumer groups of
@@ -104,14 +106,13 @@ __device__ __forceinline__ void lf_finish_query(const LookupParams& P, LfQuery& 
 }
 
 // xl / xh, yl / yh: floor indices of the first and last tap on each axis (taps are monotone, span <= R + 1)
-__device__ __forceinline__ LfBox lf_box(const LookupParams& P, int level, bool near_, int xl, int xh, int yl, int yh) {
+__device__ __forceinline__ LfBox lf_box(bool near_, int xl, int xh, int yl, int yh) {
     LfBox bx{0, 0, 0, 0};
     if (near_) {
-        // clip to the padded map: [rp_lo, rp_hi] x [pc_lo, pc_hi] (arithmetic shifts: floor)
-        const int rp_lo = max(yl >> 1, 0), rp_hi = min((yh + 1) >> 1, P.nrp[level] - 1);
-        const int pc_lo = max(xl >> 3, 0), pc_hi = min((xh + 1) >> 3, P.npc[level] - 1);
-        const int n_rp = min(rp_hi - rp_lo + 1, 6), n_pc = min(pc_hi - pc_lo + 1, 3);
-        if (n_rp > 0 && n_pc > 0) { bx.ybase = 2 * rp_lo; bx.xbase = 8 * pc_lo; bx.n_rp = n_rp; bx.n_pc = n_pc; }
+        const int rp0 = yl >> 1, pc0 = xl >> 3;                       // arithmetic shifts: floor
+        const int n_rp = ((yh + 1) >> 1) - rp0 + 1;                   // <= 6
+        const int n_pc = ((xh + 1) >> 3) - pc0 + 1;                   // <= 3
+        bx.ybase = 2 * rp0; bx.xbase = 8 * pc0; bx.n_rp = n_rp > 5 ? 6 : 5; bx.n_pc = n_pc > 2 ? 3 : 2;
     }
     return bx;
 }
@@ -133,12 +134,10 @@ __device__ __forceinline__ void lf_produce(const LookupParams& P, const LookupMa
         axis_tap<CM>(q.cx, R - 1 - RADIUS, P.ax[level], xh, t0, t1);
         axis_tap<CM>(q.cy, -RADIUS, P.ay[level], yl, t0, t1);
         axis_tap<CM>(q.cy, R - 1 - RADIUS, P.ay[level], yh, t0, t1);
-        const LfBox bx = lf_box(P, level, true, xl, xh, yl, yh);
-        if (bx.n_rp > 0) {
-            sel = lk_shape(bx.n_rp, bx.n_pc);
-            bytes = (uint32_t)(bx.n_rp * bx.n_pc * 16 * ES);
-            c0 = 2 * bx.xbase; c1 = bx.ybase >> 1;
-        }
+        const LfBox bx = lf_box(true, xl, xh, yl, yh);
+        sel = lk_shape(bx.n_rp, bx.n_pc);
+        bytes = (uint32_t)(bx.n_rp * bx.n_pc * 16 * ES);              // (the TMA unit counts zero-filled bytes too)
+        c0 = 2 * bx.xbase; c1 = bx.ybase >> 1;                        // signed tensor coordinates (arithmetic shift)
     }
     // the footprint arithmetic above ran while the stage was still being drained
     if (wait_empty) mbar_wait(&sh.empty[stage], empty_parity);
@@ -212,10 +211,9 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
         axis_tap<CM>(q.cx, -RADIUS, P.ax[level], xl, t0, t1);
         axis_tap<CM>(q.cx, R - 1 - RADIUS, P.ax[level], xh, t0, t1);
     }
-    const LfBox d = lf_box(P, level, q.near_, xl, xh, y0[0], y0[R - 1]);
+    const LfBox d = lf_box(q.near_, xl, xh, y0[0], y0[R - 1]);
     const bool valid = d.n_rp > 0;
-    const int pitch = 16 * ES * max(d.n_pc, 1);                      // bytes per window row pair
-    const int ncols = 8 * max(d.n_pc, 1), nrows = 2 * max(d.n_rp, 1);
+    const int pitch = 16 * ES * (d.n_pc > 2 ? 3 : 2);                // bytes per window row pair
 
     // outputs of this thread: out[b][level*R*R + (w*APW + aa)*R + j][p] = outq[(aa*R + j) * N]
     float* outq = P.io + ((long long)q.b * P.K + level * R * R + w * APW * R) * P.N + q.p;
@@ -234,35 +232,24 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
     // can then depend on the last load through any lane's register.
     float h[R + 1][APW];
     {
-        // byte addresses of window columns x0[0] .. x0[0]+APW (a patch jump every 8 columns); a column outside the
-        // (clipped) box is outside the padded map: its address is clamped into the box and its weight set to zero
+        // byte addresses of window columns x0[0] .. x0[0]+APW (a patch jump every 8 columns)
         uint32_t col[APW + 1];
-        bool okc[APW + 1];
 #pragma unroll
         for (int i = 0; i <= APW; ++i) {
-            const int xr = x0[0] + i - d.xbase;
-            okc[i] = (unsigned)xr < (unsigned)ncols;
-            const int xc = min(max(xr, 0), ncols - 1);
-            col[i] = wq + (uint32_t)ES * (uint32_t)(xc + (xc & ~7));
+            const int xr = min(max(x0[0] + i - d.xbase, 0), 23);
+            col[i] = wq + (uint32_t)ES * (uint32_t)(xr + (xr & ~7));
         }
-#pragma unroll
-        for (int aa = 0; aa < APW; ++aa) {
-            wx0[aa] = okc[aa] ? wx0[aa] : 0.f;
-            wx1[aa] = okc[aa + 1] ? wx1[aa] : 0.f;
-        }
-        // footprint row n sits at (m >> 1) * pitch + (m & 1) * 32 bytes, m = y0[0] - ybase + n clamped into the box
+        // footprint row n = y0[0] - ybase + r sits at (n >> 1) * pitch + (n & 1) * 8 elements
+        const int n0 = min(max(y0[0] - d.ybase, 0), 1);
+        uint32_t rofs = (uint32_t)(8 * ES * n0);
+        uint32_t step = n0 ? (uint32_t)(pitch - 8 * ES) : (uint32_t)(8 * ES);   // n even -> +8 elements, n odd -> +pitch - 8 elements
         float v[R + 1][APW + 1];
-        const int m0 = y0[0] - d.ybase;
 #pragma unroll
         for (int n = 0; n <= R; ++n) {
-            const int m = m0 + n;
-            const bool okr = (unsigned)m < (unsigned)nrows;
-            const int mc = min(max(m, 0), nrows - 1);
-            const uint32_t rofs = (uint32_t)((mc >> 1) * pitch + (mc & 1) * (8 * ES));
 #pragma unroll
             for (int i = 0; i <= APW; ++i) v[n][i] = lds_vol<VB>(col[i] + rofs);
-            if (n < R) wy0[n] = okr ? wy0[n] : 0.f;
-            if (n > 0) wy1[n - 1] = okr ? wy1[n - 1] : 0.f;
+            rofs += step;
+            step = (uint32_t)pitch - step;
         }
 #pragma unroll
         for (int n = 0; n <= R; ++n)
@@ -270,14 +257,15 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
             for (int aa = 0; aa < APW; ++aa) h[n][aa] = fmaf(wx1[aa], v[n][aa + 1], wx0[aa] * v[n][aa]);
     }
     if (early) {
-        // The arrive must not overtake the shared loads: they drain through the LSU (bank conflicts make
-        // that take a while) whereas the barrier unit answers at once, and a refill racing them was
-        // observed.  h[R][APW-1] depends on the LAST load issued; a warp's shared loads return in order.
-        __syncwarp();
-        if (lane == 0)
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];   // after %1\n" ::"r"(smem_u32(&sh.empty[stage])),
-                         "f"(h[R][APW - 1])
-                         : "memory");
+        // The arrive must not overtake the shared loads: they drain through the LSU (bank conflicts make that take a
+        // while) whereas the barrier unit answers at once, and a refill racing the LAST loads of the burst was observed
+        // (wrong values in the last rows / columns of the low lanes; tests at ring-reuse sizes and the debug variant caught
+        // it).  A dependency that exists only in the asm operand list is not enough -- ptxas sees no consumer of the
+        // register -- so every lane's last interpolated value (it depends on the last load issued; a warp's shared loads
+        // return in order) goes through a warp vote, and the arrive is predicated on the vote.  The compared pattern is a
+        // NaN payload no FFMA produces, so the vote is always true; the hardware cannot know that.
+        const bool landed = __any_sync(0xffffffffu, __float_as_uint(h[R][APW - 1]) != 0xffffffffu);
+        if (lane == 0 && landed) mbar_arrive(&sh.empty[stage]);
     }
 
     if (q.live) {
@@ -299,35 +287,20 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
             }
         } else {
             // floor flips among the taps (lattice coordinates): every tap addressed on its own
-            // (the fast-path block above zeroed weights of this lane by ITS column / row pattern: recompute them)
-#pragma unroll
-            for (int j = 0; j < R; ++j) { int t; axis_tap<CM>(q.cy, j - RADIUS, P.ay[level], t, wy0[j], wy1[j]); }
-#pragma unroll
-            for (int aa = 0; aa < APW; ++aa) {
-                int t;
-                const int a = EVEN ? w * APW + aa : min(w * APW + aa, R - 1);
-                axis_tap<CM>(q.cx, a - RADIUS, P.ax[level], t, wx0[aa], wx1[aa]);
-            }
 #pragma unroll
             for (int aa = 0; aa < APW; ++aa) {
                 if (w * APW + aa >= R) break;
-                const int xa = x0[aa] - d.xbase, xb = xa + 1;
-                const float wa = (unsigned)xa < (unsigned)ncols ? wx0[aa] : 0.f;
-                const float wb = (unsigned)xb < (unsigned)ncols ? wx1[aa] : 0.f;
-                const int xac = min(max(xa, 0), ncols - 1), xbc = min(max(xb, 0), ncols - 1);
-                const uint32_t ca = wq + (uint32_t)ES * (uint32_t)(xac + (xac & ~7)), cb = wq + (uint32_t)ES * (uint32_t)(xbc + (xbc & ~7));
+                const int xa = min(max(x0[aa] - d.xbase, 0), 22), xb = xa + 1;
+                const uint32_t ca = wq + (uint32_t)ES * (uint32_t)(xa + (xa & ~7)), cb = wq + (uint32_t)ES * (uint32_t)(xb + (xb & ~7));
                 float* oa = outq + aa * R * N;
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
-                    const int ya = y0[j] - d.ybase, yb = ya + 1;
-                    const float wt = (unsigned)ya < (unsigned)nrows ? wy0[j] : 0.f;
-                    const float wu = (unsigned)yb < (unsigned)nrows ? wy1[j] : 0.f;
-                    const int yac = min(max(ya, 0), nrows - 1), ybc = min(max(yb, 0), nrows - 1);
-                    const uint32_t ra = (uint32_t)((yac >> 1) * pitch + (yac & 1) * (8 * ES));
-                    const uint32_t rb = (uint32_t)((ybc >> 1) * pitch + (ybc & 1) * (8 * ES));
-                    const float top = fmaf(wb, lds_vol<VB>(cb + ra), wa * lds_vol<VB>(ca + ra));
-                    const float bot = fmaf(wb, lds_vol<VB>(cb + rb), wa * lds_vol<VB>(ca + rb));
-                    *oa = fmaf(wu, bot, wt * top);
+                    const int ya = min(max(y0[j] - d.ybase, 0), 10), yb = ya + 1;
+                    const uint32_t ra = (uint32_t)((ya >> 1) * pitch + (ya & 1) * (8 * ES));
+                    const uint32_t rb = (uint32_t)((yb >> 1) * pitch + (yb & 1) * (8 * ES));
+                    const float top = fmaf(wx1[aa], lds_vol<VB>(cb + ra), wx0[aa] * lds_vol<VB>(ca + ra));
+                    const float bot = fmaf(wx1[aa], lds_vol<VB>(cb + rb), wx0[aa] * lds_vol<VB>(ca + rb));
+                    *oa = fmaf(wy1[j], bot, wy0[j] * top);
                     oa += N;
                 }
             }
@@ -413,9 +386,10 @@ static int encode_level_maps(LookupMaps& M, const void* pyramid, const Pyramid& 
         cuuint64_t strides[2] = {(cuuint64_t)(2 * lv.Wp) * es, (cuuint64_t)lv.Hp * lv.Wp * es};
         cuuint32_t estr[3] = {1, 1, 1};
         void* base = const_cast<uint8_t*>(static_cast<const uint8_t*>(pyramid)) + (size_t)lv.offset * es;
-        // shapes a clipped footprint can take on this level: at most the whole map
-        for (int n_rp = 1; n_rp <= 6 && n_rp <= lv.Hp / 2; ++n_rp)
-            for (int n_pc = 1; n_pc <= 3 && n_pc <= lv.Wp / 8; ++n_pc) {
+        // the forward uses {5|6 row pairs} x {2|3 patches} (boxes may overhang the map: zero fill), the backward's
+        // reduce-adds are clipped to the map and take any of the 18 shapes
+        for (int n_rp = 1; n_rp <= 6; ++n_rp)
+            for (int n_pc = 1; n_pc <= 3; ++n_pc) {
                 cuuint32_t box[3] = {(cuuint32_t)(16 * n_pc), (cuuint32_t)n_rp, 1};
                 CUresult r = enc(&M.m[l][lk_shape(n_rp, n_pc)],
                                  vb ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
