@@ -81,6 +81,80 @@ def test_forward_matches_reference_golden(fsb, golden, name):
             assert torch.equal(out, blk(cuda(c)))                             # debug path == fast path
 
 
+@pytest.mark.parametrize("name", ["fwd_small_d128_r3", "fwd_d256_b2"])
+def test_forward_matches_reference_golden_in_the_benchmarked_mode(fsb, golden, name):
+    """The same golden vectors through the mode bench.py and 'auto' run (tcgen05 build, 3xbf16): values within the
+    1e-4 contract, integer part and out-of-bounds pattern bit-exact."""
+    g = golden(name)
+    L, r = int(g["num_levels"]), int(g["radius"])
+    with mode(fsb, math="3xbf16", coord_mode="cpu"):
+        blk = fsb.CorrBlock(cuda(g["fmap1"]), cuda(g["fmap2"]), num_levels=L, radius=r)
+        pyr = corr_spec.build(g["fmap1"], g["fmap2"], L)
+        for law in laws(g):
+            c = g[f"coords_{law}"]
+            out, x0, y0, mask = blk.lookup_debug(cuda(c))
+            ref = g[f"out_{law}"]
+            assert rel_err(out, ref) < VAL_TOL, law
+            assert np.array_equal(out.cpu().numpy() == 0, ref == 0), law
+            _, dbg = corr_spec.lookup(pyr, c, r, rounding="cpu", debug=True)
+            for l in range(L):
+                assert np.array_equal(x0[:, l].cpu().numpy(), dbg[l]["x0"]), (law, l)
+                assert np.array_equal(y0[:, l].cpu().numpy(), dbg[l]["y0"]), (law, l)
+                assert np.array_equal(mask[:, l].cpu().numpy(), dbg[l]["mask"]), (law, l)
+
+
+def test_backward_matches_reference_autograd_golden_in_the_benchmarked_mode(fsb, golden):
+    g = golden("bwd_odd_d64")
+    L, r, T = int(g["num_levels"]), int(g["radius"]), int(g["n_lookups"])
+    f1 = cuda(g["fmap1"]).requires_grad_()
+    f2 = cuda(g["fmap2"]).requires_grad_()
+    with mode(fsb, math="3xbf16", coord_mode="cpu"):
+        blk = fsb.CorrBlock(f1, f2, num_levels=L, radius=r)
+        loss = 0.0
+        for t in range(T):
+            loss = loss + (blk(cuda(g[f"coords{t}"])) * cuda(g[f"gout{t}"])).sum()
+        loss.backward()
+    assert rel_err(f1.grad, g["dfmap1"]) < VAL_TOL
+    assert rel_err(f2.grad, g["dfmap2"]) < VAL_TOL
+
+
+def test_narrow_maps_take_the_fp32_mode_or_fail_cleanly(fsb):
+    """W <= 8 tokens: one tile of two target rows would be a 16-column UMMA with M = 256 (invalid).  'auto' runs the
+    CUDA-core mode; asking for the tensor-core mode explicitly is a clean error, not a trap."""
+    gen = torch.Generator().manual_seed(1)
+    f1 = torch.randn(1, 64, 16, 8, generator=gen).cuda()
+    f2 = torch.randn(1, 64, 16, 8, generator=gen).cuda()
+    with mode(fsb, math="auto"):
+        blk = fsb.CorrBlock(f1, f2, num_levels=2, radius=2)
+    ref = corr_torch.TorchCorrBlock(f1, f2, 2, 2)
+    c = (corr_torch.coords_grid(1, 16, 8) + 0.7).cuda()
+    assert rel_err(blk(c), ref(c)) < VAL_TOL
+    with mode(fsb, math="3xbf16"):
+        with pytest.raises(RuntimeError, match="tokens"):
+            fsb.CorrBlock(f1, f2, num_levels=2, radius=2)
+    assert torch.isfinite(blk(c)).all()                                    # the device is still usable
+
+
+def test_alternate_block_accepts_unit_dimension_levels(fsb):
+    """8 x 8 tokens with 4 levels: level 3 is 1 x 1.  The reference's AlternateCorrBlock works there (its indexing never
+    divides by size - 1); so do both routes here (CorrBlock itself raises: the reference returns NaN)."""
+    gen = torch.Generator().manual_seed(2)
+    f1 = torch.randn(1, 64, 8, 8, generator=gen).cuda()
+    f2 = torch.randn(1, 64, 8, 8, generator=gen).cuda()
+    c = (corr_torch.coords_grid(1, 8, 8) + 0.4 * torch.randn(1, 2, 8, 8, generator=gen)).cuda()
+    outs = {}
+    for route in ("materialise", "ondemand"):
+        fsb.AlternateCorrBlock.route = route
+        try:
+            outs[route] = fsb.AlternateCorrBlock(f1, f2, num_levels=4, radius=4)(c)
+        finally:
+            fsb.AlternateCorrBlock.route = "auto"
+    assert torch.isfinite(outs["materialise"]).all()
+    assert rel_err(outs["materialise"], outs["ondemand"]) < VAL_TOL
+    with pytest.raises(RuntimeError, match="unit dimension"):
+        fsb.CorrBlock(f1, f2, num_levels=4, radius=4)(c)
+
+
 def test_pooling_is_bit_exact(fsb, golden):
     g = golden("fwd_odd_d32")
     with mode(fsb, math="fp32"):
