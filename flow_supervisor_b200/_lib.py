@@ -42,6 +42,10 @@ SIGNATURES = {
     "fc_altcorr_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "fc_altcorr_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "fc_upsample_flow": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "fc_fnet_tail_weights_bytes": (_z, [_i, _i]),
+    "fc_fnet_tail_supported": (_i, [_i, _i, _i, _i]),
+    "fc_fnet_tail_prepare": (_i, [_p, _p, _i, _i, _p, _z, _p]),
+    "fc_build_from_fnet_tail": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
 }
 
 _lock = threading.Lock()

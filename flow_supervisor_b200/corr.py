@@ -143,6 +143,29 @@ class CorrBlock:
         else:
             st.pyramid = ops.build(fmap1.detach(), fmap2.detach(), num_levels, st.math, self._vol_dtype)
 
+    @classmethod
+    def from_fnet_tail(cls, x, packed_weights, out_dim, num_levels=4, radius=4):
+        """Inference-only constructor fused with the feature encoder's 1x1 output convolution (SURVEY.md section 8 row
+        f3; extractor.py:184, raft.py:99-107): ``x`` = (2B, C, H, W) activations in front of ``fnet.conv2`` (frames of
+        image 1, then image 2), ``packed_weights`` = ops.fnet_tail_prepare(conv2.weight, conv2.bias).  Equivalent to
+        ``CorrBlock(*torch.split(conv2(x), B), num_levels, radius)`` without the fp32 feature maps and the pack pre-pass."""
+        if not x.is_cuda:
+            raise RuntimeError("flow_supervisor_b200.CorrBlock needs CUDA tensors: this package has no CPU fallback")
+        self = cls.__new__(cls)
+        self.num_levels, self.radius = num_levels, radius
+        st = self._state = _BlockState()
+        st.B, st.H, st.W = x.shape[0] // 2, x.shape[2], x.shape[3]
+        st.L, st.radius = num_levels, radius
+        st.math, st.coord = resolve_math(cls.math, out_dim, st.W), _COORD[cls.coord_mode]
+        if st.math == _lib.MATH_FP32 or not ops.fnet_tail_supported(x.shape[1], out_dim, st.H, st.W):
+            raise RuntimeError(f"from_fnet_tail: C={x.shape[1]}, D={out_dim}, {st.H}x{st.W} tokens with math "
+                               f"'{cls.math}' is outside the fused tail's range (tensor-core math, C in {{64, 128}}, "
+                               "D % 64 == 0, H*W % 4 == 0): run conv2 and CorrBlock(fmap1, fmap2)")
+        self._vol_dtype = _VOL[cls.volume]
+        self._token = None
+        st.pyramid = ops.build_from_fnet_tail(x.detach(), packed_weights, out_dim, num_levels, st.math, self._vol_dtype)
+        return self
+
     @property
     def corr_pyramid(self):
         """corr.py:16,24,27: list of (B*N, 1, Hl, Wl) levels (gathered copies; the hot path

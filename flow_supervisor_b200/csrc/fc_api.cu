@@ -39,8 +39,9 @@ int simt_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, flo
                    const Pyramid& pyr, int D, int H, int W, cudaStream_t s);
 // fc_build_tc.cu
 size_t tc_build_workspace_bytes(int B, int D, int H, int W, int L, int math);
+struct FeatSource { const float* x; const void* packed_w; int C; };     // fc_build.cuh
 int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr, int D, int H, int W,
-             int vol_dtype, int math, void* ws, size_t ws_bytes, cudaStream_t s);
+             int vol_dtype, int math, void* ws, size_t ws_bytes, cudaStream_t s, const FeatSource* feat);
 
 // fc_bwd_tc.cu
 bool tc_bwd_supported(int D, int H, int W);
@@ -226,7 +227,7 @@ extern "C" int fc_build(const float* fmap1, const float* fmap2, void* pyramid,
         return simt_build(fmap1, fmap2, static_cast<float*>(pyramid), pyr, D, H, W, s);
     }
     FC_REQUIRE(math == FC_MATH_TC_3XBF16 || math == FC_MATH_TC_BF16, "fc_build: unknown math mode %d", math);
-    return tc_build(fmap1, fmap2, pyramid, pyr, D, H, W, vol_dtype, math, workspace, workspace_bytes, s);
+    return tc_build(fmap1, fmap2, pyramid, pyr, D, H, W, vol_dtype, math, workspace, workspace_bytes, s, nullptr);
 }
 
 extern "C" size_t fc_build_bwd_workspace_bytes(int B, int D, int H, int W, int num_levels, int math) {
@@ -256,4 +257,17 @@ extern "C" int fc_build_bwd(float* grad_pyramid, const float* fmap1, const float
                   "(D %% 64 == 0, D <= 256, padded map <= 16384 targets): running the fp32 CUDA-core contractions", D, H, W);
     if (int e = simt_fold(grad_pyramid, pyr, s)) return e;
     return simt_build_bwd(grad_pyramid, fmap1, fmap2, dfmap1, dfmap2, pyr, D, H, W, s);
+}
+
+extern "C" int fc_build_from_fnet_tail(const float* x, const void* packed_weights, void* pyramid,
+                                       int B, int C, int D, int H, int W, int num_levels, int vol_dtype, int math,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+    FC_REQUIRE(x && packed_weights && pyramid, "fc_build_from_fnet_tail: null pointer");
+    FC_REQUIRE(aligned16(x) && aligned16(pyramid), "fc_build_from_fnet_tail: pointers must be 16-byte aligned");
+    FC_REQUIRE(math == FC_MATH_TC_3XBF16 || math == FC_MATH_TC_BF16, "fc_build_from_fnet_tail: tensor-core math modes only (got %d)", math);
+    Pyramid pyr;
+    FC_REQUIRE(make_pyramid(pyr, B, H, W, num_levels), "fc_build_from_fnet_tail: bad geometry B=%d H=%d W=%d L=%d", B, H, W, num_levels);
+    const FeatSource src{x, packed_weights, C};
+    return tc_build(nullptr, nullptr, pyramid, pyr, D, H, W, vol_dtype, math, workspace, workspace_bytes,
+                    static_cast<cudaStream_t>(stream), &src);
 }

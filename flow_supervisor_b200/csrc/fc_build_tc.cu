@@ -28,7 +28,7 @@
 // (FLOWCORR_PROBE, results are garbage) exist only in a library compiled with -DFC_PROBES.
 #include <cstdlib>
 
-#include "fc_umma.cuh"
+#include "fc_build.cuh"
 
 namespace fc {
 
@@ -657,8 +657,9 @@ static int launch_tc(const CUtensorMap* maps, const TcStoreMaps& SM, const TcPar
     return FC_OK;
 }
 
+// feat != nullptr: the packed operands come from the fused fnet tail (fc_feat.cu) instead of the pack pre-pass
 int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr, int D, int H, int W,
-             int vol_dtype, int math, void* ws, size_t ws_bytes, cudaStream_t s) {
+             int vol_dtype, int math, void* ws, size_t ws_bytes, cudaStream_t s, const FeatSource* feat) {
     FC_REQUIRE(vol_dtype == FC_VOL_F32 || vol_dtype == FC_VOL_BF16, "fc_build: unknown vol_dtype %d", vol_dtype);
     const bool vb = vol_dtype == FC_VOL_BF16;
     const size_t es = vb ? 2 : 4;
@@ -687,7 +688,11 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
     // exact, bit-identical to scaling the product); otherwise the epilogue multiplies
     const float inv_sqrt_d = 1.0f / sqrtf((float)D);
     const bool fold_scale = (D == 4 || D == 16 || D == 64 || D == 256);
-    {
+    if (feat != nullptr) {
+        TcPacked dst{a_hi, three ? a_lo : nullptr, b_hi, three ? b_lo : nullptr, B, D, N, (int)NP, H, W, Wp,
+                     fold_scale ? inv_sqrt_d : 1.0f};
+        if (int e = fnet_tail_pack(*feat, dst, s)) return e;
+    } else {
         PackParams K{};
         K.src[0] = f1; K.src[1] = f2;
         K.hi[0] = a_hi; K.hi[1] = b_hi;

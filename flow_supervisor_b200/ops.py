@@ -304,3 +304,54 @@ def upsample_flow(flow: Tensor, mask: Tensor) -> Tensor:
 def _(flow, mask):
     B, _, H, W = flow.shape
     return flow.new_empty(B, 2, 8 * H, 8 * W, dtype=torch.float32)
+
+
+@custom_op("flowcorr::fnet_tail_prepare", mutates_args=())
+def fnet_tail_prepare(weight: Tensor, bias: Tensor) -> Tensor:
+    """Pre-pack the weights of the encoder's 1x1 output convolution (extractor.py:145 ``conv2``: (D, C, 1, 1) + (D,))
+    as K-major bf16 hi/lo + fp32 bias.  Once per model."""
+    _need_cuda(weight, bias)
+    w = _f32c(weight).reshape(weight.shape[0], -1)
+    b = _f32c(bias)
+    D, Cin = w.shape
+    lib = _lib.load()
+    with _on(w.device):
+        packed = torch.empty(lib.fc_fnet_tail_weights_bytes(Cin, D), dtype=torch.uint8, device=w.device)
+        _lib.check(lib.fc_fnet_tail_prepare(w.data_ptr(), b.data_ptr(), Cin, D, packed.data_ptr(), packed.numel(), _stream()),
+                   "fc_fnet_tail_prepare")
+    return packed
+
+
+@fnet_tail_prepare.register_fake
+def _(weight, bias):
+    D, Cin = weight.shape[0], weight.shape[1]
+    return weight.new_empty(D * Cin * 4 + D * 4, dtype=torch.uint8)
+
+
+def fnet_tail_supported(Cin: int, D: int, H: int, W: int) -> bool:
+    return bool(_lib.load().fc_fnet_tail_supported(Cin, D, H, W))
+
+
+@custom_op("flowcorr::build_from_fnet_tail", mutates_args=())
+def build_from_fnet_tail(x: Tensor, packed_weights: Tensor, out_dim: int, num_levels: int, math: int, vol_dtype: int) -> Tensor:
+    """CorrBlock.__init__ fused with the encoder's output convolution: x = (2B, C, H, W) activations in front of ``conv2``
+    (frames of image 1, then image 2) -> the pyramid of CorrBlock(conv2(x)[:B], conv2(x)[B:])."""
+    _need_cuda(x, packed_weights)
+    xc = _f32c(x)
+    F2, Cin, H, W = xc.shape
+    B = F2 // 2
+    lib = _lib.load()
+    with _on(xc.device):
+        pyr = torch.empty(pyramid_numel(B, H, W, num_levels), dtype=_VOL_TORCH[vol_dtype], device=xc.device)
+        ws_bytes = lib.fc_build_workspace_bytes(B, out_dim, H, W, num_levels, math)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=xc.device)
+        _lib.check(lib.fc_build_from_fnet_tail(xc.data_ptr(), packed_weights.data_ptr(), pyr.data_ptr(), B, Cin, out_dim, H, W,
+                                               num_levels, vol_dtype, math, ws.data_ptr(), ws_bytes, _stream()),
+                   "fc_build_from_fnet_tail")
+    return pyr
+
+
+@build_from_fnet_tail.register_fake
+def _(x, packed_weights, out_dim, num_levels, math, vol_dtype):
+    F2, _, H, W = x.shape
+    return x.new_empty(pyramid_numel(F2 // 2, H, W, num_levels), dtype=_VOL_TORCH[vol_dtype])

@@ -28,8 +28,12 @@ from .corr import CorrBlock, coords_grid
 
 class RaftRunner:
     def __init__(self, model, iters: int = 12, graph: bool = True, fused_upsample: bool = True,
-                 corr_block=CorrBlock):
+                 corr_block=CorrBlock, fused_fnet_tail: bool = False):
         self.model = model
+        # fused_fnet_tail (row f3): fnet's 1x1 output convolution runs inside the volume build (CorrBlock.from_fnet_tail)
+        # -- no fp32 feature maps, no pack launch.  Needs an encoder shaped like extractor.py's BasicEncoder.
+        self.fused_fnet_tail = bool(fused_fnet_tail)
+        self._packed_tail = None
         self.iters = int(iters)
         self.use_graph = bool(graph)
         self.fused_upsample = bool(fused_upsample)
@@ -45,9 +49,19 @@ class RaftRunner:
         hdim, cdim = m.hidden_dim, m.context_dim
         image1 = (2 * (image1 / 255.0) - 1.0).contiguous()                   # raft.py:89-93
         image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
-        with self._autocast():
-            fmap1, fmap2 = m.fnet([image1, image2])                          # raft.py:99-100
-        corr_fn = self.corr_block(fmap1.float(), fmap2.float(), radius=m.args.corr_radius)
+        if self.fused_fnet_tail and self._tail_ok(m.fnet):
+            f = m.fnet
+            with self._autocast():                                           # extractor.py:166-182 without conv2
+                x = torch.cat([image1, image2], dim=0)
+                x = f.layer3(f.layer2(f.layer1(f.relu1(f.norm1(f.conv1(x))))))
+            if self._packed_tail is None:
+                self._packed_tail = ops.fnet_tail_prepare(f.conv2.weight.detach(), f.conv2.bias.detach())
+            corr_fn = self.corr_block.from_fnet_tail(x.float(), self._packed_tail, f.conv2.out_channels,
+                                                     radius=m.args.corr_radius)
+        else:
+            with self._autocast():
+                fmap1, fmap2 = m.fnet([image1, image2])                      # raft.py:99-100
+            corr_fn = self.corr_block(fmap1.float(), fmap2.float(), radius=m.args.corr_radius)
         with self._autocast():
             cnet = m.cnet(image1)                                            # raft.py:110-114
             net, inp = torch.split(cnet, [hdim, cdim], dim=1)
@@ -77,6 +91,13 @@ class RaftRunner:
             flow_up = m.upsample_flow(flow_low, up_mask)
         return flow_low, flow_up
 
+    @staticmethod
+    def _tail_ok(fnet) -> bool:
+        conv2 = getattr(fnet, "conv2", None)
+        return (all(hasattr(fnet, n) for n in ("conv1", "norm1", "relu1", "layer1", "layer2", "layer3"))
+                and isinstance(conv2, torch.nn.Conv2d) and conv2.kernel_size == (1, 1) and conv2.bias is not None
+                and not (fnet.training and getattr(fnet, "dropout", None) is not None))
+
     # ------------------------------------------------------------------ graph capture / replay
     def _capture(self, image1, image2, flow_init):
         s_im1, s_im2 = torch.empty_like(image1), torch.empty_like(image2)
@@ -102,7 +123,7 @@ class RaftRunner:
         if not self.use_graph:
             return self.forward_eager(image1, image2, flow_init)
         key = (tuple(image1.shape), image1.dtype, image1.device, flow_init is not None, self.iters,
-               self.fused_upsample)
+               self.fused_upsample, self.fused_fnet_tail)
         if key not in self._graphs:
             self._graphs[key] = self._capture(image1, image2, flow_init)
         g, (s_im1, s_im2, s_init), (flow_low, flow_up) = self._graphs[key]

@@ -175,6 +175,22 @@ int fc_altcorr_bwd(const float* fmap1, const float* fmap2, const float* coords,
  * flow (B,2,H,W), mask (B,576,H,W), out (B,2,8H,8W), all fp32 contiguous.  One pass over the mask. */
 int fc_upsample_flow(const float* flow, const float* mask, float* out, int B, int H, int W, void* stream);
 
+/* Fused tail of the feature encoder (pytorch/core/extractor.py:145,184 `conv2`, the 1x1 output convolution of `fnet`;
+ * raft.py:99-107): the convolution runs on the tensor cores and its epilogue writes the build's packed K-major bf16
+ * hi/lo operands directly, so the fp32 feature maps and the pack pre-pass of fc_build do not exist.
+ *   fc_fnet_tail_prepare   once per model: weight (D, C) fp32 [+ bias (D), may be NULL] -> packed buffer of
+ *                          fc_fnet_tail_weights_bytes(C, D) bytes (128-byte aligned)
+ *   fc_build_from_fnet_tail  x (2B, C, H, W) fp32 = the activations in front of conv2, frames of image 1 then image 2
+ *                          (extractor.py:170-172 concatenates them) -> the pyramid, exactly as fc_build would produce it
+ *                          from fmap = conv2(x).  Tensor-core math modes only; workspace = fc_build_workspace_bytes.
+ *   fc_fnet_tail_supported C in {64, 128}, D % 64 == 0, D <= 256, H*W % 4 == 0 (else run conv2 + fc_build). */
+size_t fc_fnet_tail_weights_bytes(int C, int D);
+int fc_fnet_tail_supported(int C, int D, int H, int W);
+int fc_fnet_tail_prepare(const float* weight, const float* bias, int C, int D, void* packed, size_t packed_bytes, void* stream);
+int fc_build_from_fnet_tail(const float* x, const void* packed_weights, void* pyramid,
+                            int B, int C, int D, int H, int W, int num_levels, int vol_dtype, int math,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

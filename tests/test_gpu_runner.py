@@ -98,3 +98,52 @@ def test_runner_flow_init_and_mixed_precision(core):
             low_p, up_p = model(im1, im2, iters=6, flow_init=init, test_mode=True)
         low_g, up_g = fsb.RaftRunner(model, iters=6, graph=True, fused_upsample=False)(im1, im2, flow_init=init)
     assert torch.equal(low_g, low_p) and torch.equal(up_g, up_p)
+
+
+@pytest.mark.parametrize("shape,cin,dout", [((2, 46, 62), 128, 256), ((1, 55, 128), 128, 256), ((1, 24, 40), 64, 128),
+                                            ((2, 47, 156), 128, 256), ((1, 17, 20), 128, 64)])
+@pytest.mark.parametrize("math", ["3xbf16", "bf16"])
+def test_fused_fnet_tail_builds_the_same_pyramid(shape, cin, dout, math):
+    """fc_build_from_fnet_tail (the encoder's 1x1 output convolution inside the volume build, row f3) against
+    conv2 in fp32 followed by the ordinary build: every level within 1e-4 of the volume's scale in the parity mode
+    (the convolution itself carries the 3xbf16 split), pads exactly zero."""
+    import flow_supervisor_b200 as fsb
+    B, H, W = shape
+    g = torch.Generator().manual_seed(21)
+    x = torch.relu(torch.randn(2 * B, cin, H, W, generator=g)).cuda()           # post-ReLU activations, like layer3's output
+    conv2 = torch.nn.Conv2d(cin, dout, kernel_size=1).cuda()
+    with torch.no_grad():
+        conv2.weight.copy_(torch.randn(dout, cin, 1, 1, generator=g).cuda() * (2.0 / cin) ** 0.5)
+        conv2.bias.copy_(0.1 * torch.randn(dout, generator=g).cuda())
+    packed = fsb.ops.fnet_tail_prepare(conv2.weight.detach(), conv2.bias.detach())
+    old = fsb.CorrBlock.math
+    fsb.CorrBlock.math = math
+    try:
+        with rm.strict_fp32(), torch.no_grad():
+            f1, f2 = torch.split(conv2(x), [B, B], dim=0)
+            ref = fsb.CorrBlock(f1.contiguous(), f2.contiguous())
+            fused = fsb.CorrBlock.from_fnet_tail(x, packed, dout)
+    finally:
+        fsb.CorrBlock.math = old
+    tol = 1e-4 if math == "3xbf16" else 2e-2
+    la = fsb.ops.level_padded(ref._state.pyramid, B, H, W, 4)
+    lb = fsb.ops.level_padded(fused._state.pyramid, B, H, W, 4)
+    scale = float(la[0].abs().max())
+    for l, (a, b) in enumerate(zip(la, lb)):
+        assert float((a - b).abs().max()) <= tol * scale, (l, float((a - b).abs().max()) / scale)
+        assert not b[:, (H >> l):, :].any() and not b[:, :, (W >> l):].any()
+    c = fsb.coords_grid(B, H, W, device="cuda") + 3.0 * torch.randn(B, 2, H, W, generator=g).cuda()
+    assert float((fused(c) - ref(c)).abs().max()) <= tol * scale
+
+
+def test_runner_fused_fnet_tail_matches_reference_forward(core):
+    import flow_supervisor_b200 as fsb
+    torch.manual_seed(1234)
+    model = core.raft.RAFT(rm.raft_args()).eval().cuda()
+    im1, im2 = (t.cuda() for t in rm.synth_pair(440, 1024, seed=13, batch=2))
+    with rm.strict_fp32(), torch.no_grad():
+        _, up_r = model(im1, im2, iters=12, test_mode=True)
+        low_e, up_e = fsb.RaftRunner(model, iters=12, graph=False, fused_fnet_tail=True)(im1, im2)
+        low_g, up_g = fsb.RaftRunner(model, iters=12, graph=True, fused_fnet_tail=True)(im1, im2)
+    assert torch.equal(low_g, low_e) and torch.equal(up_g, up_e)
+    assert rm.epe(up_g, up_r) <= 0.01, rm.epe(up_g, up_r)
