@@ -88,6 +88,7 @@ def collect(reps=5, ref_kernel=True, model=True):
     row_backward(6, 54, 128, reps)
     row_ondemand(2, 136, 240, reps)
     row_bf16_volume(8, 55, 128, reps)
+    row_fnet_tail(8, 55, 128, reps)
     if model:
         row_model(8, 436, 1024, max(2, reps // 2))
     return list(ROWS)
@@ -118,6 +119,32 @@ def row_bf16_volume(B, H, W, reps, iters=12):
     finally:
         fsb.CorrBlock.math, fsb.CorrBlock.volume = keep
     emit(row="bf16 volume mode (build + lookups), stated tolerance 2^-8 of max / 0.05 px EPE", geometry=f"B={B} {H}x{W}", **out)
+
+
+def row_fnet_tail(B, H, W, reps, cin=128):
+    """Row f3: fnet's 1x1 output convolution (128 -> 256) fused into the volume build.  'separate' = torch conv2d
+    (cuDNN, torch default math) + fc_build (pack + GEMM); 'fused' = fc_build_from_fnet_tail (conv on the tensor cores writing
+    the packed operands) -- same pyramid."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.relu(torch.randn(2 * B, cin, H, W, generator=g)).cuda()
+    conv2 = torch.nn.Conv2d(cin, D, kernel_size=1).cuda()
+    packed = ops.fnet_tail_prepare(conv2.weight.detach(), conv2.bias.detach())
+    keep = fsb.CorrBlock.math
+    fsb.CorrBlock.math = "3xbf16"
+    try:
+        with torch.no_grad():
+            def separate():
+                f1, f2 = torch.split(conv2(x), [B, B], dim=0)
+                return fsb.CorrBlock(f1.float(), f2.float(), L, R)
+            ms_conv = timed(lambda: conv2(x), reps, inner=4)
+            ms_sep = timed(separate, reps)
+            ms_fused = timed(lambda: fsb.CorrBlock.from_fnet_tail(x, packed, D, L, R), reps)
+            a, b = separate()._state.pyramid, fsb.CorrBlock.from_fnet_tail(x, packed, D, L, R)._state.pyramid
+            diff = float((a - b).abs().max() / a.abs().max())
+    finally:
+        fsb.CorrBlock.math = keep
+    emit(row="f3 fnet tail fused into the build (conv2 1x1 128->256 + build)", geometry=f"B={B} {H}x{W}", conv2_cudnn_ms=ms_conv,
+         separate_ms=ms_sep, fused_ms=ms_fused, saved_ms=ms_sep - ms_fused, max_rel_diff_vs_separate_tf32_conv=diff)
 
 
 def row_model(B, Himg, Wimg, reps, iters=12):
@@ -154,11 +181,13 @@ def row_model(B, Himg, Wimg, reps, iters=12):
         res["runner_eager_ms"] = timed(lambda: eager(im1, im2), reps, warm=2)
         graphed = fsb.RaftRunner(model, iters=iters, graph=True)
         res["runner_graph_ms"] = timed(lambda: graphed(im1, im2), reps, warm=2)
+        tail = fsb.RaftRunner(model, iters=iters, graph=True, fused_fnet_tail=True)
+        res["runner_graph_fused_tail_ms"] = timed(lambda: tail(im1, im2), reps, warm=2)
     emit(row="RAFT forward pairs/s @436x1024, 12 iterations: unmodified reference model, same GPU",
          geometry=f"B={B} {Hp}x{Wp} px", conv_math="torch defaults (cuDNN TF32 convolutions)", **res,
          pairs_per_s={k[:-3]: B / v * 1e3 for k, v in res.items()},
          speedup_vs_reference_block={k[:-3]: res["reference_block_ms"] / v for k, v in res.items()})
-    del model, eager, graphed
+    del model, eager, graphed, tail
     torch.cuda.empty_cache()
 
 
