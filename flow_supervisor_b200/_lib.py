@@ -42,6 +42,10 @@ SIGNATURES = {
     "fc_altcorr_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "fc_altcorr_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "fc_upsample_flow": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "fc_convc1_weights_bytes": (_z, []),
+    "fc_lookup_convc1_supported": (_i, [_i, _i, _i]),
+    "fc_convc1_prepare": (_i, [_p, _p, _p, _z, _p]),
+    "fc_lookup_convc1_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "fc_fnet_tail_weights_bytes": (_z, [_i, _i]),
     "fc_fnet_tail_supported": (_i, [_i, _i, _i, _i]),
     "fc_fnet_tail_prepare": (_i, [_p, _p, _i, _i, _p, _z, _p]),

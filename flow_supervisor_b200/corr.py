@@ -182,6 +182,15 @@ class CorrBlock:
             return _Lookup.apply(self._token, coords.detach(), st)
         return _lookup_fn()(st.pyramid, coords.detach(), st.L, st.radius, st.coord)
 
+    def lookup_convc1(self, coords, packed_weights):
+        """Inference-only: ``relu(convc1(self(coords)))`` (update.py:90) in one kernel, the 324-channel tensor never written
+        (SURVEY.md section 8 row f1).  ``packed_weights`` = ops.convc1_prepare(convc1.weight, convc1.bias)."""
+        st = self._state
+        if not _lib.load().fc_lookup_convc1_supported(st.L, st.radius, 256):
+            raise RuntimeError(f"lookup_convc1 is built for num_levels = 4, radius = 4 (got {st.L}, {st.radius})")
+        fn = ops.lookup_convc1 if torch.compiler.is_compiling() else ops.lookup_convc1_direct
+        return fn(st.pyramid, coords.detach(), packed_weights, st.L, st.radius, st.coord)
+
     def lookup_debug(self, coords):
         """(out, x0, y0, corner_mask): the lookup plus its integer part, for parity tests."""
         st = self._state

@@ -355,3 +355,49 @@ def build_from_fnet_tail(x: Tensor, packed_weights: Tensor, out_dim: int, num_le
 def _(x, packed_weights, out_dim, num_levels, math, vol_dtype):
     F2, _, H, W = x.shape
     return x.new_empty(pyramid_numel(F2 // 2, H, W, num_levels), dtype=_VOL_TORCH[vol_dtype])
+
+
+@custom_op("flowcorr::convc1_prepare", mutates_args=())
+def convc1_prepare(weight: Tensor, bias: Tensor) -> Tensor:
+    """Pre-pack the motion encoder's first convolution (update.py:83 ``convc1``: (256, 324, 1, 1) + (256,)) for
+    lookup_convc1.  Once per model."""
+    _need_cuda(weight, bias)
+    w = _f32c(weight).reshape(weight.shape[0], -1)
+    b = _f32c(bias)
+    if tuple(w.shape) != (256, 324):
+        raise ValueError(f"convc1 weight must be (256, 324[, 1, 1]); got {tuple(weight.shape)}")
+    lib = _lib.load()
+    with _on(w.device):
+        packed = torch.empty(lib.fc_convc1_weights_bytes(), dtype=torch.uint8, device=w.device)
+        _lib.check(lib.fc_convc1_prepare(w.data_ptr(), b.data_ptr(), packed.data_ptr(), packed.numel(), _stream()),
+                   "fc_convc1_prepare")
+    return packed
+
+
+@convc1_prepare.register_fake
+def _(weight, bias):
+    return weight.new_empty(256 * 384 * 4 + 256 * 4, dtype=torch.uint8)
+
+
+def lookup_convc1_direct(pyramid: Tensor, coords: Tensor, packed_weights: Tensor, num_levels: int, radius: int,
+                         coord_mode: int) -> Tensor:
+    """relu(convc1(CorrBlock.__call__(coords))) in one kernel (update.py:90 after raft.py:124): -> (B, 256, H, W)."""
+    _need_cuda(pyramid, coords, packed_weights)
+    c = _f32c(coords)
+    B, _, H, W = c.shape
+    vol_dtype = _lib.VOL_F32 if pyramid.dtype == torch.float32 else _lib.VOL_BF16
+    with _on(c.device):
+        out = torch.empty(B, 256, H, W, dtype=torch.float32, device=c.device)
+        _lib.check(_lib.load().fc_lookup_convc1_fwd(pyramid.data_ptr(), c.data_ptr(), packed_weights.data_ptr(), out.data_ptr(),
+                                                    B, H, W, num_levels, radius, vol_dtype, coord_mode, _stream()),
+                   "fc_lookup_convc1_fwd")
+    return out
+
+
+lookup_convc1 = custom_op("flowcorr::lookup_convc1", mutates_args=())(lookup_convc1_direct)
+
+
+@lookup_convc1.register_fake
+def _(pyramid, coords, packed_weights, num_levels, radius, coord_mode):
+    B, _, H, W = coords.shape
+    return coords.new_empty(B, 256, H, W, dtype=torch.float32)

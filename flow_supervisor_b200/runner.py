@@ -28,8 +28,12 @@ from .corr import CorrBlock, coords_grid
 
 class RaftRunner:
     def __init__(self, model, iters: int = 12, graph: bool = True, fused_upsample: bool = True,
-                 corr_block=CorrBlock, fused_fnet_tail: bool = False):
+                 corr_block=CorrBlock, fused_fnet_tail: bool = False, fused_convc1: bool = False):
         self.model = model
+        # fused_convc1 (row f1): the lookup and the motion encoder's first 1x1 convolution + ReLU run as one kernel
+        # (CorrBlock.lookup_convc1); the rest of the update block runs through the model's own sub-modules.
+        self.fused_convc1 = bool(fused_convc1)
+        self._packed_convc1 = None
         # fused_fnet_tail (row f3): fnet's 1x1 output convolution runs inside the volume build (CorrBlock.from_fnet_tail)
         # -- no fp32 feature maps, no pack launch.  Needs an encoder shaped like extractor.py's BasicEncoder.
         self.fused_fnet_tail = bool(fused_fnet_tail)
@@ -73,14 +77,23 @@ class RaftRunner:
         if flow_init is not None:
             coords1 = coords1 + flow_init
         up_mask = None
+        fuse_c1 = self.fused_convc1 and attention is None and self._convc1_ok(m.update_block, corr_fn)
+        if fuse_c1 and self._packed_convc1 is None:
+            c1 = m.update_block.encoder.convc1
+            self._packed_convc1 = ops.convc1_prepare(c1.weight.detach(), c1.bias.detach())
         for _ in range(self.iters):                                          # raft.py:122-132
-            corr = corr_fn(coords1)
             flow = coords1 - coords0
-            with self._autocast():
-                if attention is None:
-                    net, up_mask, delta = m.update_block(net, inp, corr, flow)
-                else:
-                    net, up_mask, delta = m.update_block(net, inp, corr, flow, attention)
+            if fuse_c1:
+                cor = corr_fn.lookup_convc1(coords1, self._packed_convc1)    # = relu(convc1(corr_fn(coords1)))
+                with self._autocast():
+                    net, up_mask, delta = self._update_after_convc1(m.update_block, net, inp, cor, flow)
+            else:
+                corr = corr_fn(coords1)
+                with self._autocast():
+                    if attention is None:
+                        net, up_mask, delta = m.update_block(net, inp, corr, flow)
+                    else:
+                        net, up_mask, delta = m.update_block(net, inp, corr, flow, attention)
             coords1 = coords1 + delta
         flow_low = coords1 - coords0
         if up_mask is None:                                                  # small model: bilinear x8 (utils.py:80-82)
@@ -90,6 +103,28 @@ class RaftRunner:
         else:
             flow_up = m.upsample_flow(flow_low, up_mask)
         return flow_low, flow_up
+
+    @staticmethod
+    def _convc1_ok(ub, corr_fn) -> bool:
+        enc = getattr(ub, "encoder", None)
+        c1 = getattr(enc, "convc1", None)
+        return (isinstance(c1, torch.nn.Conv2d) and tuple(c1.weight.shape) == (256, 324, 1, 1) and c1.bias is not None
+                and all(hasattr(enc, n) for n in ("convc2", "convf1", "convf2", "conv"))
+                and all(hasattr(ub, n) for n in ("gru", "flow_head", "mask")) and hasattr(corr_fn, "lookup_convc1"))
+
+    @staticmethod
+    def _update_after_convc1(ub, net, inp, cor, flow):
+        """BasicUpdateBlock.forward (update.py:127-136) with BasicMotionEncoder.forward (update.py:89-98) entered after
+        its first convolution + ReLU."""
+        relu = torch.nn.functional.relu
+        enc = ub.encoder
+        cor = relu(enc.convc2(cor))
+        flo = relu(enc.convf2(relu(enc.convf1(flow))))
+        out = relu(enc.conv(torch.cat([cor, flo], dim=1)))
+        motion = torch.cat([out, flow], dim=1)
+        net = ub.gru(net, torch.cat([inp, motion], dim=1))
+        delta = ub.flow_head(net)
+        return net, .25 * ub.mask(net), delta
 
     @staticmethod
     def _tail_ok(fnet) -> bool:
@@ -123,7 +158,7 @@ class RaftRunner:
         if not self.use_graph:
             return self.forward_eager(image1, image2, flow_init)
         key = (tuple(image1.shape), image1.dtype, image1.device, flow_init is not None, self.iters,
-               self.fused_upsample, self.fused_fnet_tail)
+               self.fused_upsample, self.fused_fnet_tail, self.fused_convc1)
         if key not in self._graphs:
             self._graphs[key] = self._capture(image1, image2, flow_init)
         g, (s_im1, s_im2, s_init), (flow_low, flow_up) = self._graphs[key]

@@ -175,6 +175,18 @@ int fc_altcorr_bwd(const float* fmap1, const float* fmap2, const float* coords,
  * flow (B,2,H,W), mask (B,576,H,W), out (B,2,8H,8W), all fp32 contiguous.  One pass over the mask. */
 int fc_upsample_flow(const float* flow, const float* mask, float* out, int B, int H, int W, void* stream);
 
+/* Lookup fused into the motion encoder's first convolution (pytorch/core/update.py:83,90: `F.relu(self.convc1(corr))`
+ * applied to `corr = corr_fn(coords1)`, raft.py:124): out[b,co,p] = relu(bias[co] + sum_k W[co,k] * lookup[b,k,p]).
+ * The (B, 324, H, W) tensor never reaches HBM; the weights live in tensor memory for the whole kernel.
+ *   fc_convc1_prepare     once per model: weight (256, 324) fp32 [+ bias (256), may be NULL] -> fc_convc1_weights_bytes() bytes
+ *   fc_lookup_convc1_fwd  pyramid + coords (B, 2, H, W) -> out (B, 256, H, W) fp32
+ *   fc_lookup_convc1_supported  num_levels == 4, radius == 4, 256 output channels (RAFT / GMA basic models). */
+size_t fc_convc1_weights_bytes(void);
+int fc_lookup_convc1_supported(int num_levels, int radius, int out_channels);
+int fc_convc1_prepare(const float* weight, const float* bias, void* packed, size_t packed_bytes, void* stream);
+int fc_lookup_convc1_fwd(const void* pyramid, const float* coords, const void* packed_weights, float* out,
+                         int B, int H, int W, int num_levels, int radius, int vol_dtype, int coord_mode, void* stream);
+
 /* Fused tail of the feature encoder (pytorch/core/extractor.py:145,184 `conv2`, the 1x1 output convolution of `fnet`;
  * raft.py:99-107): the convolution runs on the tensor cores and its epilogue writes the build's packed K-major bf16
  * hi/lo operands directly, so the fp32 feature maps and the pack pre-pass of fc_build do not exist.

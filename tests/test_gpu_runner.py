@@ -147,3 +147,52 @@ def test_runner_fused_fnet_tail_matches_reference_forward(core):
         low_g, up_g = fsb.RaftRunner(model, iters=12, graph=True, fused_fnet_tail=True)(im1, im2)
     assert torch.equal(low_g, low_e) and torch.equal(up_g, up_e)
     assert rm.epe(up_g, up_r) <= 0.01, rm.epe(up_g, up_r)
+
+
+@pytest.mark.parametrize("shape,law", [((2, 46, 62), "random"), ((1, 55, 128), "random"), ((1, 55, 128), "lattice"),
+                                       ((2, 47, 156), "border"), ((1, 24, 40), "random"), ((3, 17, 21), "random")])
+@pytest.mark.parametrize("volume", ["f32", "bf16"])
+def test_lookup_convc1_matches_relu_conv1x1_of_the_lookup(shape, law, volume):
+    """fc_lookup_convc1_fwd (row f1) against relu(conv1x1(lookup)) in fp32: <= 1e-4 of the output's max magnitude
+    (three-pass bf16 split of weights and looked-up values, fp32 accumulate), exact zeros where ReLU clips."""
+    import flow_supervisor_b200 as fsb
+    B, H, W = shape
+    g = torch.Generator().manual_seed(31)
+    f1 = (1.57 * torch.randn(B, 256, H, W, generator=g)).cuda()
+    f2 = (1.57 * torch.randn(B, 256, H, W, generator=g)).cuda()
+    grid = fsb.coords_grid(B, H, W)
+    if law == "random":
+        c = grid + 4.0 * torch.randn(B, 2, H, W, generator=g)
+    elif law == "lattice":
+        c = grid + torch.randint(-3, 4, (B, 2, H, W), generator=g).float()
+    else:
+        c = grid + 40.0 * torch.randn(B, 2, H, W, generator=g)
+        c[0, :, 0, 0] = float("nan")
+    c = c.cuda()
+    conv = torch.nn.Conv2d(324, 256, 1).cuda()
+    packed = fsb.ops.convc1_prepare(conv.weight.detach(), conv.bias.detach())
+    old = fsb.CorrBlock.volume
+    fsb.CorrBlock.volume = volume
+    try:
+        with rm.strict_fp32(), torch.no_grad():
+            blk = fsb.CorrBlock(f1, f2)
+            ref = torch.relu(conv(blk(c)))
+            out = blk.lookup_convc1(c, packed)
+    finally:
+        fsb.CorrBlock.volume = old
+    assert out.shape == ref.shape and out.is_contiguous()
+    assert float((out - ref).abs().max()) <= 1e-4 * float(ref.abs().max()), float((out - ref).abs().max()) / float(ref.abs().max())
+    assert float(((out == 0) != (ref == 0)).float().mean()) < 1e-3
+
+
+def test_runner_fused_convc1_matches_reference_forward(core):
+    import flow_supervisor_b200 as fsb
+    torch.manual_seed(1234)
+    model = core.raft.RAFT(rm.raft_args()).eval().cuda()
+    im1, im2 = (t.cuda() for t in rm.synth_pair(440, 1024, seed=14, batch=2))
+    with rm.strict_fp32(), torch.no_grad():
+        _, up_r = model(im1, im2, iters=12, test_mode=True)
+        low_e, up_e = fsb.RaftRunner(model, iters=12, graph=False, fused_convc1=True)(im1, im2)
+        low_g, up_g = fsb.RaftRunner(model, iters=12, graph=True, fused_convc1=True, fused_fnet_tail=True)(im1, im2)
+    assert rm.epe(up_e, up_r) <= 0.01, rm.epe(up_e, up_r)
+    assert rm.epe(up_g, up_r) <= 0.01, rm.epe(up_g, up_r)
