@@ -16,17 +16,34 @@
 // 32 queries x 384 slots, bf16 hi and lo, K-major SWIZZLE_128B written by the consumers themselves).
 // fp32 parity through the same three-pass split as the volume build: W_hi*V_hi + W_lo*V_hi + W_hi*V_lo, fp32 accumulate.
 //
-// Warps (384 threads per CTA): 0 = footprint producer (TMA), 1 = TMEM allocator + MMA issuer (leader CTA), 2-5 = weights
-// -> TMEM once, then epilogue (TMEM -> + bias -> ReLU -> (B, 256, H, W)), 6-11 = two lookup consumer groups.
+// Warps: 0 = footprint producer (TMA), 1 = TMEM allocator + MMA issuer (leader CTA), 2-5 = weights -> TMEM once, then
+// epilogue (TMEM -> + bias -> ReLU -> (B, 256, H, W)), 6.. = lookup consumer groups of three warps.
 #include "fc_lookup_fwd.cuh"
 #include "fc_umma.cuh"
 
 namespace fc {
 
 constexpr int LC_RADIUS = 4, LC_R = 2 * LC_RADIUS + 1, LC_L = 4;
-constexpr int LC_STAGES = 3;                              // footprint ring depth (LfShared holds 6 barriers; 3 in use)
-constexpr int LC_GROUPS = 2;                              // consumer groups of LF_GWARPS warps
-constexpr int LC_THREADS = 32 * (1 + 1 + 4 + LC_GROUPS * LF_GWARPS);      // 384
+#ifndef FC_LC_STAGES
+#define FC_LC_STAGES 3
+#endif
+#ifndef FC_LC_GROUPS
+#define FC_LC_GROUPS 3
+#endif
+#ifndef FC_LC_BBUFS
+#define FC_LC_BBUFS 2
+#endif
+constexpr int LC_STAGES = FC_LC_STAGES;                   // footprint ring depth (LfShared holds 6 barriers)
+constexpr int LC_GROUPS = FC_LC_GROUPS;                   // consumer groups of LF_GWARPS warps
+#ifndef FC_LC_PRODUCERS
+#define FC_LC_PRODUCERS 1
+#endif
+constexpr int LC_PRODUCERS = FC_LC_PRODUCERS;             // footprint producer warps: warp 0 and, with 2, the last warp
+constexpr int LC_NB = FC_LC_BBUFS;
+// a ring stage must always be filled by the same producer and drained by the same consumer group: an mbarrier parity wait
+// may run at most one phase behind the barrier it waits on (a waiter two phases late sees a stale "completed")
+static_assert(LC_STAGES % LC_GROUPS == 0 && LC_STAGES % LC_PRODUCERS == 0, "stage ownership");                        // B-operand buffers (1: a pair-tile's values wait in registers for the previous MMAs)
+constexpr int LC_THREADS = 32 * (1 + 1 + 4 + LC_GROUPS * LF_GWARPS + (LC_PRODUCERS - 1));
 constexpr int LC_KL = 96;                                 // K slots per level: 9 x 10 = 90 used
 constexpr int LC_K = LC_L * LC_KL;                        // 384
 constexpr int LC_COUT = 256;
@@ -82,10 +99,9 @@ __device__ __forceinline__ LfQuery lc_query(const LookupParams& P, const ConvPar
     q.cx = 0.f; q.cy = 0.f; q.near_ = false;
     if (q.live) {
         const float* c = P.coords + (long long)q.b * 2 * P.N + q.p;
-        q.cx = __ldg(c);
+        q.cx = __ldg(c);                     // raw: scaled by lf_finish_query, so a prefetch does not stall on the load
         q.cy = __ldg(c + P.N);
     }
-    lf_finish_query(P, q);
     return q;
 }
 
@@ -95,15 +111,16 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
     constexpr int LF_STAGE_BYTES = lf_stage_bytes(VB);
     extern __shared__ __align__(1024) uint8_t lc_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lc_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* bbuf = smem;                                               // [2][hi plane | lo plane]
-    const uint32_t win = smem_u32(smem + 2 * LC_BBUF);                  // [stage][query][window]
-    LfShared& sh = *reinterpret_cast<LfShared*>(smem + 2 * LC_BBUF + LC_STAGES * LF_STAGE_BYTES);
+    uint8_t* bbuf = smem;                                               // [LC_NB][hi plane | lo plane]
+    const uint32_t win = smem_u32(smem + LC_NB * LC_BBUF);              // [stage][query][window]
+    LfShared& sh = *reinterpret_cast<LfShared*>(smem + LC_NB * LC_BBUF + LC_STAGES * LF_STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(&sh + 1);
-    uint64_t* b_full = bars;             // 2, used in the leader: 2 CTAs x 4 levels x 3 consumer warps = 24 arrivals
-    uint64_t* b_empty = bars + 2;        // 2, one multicast commit
-    uint64_t* t_full = bars + 4;         // 2, one multicast commit
-    uint64_t* t_empty = bars + 6;        // 2, used in the leader: 2 CTAs x 4 epilogue warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* b_part = bars;             // 2, per CTA: its 4 levels x 3 consumer warps = 12 arrivals (CTA scope: cheap)
+    uint64_t* b_peer = bars + 2;         // 2, used in the leader: ONE cluster-scope release per pair-tile from the peer's relay
+    uint64_t* b_empty = bars + 4;        // 2, one multicast commit
+    uint64_t* t_full = bars + 6;         // 2, one multicast commit
+    uint64_t* t_empty = bars + 8;        // 2, used in the leader: 2 CTAs x 4 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -114,7 +131,7 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
     if (threadIdx.x == 0) {
         for (int i = 0; i < LC_STAGES; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], LF_GWARPS); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(b_full + i, 2 * LC_L * LF_GWARPS); mbar_init(b_empty + i, 1);
+            mbar_init(b_part + i, LC_L * LF_GWARPS); mbar_init(b_peer + i, 1); mbar_init(b_empty + i, 1);
             mbar_init(t_full + i, 1); mbar_init(t_empty + i, 2 * 4);
         }
         mbar_fence_init();
@@ -123,58 +140,83 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
     }
-    // the B operand starts out as zeros: pad slots (y-offset 9 of every x-offset, slots 90..95 of every level) are never
-    // written again and must not hold NaN patterns (their weights are zero)
-    for (int i = threadIdx.x; i < 2 * LC_BBUF / 16; i += LC_THREADS) reinterpret_cast<uint4*>(bbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
-    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 2 && warp < 6) {
-        // weights of this CTA's 128 output channels -> tensor memory: lane = channel, 32-bit column = two consecutive slots
-        const int quarter = warp & 3;
-        const int co = (int)rank * 128 + quarter * 32 + lane;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    // weights of this CTA's 128 output channels -> tensor memory (lane = channel, 32-bit column = two consecutive slots).
+    // A thread needs its channel's whole row (768 B per plane): read straight from global that is one sector per lane and
+    // load instruction (all 148 CTAs hammering the same 393 KB: ~40 us of prologue, ncu long-scoreboard 8.6 per issue), so
+    // each plane is first copied coalesced into the (still idle) footprint ring at a conflict-free row pitch.
+    {
+        constexpr int WPITCH = LC_K * 2 + 16;                              // 784 B: rows 16 B apart modulo 128 B
+        static_assert(128 * WPITCH <= LC_NB * LC_BBUF + LC_STAGES * lf_stage_bytes(1), "weight staging fits B buffers + ring");
+        uint8_t* stagew = smem;
         for (int plane = 0; plane < 2; ++plane) {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>((plane ? C.w_lo : C.w_hi) + (long long)co * LC_K);
-            for (int part = 0; part < LC_K / 64; ++part) {
-                uint32_t v[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __ldg(src + part * 32 + i);
-                tmem_st32(lane_addr + (plane ? LC_ALO : LC_AHI) + (uint32_t)(part * 32), v);
+            const uint4* src = reinterpret_cast<const uint4*>((plane ? C.w_lo : C.w_hi) + (long long)rank * 128 * LC_K);
+            for (int i = threadIdx.x; i < 128 * (LC_K * 2 / 16); i += LC_THREADS) {
+                const int row = i / (LC_K * 2 / 16), ch = i - row * (LC_K * 2 / 16);
+                *reinterpret_cast<uint4*>(stagew + row * WPITCH + ch * 16) = __ldg(src + i);
             }
+            __syncthreads();
+            if (warp >= 2 && warp < 6) {
+                const int quarter = warp & 3;
+                const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+                const uint4* rowp = reinterpret_cast<const uint4*>(stagew + (quarter * 32 + lane) * WPITCH);
+                for (int part = 0; part < LC_K / 64; ++part) {
+                    uint32_t v[32];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint4 t = rowp[part * 8 + i];
+                        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+                    }
+                    tmem_st32(lane_addr + (plane ? LC_ALO : LC_AHI) + (uint32_t)(part * 32), v);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+            }
+            __syncthreads();
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
     }
+    // the B operand starts out as zeros: pad slots (y-offset 9 of every x-offset, slots 90..95 of every level) are never
+    // written again and must not hold NaN patterns (their weights are zero)
+    for (int i = threadIdx.x; i < LC_NB * LC_BBUF / 16; i += LC_THREADS) reinterpret_cast<uint4*>(bbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                  // both CTAs: barriers initialised, weights in place
     tc_fence_after();
 
-    if (warp == 0) {
-        // ================= footprint producer =================
-        for (int i = 0, k = 0; i < n_mine; ++i) {
-            const int T = pair + i * n_pairs;
-            for (int l = 0; l < LC_L; ++l, ++k) {
-                const LfQuery q = lc_query(P, C, T, l, (int)rank, lane);
-                lf_produce<LC_RADIUS, CM, VB>(P, M, sh, win, q, k % LC_STAGES, lane, 0, k >= LC_STAGES,
-                                              ((uint32_t)(k / LC_STAGES) & 1u) ^ 1u);
-            }
+    constexpr int LAST_WARP = LC_THREADS / 32 - 1;
+    if (warp == 0 || (LC_PRODUCERS == 2 && warp == LAST_WARP)) {
+        // ================= footprint producer(s): lookup tiles pw, pw + LC_PRODUCERS, ... =================
+        const int n_k = n_mine * LC_L, pw = warp == 0 ? 0 : 1;
+        LfQuery q{};
+        if (pw < n_k) q = lc_query(P, C, pair + (pw / LC_L) * n_pairs, pw % LC_L, (int)rank, lane);
+        for (int k = pw; k < n_k; k += LC_PRODUCERS) {
+            LfQuery qn = q;
+            const int k1 = k + LC_PRODUCERS;
+            if (k1 < n_k) qn = lc_query(P, C, pair + (k1 / LC_L) * n_pairs, k1 % LC_L, (int)rank, lane);   // coordinates one turn ahead
+            lf_finish_query(P, q);
+            lf_produce<LC_RADIUS, CM, VB>(P, M, sh, win, q, k % LC_STAGES, lane, 0, k >= LC_STAGES,
+                                          ((uint32_t)(k / LC_STAGES) & 1u) ^ 1u);
+            q = qn;
         }
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA) =================
         if (lane == 0 && leader) {
             const uint32_t idesc = umma_idesc_bf16(2 * 128, LC_QT);
             for (int i = 0; i < n_mine; ++i) {
-                const int bb = i & 1;
-                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-                mbar_wait_cluster(b_full + bb, ph);
-                mbar_wait_cluster(t_empty + bb, ph ^ 1u);
+                const int bb = i % LC_NB, db = i & 1;
+                mbar_wait(b_part + bb, (uint32_t)(i / LC_NB) & 1u);             // this CTA's half of the B operand
+                mbar_wait_cluster(b_peer + bb, (uint32_t)(i / LC_NB) & 1u);     // the peer's half
+                mbar_wait_cluster(t_empty + db, ((uint32_t)(i >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t d_addr = tmem_base + (bb ? LC_D1 : LC_D0);
+                const uint32_t d_addr = tmem_base + (db ? LC_D1 : LC_D0);
                 const uint32_t bh = smem_u32(bbuf + bb * LC_BBUF), bl = bh + LC_BPLANE;
+#ifdef FC_LC_NOMMA
+                if (false)
+#endif
 #pragma unroll 4
                 for (int ks = 0; ks < LC_K / 16; ++ks) {
                     const uint32_t boff = (uint32_t)((ks >> 2) * (QT * 128) + (ks & 3) * 32);
@@ -185,7 +227,16 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
                     umma2_ts_bf16(d_addr, ah, dl, idesc, 1u);
                 }
                 umma2_commit(b_empty + bb);              // both CTAs: this B buffer may be overwritten
-                umma2_commit(t_full + bb);               // both CTAs: accumulator complete
+                umma2_commit(t_full + db);               // both CTAs: accumulator complete
+            }
+        } else if (lane == 0) {
+            // relay of the peer CTA: its consumers arrive on a local barrier; ONE release at cluster scope per pair-tile tells
+            // the leader that this CTA's half of the B operand is written (a cluster-scope release per consumer warp and
+            // lookup tile cost the consumers more than the lookups themselves)
+            for (int i = 0; i < n_mine; ++i) {
+                const int bb = i % LC_NB;
+                mbar_wait(b_part + bb, (uint32_t)(i / LC_NB) & 1u);
+                mbar_arrive_remote_release(b_peer + bb, 0);
             }
         }
     } else if (warp < 6) {
@@ -196,7 +247,7 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
         const float bias = __ldg(C.bias + co);
         const bool vec = (P.N & 3) == 0;
         for (int i = 0; i < n_mine; ++i) {
-            const int T = pair + i * n_pairs, bb = i & 1;
+            const int T = pair + i * n_pairs, bb = i & 1;                 // (bb: accumulator buffer)
             const int b = T / C.tiles_per_sample, p0 = (T - b * C.tiles_per_sample) * LC_QT;
             mbar_wait(t_full + bb, (uint32_t)(i >> 1) & 1u);
             tc_fence_after();
@@ -209,6 +260,9 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
             if (lane == 0) mbar_arrive_remote(t_empty + bb, 0);          // the accumulator is in registers
             float* dst = C.out + ((long long)b * LC_COUT + co) * P.N + p0;
             const int n_valid = min(LC_QT, P.N - p0);
+#ifdef FC_LC_NOSTORE
+            if (v[0] == 12345.678f)
+#endif
             if (vec && n_valid == LC_QT) {
 #pragma unroll
                 for (int j = 0; j < LC_QT / 4; ++j)
@@ -220,42 +274,46 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
                     if (j < n_valid) dst[j] = fmaxf(v[j] + bias, 0.f);
             }
         }
-    } else {
+    } else if (warp < 6 + LC_GROUPS * LF_GWARPS) {
         // ================= lookup consumers: interpolate, split, write the B operand =================
         const int cw = warp - 6, g = cw / LF_GWARPS, w = cw - g * LF_GWARPS;
         constexpr int APW = (LC_R + LF_GWARPS - 1) / LF_GWARPS;              // 3 x-offsets per warp
-        for (int i = 0, k = 0; i < n_mine; ++i) {
-            const int T = pair + i * n_pairs, bb = i & 1;
-            for (int l = 0; l < LC_L; ++l, ++k) {
-                if ((k % LC_GROUPS) != g) continue;
-                const LfQuery q = lc_query(P, C, T, l, (int)rank, lane);
-                RegSink<APW, LC_R> sink;
+        const int n_k = n_mine * LC_L;
+        LfQuery q{};
+        if (g < n_k) q = lc_query(P, C, pair + (g / LC_L) * n_pairs, g % LC_L, (int)rank, lane);
+        for (int k = g; k < n_k; k += LC_GROUPS) {
+            const int i = k / LC_L, l = k - i * LC_L, bb = i % LC_NB;
+            LfQuery qn = q;
+            const int kn = k + LC_GROUPS;
+            if (kn < n_k) qn = lc_query(P, C, pair + (kn / LC_L) * n_pairs, kn % LC_L, (int)rank, lane);   // coordinates one turn ahead
+            lf_finish_query(P, q);
+            RegSink<APW, LC_R> sink;
 #pragma unroll
-                for (int aa = 0; aa < APW; ++aa)
+            for (int aa = 0; aa < APW; ++aa)
 #pragma unroll
-                    for (int j = 0; j < LC_R; ++j) sink.o[aa][j] = 0.f;
-                lf_consume<LC_RADIUS, CM, false, VB>(P, sh, win, q, k % LC_STAGES, (uint32_t)(k / LC_STAGES) & 1u, lane, w, sink);
-                // the MMAs that read this buffer two pair-tiles ago have retired
-                if (i >= 2) mbar_wait(b_empty + bb, (uint32_t)((i >> 1) - 1) & 1u);
-                uint8_t* hi_row = bbuf + bb * LC_BBUF + lane * 128;
-                uint8_t* lo_row = hi_row + LC_BPLANE;
+                for (int j = 0; j < LC_R; ++j) sink.o[aa][j] = 0.f;
+            lf_consume<LC_RADIUS, CM, false, VB>(P, sh, win, q, k % LC_STAGES, (uint32_t)(k / LC_STAGES) & 1u, lane, w, sink);
+            // the MMAs that read this buffer LC_NB pair-tiles ago have retired
+            if (i >= LC_NB) mbar_wait(b_empty + bb, (uint32_t)(i / LC_NB - 1) & 1u);
+            uint8_t* hi_row = bbuf + bb * LC_BBUF + lane * 128;
+            uint8_t* lo_row = hi_row + LC_BPLANE;
 #pragma unroll
-                for (int aa = 0; aa < APW; ++aa) {
-                    const int kp0 = l * LC_KL + (w * APW + aa) * (LC_R + 1);     // slot of (x-offset, y-offset 0): even
+            for (int aa = 0; aa < APW; ++aa) {
+                const int kp0 = l * LC_KL + (w * APW + aa) * (LC_R + 1);     // slot of (x-offset, y-offset 0): even
 #pragma unroll
-                    for (int jj = 0; jj < (LC_R + 1) / 2; ++jj) {
-                        const float v0 = sink.o[aa][2 * jj], v1 = (2 * jj + 1 < LC_R) ? sink.o[aa][2 * jj + 1 < LC_R ? 2 * jj + 1 : 0] : 0.f;
-                        const float h0 = lc_round(v0), h1 = lc_round(v1);
-                        const int kp = kp0 + 2 * jj;
-                        const uint32_t off = (uint32_t)((kp >> 6) * (QT * 128) + ((((kp & 63) >> 3) ^ (lane & 7)) << 4) + (kp & 7) * 2);
-                        *reinterpret_cast<uint32_t*>(hi_row + off) = lc_pack2(h0, h1);
-                        *reinterpret_cast<uint32_t*>(lo_row + off) = lc_pack2(v0 - h0, v1 - h1);
-                    }
+                for (int jj = 0; jj < (LC_R + 1) / 2; ++jj) {
+                    const float v0 = sink.o[aa][2 * jj], v1 = (2 * jj + 1 < LC_R) ? sink.o[aa][2 * jj + 1 < LC_R ? 2 * jj + 1 : 0] : 0.f;
+                    const float h0 = lc_round(v0), h1 = lc_round(v1);
+                    const int kp = kp0 + 2 * jj;
+                    const uint32_t off = (uint32_t)((kp >> 6) * (QT * 128) + ((((kp & 63) >> 3) ^ (lane & 7)) << 4) + (kp & 7) * 2);
+                    *reinterpret_cast<uint32_t*>(hi_row + off) = lc_pack2(h0, h1);
+                    *reinterpret_cast<uint32_t*>(lo_row + off) = lc_pack2(v0 - h0, v1 - h1);
                 }
-                fence_proxy_async_smem();                                  // generic-proxy writes -> the tensor core's reads
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote_release(b_full + bb, 0);
             }
+            fence_proxy_async_smem();                                  // generic-proxy writes -> the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_part + bb);
+            q = qn;
         }
     }
 
@@ -292,11 +350,11 @@ static int launch_lc(const LookupMaps& M, const LookupParams& P, const ConvParam
     int n_pairs = n_sm / 2;
     if (n_pairs > C.n_pair_tiles) n_pairs = C.n_pair_tiles;
     if (vb) {
-        const size_t smem = 1024 + 2 * LC_BBUF + (size_t)LC_STAGES * lf_stage_bytes(1) + sizeof(LfShared) + 128;
+        const size_t smem = 1024 + LC_NB * LC_BBUF + (size_t)LC_STAGES * lf_stage_bytes(1) + sizeof(LfShared) + 128;
         FC_SMEM_ATTR_ONCE((lookup_convc1_kernel<CM, 1>), smem);
         lookup_convc1_kernel<CM, 1><<<2 * n_pairs, LC_THREADS, smem, s>>>(M, P, C);
     } else {
-        const size_t smem = 1024 + 2 * LC_BBUF + (size_t)LC_STAGES * lf_stage_bytes(0) + sizeof(LfShared) + 128;
+        const size_t smem = 1024 + LC_NB * LC_BBUF + (size_t)LC_STAGES * lf_stage_bytes(0) + sizeof(LfShared) + 128;
         FC_SMEM_ATTR_ONCE((lookup_convc1_kernel<CM, 0>), smem);
         lookup_convc1_kernel<CM, 0><<<2 * n_pairs, LC_THREADS, smem, s>>>(M, P, C);
     }

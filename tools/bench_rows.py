@@ -89,6 +89,7 @@ def collect(reps=5, ref_kernel=True, model=True):
     row_ondemand(2, 136, 240, reps)
     row_bf16_volume(8, 55, 128, reps)
     row_fnet_tail(8, 55, 128, reps)
+    row_lookup_convc1(8, 55, 128, reps)
     if model:
         row_model(8, 436, 1024, max(2, reps // 2))
     return list(ROWS)
@@ -119,6 +120,32 @@ def row_bf16_volume(B, H, W, reps, iters=12):
     finally:
         fsb.CorrBlock.math, fsb.CorrBlock.volume = keep
     emit(row="bf16 volume mode (build + lookups), stated tolerance 2^-8 of max / 0.05 px EPE", geometry=f"B={B} {H}x{W}", **out)
+
+
+def row_lookup_convc1(B, H, W, reps):
+    """Row f1: lookup + convc1 (1x1, 324 -> 256) + ReLU.  'separate' = fc_lookup_fwd + torch conv2d + relu (cuDNN, torch
+    default math); 'fused' = fc_lookup_convc1_fwd (weights in tensor memory, the 324-channel tensor never written)."""
+    hbm, tf = peaks()
+    g = torch.Generator().manual_seed(0)
+    f1 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
+    f2 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
+    c = (fsb.coords_grid(B, H, W) + 5.0 * torch.randn(B, 2, H, W, generator=g)).cuda()
+    conv = torch.nn.Conv2d(K, 256, 1).cuda()
+    packed = ops.convc1_prepare(conv.weight.detach(), conv.bias.detach())
+    blk = fsb.CorrBlock(f1, f2, L, R)
+    with torch.no_grad():
+        ms_look = timed(lambda: blk(c), reps, inner=12)
+        ms_sep = timed(lambda: torch.relu(conv(blk(c))), reps, inner=12)
+        ms_fused = timed(lambda: blk.lookup_convc1(c, packed), reps, inner=12)
+        ref, out = torch.relu(conv(blk(c))), blk.lookup_convc1(c, packed)
+    Q = B * H * W
+    foot = inbounds_footprint(c.cpu(), H, W)
+    byts = Q * (foot * 4 + 256 * 4 + 8)                       # in-bounds footprint read + 256-channel output + coords
+    flop = 2.0 * Q * K * 256
+    emit(row="f1 lookup fused into convc1 (1x1, 324 -> 256) + ReLU", geometry=f"B={B} {H}x{W}", lookup_ms=ms_look,
+         separate_ms=ms_sep, fused_ms=ms_fused, speedup=ms_sep / ms_fused, bytes_algorithmic=byts, gbs=byts / ms_fused / 1e6,
+         bound="hbm", peak=hbm, frac=byts / ms_fused / 1e6 / hbm, gflop=flop / 1e9, tflops_useful=flop / ms_fused / 1e9,
+         max_rel_diff_vs_separate_tf32_conv=float((out - ref).abs().max() / ref.abs().max()))
 
 
 def row_fnet_tail(B, H, W, reps, cin=128):
@@ -183,11 +210,13 @@ def row_model(B, Himg, Wimg, reps, iters=12):
         res["runner_graph_ms"] = timed(lambda: graphed(im1, im2), reps, warm=2)
         tail = fsb.RaftRunner(model, iters=iters, graph=True, fused_fnet_tail=True)
         res["runner_graph_fused_tail_ms"] = timed(lambda: tail(im1, im2), reps, warm=2)
+        allf = fsb.RaftRunner(model, iters=iters, graph=True, fused_fnet_tail=True, fused_convc1=True)
+        res["runner_graph_fused_tail_convc1_ms"] = timed(lambda: allf(im1, im2), reps, warm=2)
     emit(row="RAFT forward pairs/s @436x1024, 12 iterations: unmodified reference model, same GPU",
          geometry=f"B={B} {Hp}x{Wp} px", conv_math="torch defaults (cuDNN TF32 convolutions)", **res,
          pairs_per_s={k[:-3]: B / v * 1e3 for k, v in res.items()},
          speedup_vs_reference_block={k[:-3]: res["reference_block_ms"] / v for k, v in res.items()})
-    del model, eager, graphed, tail
+    del model, eager, graphed, tail, allf
     torch.cuda.empty_cache()
 
 
