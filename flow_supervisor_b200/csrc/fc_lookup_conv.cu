@@ -16,8 +16,9 @@
 // 32 queries x 384 slots, bf16 hi and lo, K-major SWIZZLE_128B written by the consumers themselves).
 // fp32 parity through the same three-pass split as the volume build: W_hi*V_hi + W_lo*V_hi + W_hi*V_lo, fp32 accumulate.
 //
-// Warps: 0 = footprint producer (TMA), 1 = TMEM allocator + MMA issuer (leader CTA), 2-5 = weights -> TMEM once, then
-// epilogue (TMEM -> + bias -> ReLU -> (B, 256, H, W)), 6.. = lookup consumer groups of three warps.
+// Warps (512 threads): 0-2 = footprint producers (TMA), 3-6 = weights -> TMEM once, then epilogue (TMEM -> + bias -> ReLU
+// -> (B, 256, H, W)); lane 0 of warp 3 also allocates TMEM and issues the MMAs (leader CTA) / relays the peer's
+// completion, 7-15 = three lookup consumer groups of three warps.
 #include "fc_lookup_fwd.cuh"
 #include "fc_umma.cuh"
 
@@ -36,14 +37,17 @@ constexpr int LC_RADIUS = 4, LC_R = 2 * LC_RADIUS + 1, LC_L = 4;
 constexpr int LC_STAGES = FC_LC_STAGES;                   // footprint ring depth (LfShared holds 6 barriers)
 constexpr int LC_GROUPS = FC_LC_GROUPS;                   // consumer groups of LF_GWARPS warps
 #ifndef FC_LC_PRODUCERS
-#define FC_LC_PRODUCERS 1
+#define FC_LC_PRODUCERS 3
 #endif
-constexpr int LC_PRODUCERS = FC_LC_PRODUCERS;             // footprint producer warps: warp 0 and, with 2, the last warp
+constexpr int LC_PRODUCERS = FC_LC_PRODUCERS;             // footprint producer warps: warp 0 and the last LC_PRODUCERS - 1 warps
 constexpr int LC_NB = FC_LC_BBUFS;
 // a ring stage must always be filled by the same producer and drained by the same consumer group: an mbarrier parity wait
 // may run at most one phase behind the barrier it waits on (a waiter two phases late sees a stale "completed")
 static_assert(LC_STAGES % LC_GROUPS == 0 && LC_STAGES % LC_PRODUCERS == 0, "stage ownership");                        // B-operand buffers (1: a pair-tile's values wait in registers for the previous MMAs)
-constexpr int LC_THREADS = 32 * (1 + 1 + 4 + LC_GROUPS * LF_GWARPS + (LC_PRODUCERS - 1));
+// warps: [0, P) footprint producers, [P, P + 4) epilogue (the first of them also issues the MMAs), then the consumer groups
+constexpr int LC_EW0 = LC_PRODUCERS;                      // first epilogue warp
+constexpr int LC_CW0 = LC_PRODUCERS + 4;                  // first consumer warp
+constexpr int LC_THREADS = 32 * (LC_PRODUCERS + 4 + LC_GROUPS * LF_GWARPS);
 constexpr int LC_KL = 96;                                 // K slots per level: 9 x 10 = 90 used
 constexpr int LC_K = LC_L * LC_KL;                        // 384
 constexpr int LC_COUT = 256;
@@ -136,7 +140,7 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
         }
         mbar_fence_init();
     }
-    if (warp == 1) {
+    if (warp == LC_EW0) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
     }
@@ -160,7 +164,7 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
                 *reinterpret_cast<uint4*>(stagew + row * WPITCH + ch * 16) = __ldg(src + i);
             }
             __syncthreads();
-            if (warp >= 2 && warp < 6) {
+            if (warp >= LC_EW0 && warp < LC_CW0) {
                 const int quarter = warp & 3;
                 const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
                 const uint4* rowp = reinterpret_cast<const uint4*>(stagew + (quarter * 32 + lane) * WPITCH);
@@ -187,10 +191,11 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
     cluster_sync_all();                  // both CTAs: barriers initialised, weights in place
     tc_fence_after();
 
-    constexpr int LAST_WARP = LC_THREADS / 32 - 1;
-    if (warp == 0 || (LC_PRODUCERS == 2 && warp == LAST_WARP)) {
-        // ================= footprint producer(s): lookup tiles pw, pw + LC_PRODUCERS, ... =================
-        const int n_k = n_mine * LC_L, pw = warp == 0 ? 0 : 1;
+    if (warp < LC_PRODUCERS) {
+        // ================= footprint producers: lookup tiles pw, pw + LC_PRODUCERS, ... =================
+        // (one warp issues a tile's 32 footprint loads one by one through the uniform datapath, ~2.5 us per tile:
+        // a single producer warp bounded the whole kernel at 120 us; three bring it to the consumers' pace)
+        const int n_k = n_mine * LC_L, pw = warp;
         LfQuery q{};
         if (pw < n_k) q = lc_query(P, C, pair + (pw / LC_L) * n_pairs, pw % LC_L, (int)rank, lane);
         for (int k = pw; k < n_k; k += LC_PRODUCERS) {
@@ -202,67 +207,62 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
                                           ((uint32_t)(k / LC_STAGES) & 1u) ^ 1u);
             q = qn;
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer (leader CTA) =================
-        if (lane == 0 && leader) {
-            const uint32_t idesc = umma_idesc_bf16(2 * 128, LC_QT);
-            for (int i = 0; i < n_mine; ++i) {
-                const int bb = i % LC_NB, db = i & 1;
-                mbar_wait(b_part + bb, (uint32_t)(i / LC_NB) & 1u);             // this CTA's half of the B operand
-                mbar_wait_cluster(b_peer + bb, (uint32_t)(i / LC_NB) & 1u);     // the peer's half
-                mbar_wait_cluster(t_empty + db, ((uint32_t)(i >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t d_addr = tmem_base + (db ? LC_D1 : LC_D0);
-                const uint32_t bh = smem_u32(bbuf + bb * LC_BBUF), bl = bh + LC_BPLANE;
-#ifdef FC_LC_NOMMA
-                if (false)
-#endif
-#pragma unroll 4
-                for (int ks = 0; ks < LC_K / 16; ++ks) {
-                    const uint32_t boff = (uint32_t)((ks >> 2) * (QT * 128) + (ks & 3) * 32);
-                    const uint64_t dh = umma_desc_sw128(bh + boff), dl = umma_desc_sw128(bl + boff);
-                    const uint32_t ah = tmem_base + LC_AHI + (uint32_t)(ks * 8), al = tmem_base + LC_ALO + (uint32_t)(ks * 8);
-                    umma2_ts_bf16(d_addr, ah, dh, idesc, ks != 0 ? 1u : 0u);
-                    umma2_ts_bf16(d_addr, al, dh, idesc, 1u);
-                    umma2_ts_bf16(d_addr, ah, dl, idesc, 1u);
-                }
-                umma2_commit(b_empty + bb);              // both CTAs: this B buffer may be overwritten
-                umma2_commit(t_full + db);               // both CTAs: accumulator complete
-            }
-        } else if (lane == 0) {
-            // relay of the peer CTA: its consumers arrive on a local barrier; ONE release at cluster scope per pair-tile tells
-            // the leader that this CTA's half of the B operand is written (a cluster-scope release per consumer warp and
-            // lookup tile cost the consumers more than the lookups themselves)
-            for (int i = 0; i < n_mine; ++i) {
-                const int bb = i % LC_NB;
-                mbar_wait(b_part + bb, (uint32_t)(i / LC_NB) & 1u);
-                mbar_arrive_remote_release(b_peer + bb, 0);
-            }
-        }
-    } else if (warp < 6) {
-        // ================= epilogue: TMEM -> + bias -> ReLU -> (B, 256, H, W) =================
+    } else if (warp < LC_CW0) {
+        // ================= epilogue: TMEM -> + bias -> ReLU -> (B, 256, H, W); its first warp also issues the MMAs ======
         const int quarter = warp & 3;
         const int co = (int)rank * 128 + quarter * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const float bias = __ldg(C.bias + co);
         const bool vec = (P.N & 3) == 0;
+        const uint32_t idesc = umma_idesc_bf16(2 * 128, LC_QT);
+
+        // pair-tile i: (leader) wait for both halves of the B operand and a free accumulator, issue 3 x 24 MMAs;
+        // (peer) ONE release at cluster scope per pair-tile tells the leader that this CTA's half is written -- its
+        // consumers arrive on a local barrier (a cluster-scope release per consumer warp and lookup tile cost the
+        // consumers more than the lookups themselves)
+        auto issue = [&](int i) {
+            const int bb = i % LC_NB, db = i & 1;
+            mbar_wait(b_part + bb, (uint32_t)(i / LC_NB) & 1u);                 // this CTA's half of the B operand
+            if (!leader) { mbar_arrive_remote_release(b_peer + bb, 0); return; }
+            mbar_wait_cluster(b_peer + bb, (uint32_t)(i / LC_NB) & 1u);         // the peer's half
+            mbar_wait_cluster(t_empty + db, ((uint32_t)(i >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d_addr = tmem_base + (db ? LC_D1 : LC_D0);
+            const uint32_t bh = smem_u32(bbuf + bb * LC_BBUF), bl = bh + LC_BPLANE;
+#pragma unroll 4
+            for (int ks = 0; ks < LC_K / 16; ++ks) {
+                const uint32_t boff = (uint32_t)((ks >> 2) * (QT * 128) + (ks & 3) * 32);
+                const uint64_t dh = umma_desc_sw128(bh + boff), dl = umma_desc_sw128(bl + boff);
+                const uint32_t ah = tmem_base + LC_AHI + (uint32_t)(ks * 8), al = tmem_base + LC_ALO + (uint32_t)(ks * 8);
+                umma2_ts_bf16(d_addr, ah, dh, idesc, ks != 0 ? 1u : 0u);
+                umma2_ts_bf16(d_addr, al, dh, idesc, 1u);
+                umma2_ts_bf16(d_addr, ah, dl, idesc, 1u);
+            }
+            umma2_commit(b_empty + bb);              // both CTAs: this B buffer may be overwritten
+            umma2_commit(t_full + db);               // both CTAs: accumulator complete
+        };
+        if (warp == LC_EW0 && n_mine > 0) {
+            if (lane == 0) issue(0);
+            __syncwarp();
+        }
         for (int i = 0; i < n_mine; ++i) {
-            const int T = pair + i * n_pairs, bb = i & 1;                 // (bb: accumulator buffer)
+            if (warp == LC_EW0 && i + 1 < n_mine) {      // the next pair-tile's MMAs before this one's epilogue
+                if (lane == 0) issue(i + 1);
+                __syncwarp();
+            }
+            const int T = pair + i * n_pairs, db = i & 1;
             const int b = T / C.tiles_per_sample, p0 = (T - b * C.tiles_per_sample) * LC_QT;
-            mbar_wait(t_full + bb, (uint32_t)(i >> 1) & 1u);
+            mbar_wait(t_full + db, (uint32_t)(i >> 1) & 1u);
             tc_fence_after();
             float v[LC_QT];
-            tmem_ld32(lane_addr + (bb ? LC_D1 : LC_D0), v);
-            tmem_ld32(lane_addr + (bb ? LC_D1 : LC_D0) + 32u, v + 32);
+            tmem_ld32(lane_addr + (db ? LC_D1 : LC_D0), v);
+            tmem_ld32(lane_addr + (db ? LC_D1 : LC_D0) + 32u, v + 32);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_remote(t_empty + bb, 0);          // the accumulator is in registers
+            if (lane == 0) mbar_arrive_remote(t_empty + db, 0);          // the accumulator is in registers
             float* dst = C.out + ((long long)b * LC_COUT + co) * P.N + p0;
             const int n_valid = min(LC_QT, P.N - p0);
-#ifdef FC_LC_NOSTORE
-            if (v[0] == 12345.678f)
-#endif
             if (vec && n_valid == LC_QT) {
 #pragma unroll
                 for (int j = 0; j < LC_QT / 4; ++j)
@@ -274,9 +274,9 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
                     if (j < n_valid) dst[j] = fmaxf(v[j] + bias, 0.f);
             }
         }
-    } else if (warp < 6 + LC_GROUPS * LF_GWARPS) {
+    } else {
         // ================= lookup consumers: interpolate, split, write the B operand =================
-        const int cw = warp - 6, g = cw / LF_GWARPS, w = cw - g * LF_GWARPS;
+        const int cw = warp - LC_CW0, g = cw / LF_GWARPS, w = cw - g * LF_GWARPS;
         constexpr int APW = (LC_R + LF_GWARPS - 1) / LF_GWARPS;              // 3 x-offsets per warp
         const int n_k = n_mine * LC_L;
         LfQuery q{};
@@ -320,7 +320,7 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
     // neither CTA may leave while its peer can still touch its barriers / tensor memory
     tc_fence_before();
     cluster_sync_all();
-    if (warp == 1) {
+    if (warp == LC_EW0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
     }
