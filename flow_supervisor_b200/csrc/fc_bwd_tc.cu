@@ -51,6 +51,12 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
            (1ull << 46) | (2ull << 61);
 }
+__device__ __forceinline__ void lds128(uint32_t addr, float* v) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint32_t* v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
     asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(p), "f"(v) : "memory");
 }
@@ -369,6 +375,337 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------- GEMM straight from the fp32 gradient pyramid
+// The default backward.  Same CTA-pair GEMMs as tc_bwd_kernel, but the G operand comes from the fp32 gradient pyramid
+// itself: the fold (avg_pool2d backward of corr.py:24-27), the bf16 hi/lo split and the swizzled operand layout happen in
+// shared memory on the way to the tensor core, so the fold + pack pass over the volume (a read AND a write of 4 N NP
+// bytes per sample) and the in-place planes do not exist, the gradient pyramid is left untouched and there is no
+// "whole query row in shared memory" size limit.
+//
+//   warp 0      TMA: per k-block one fp32 box of G level 0 into this CTA's `raw` buffer ([128 p][64 q'] for dF1,
+//               [64 p][128 q'] for dF2; rows past the tensor arrive as zeros) + the feature operand's bf16 hi/lo boxes
+//   warps 6-13  converters: thread = 4 consecutive targets q' of one row: += the folded coarse levels (read through the
+//               read-only path: 32-byte pieces of the level-1..L-1 maps of the same query), split into bf16 hi/lo and
+//               store where a SWIZZLE_128B TMA box would have put them (row r, 16-byte chunk j at j ^ (r & 7)); the
+//               same bytes serve as K-major operand (dF1: rows = p) and MN-major operand (dF2: rows = k = p)
+//   warp 1      leader: waits for both CTAs' converted halves + the feature boxes, issues the MMAs; peer: relays its
+//               CTA's "converted" barrier to the leader with ONE cluster-scope release per k-block
+//   warps 2-5   epilogue as in tc_bwd_kernel
+constexpr int BF_THREADS = 448;
+constexpr int BF_EPI0 = 2, BF_CONV0 = 6, BF_CONV_WARPS = 8;
+constexpr int BF_STAGES = 2;
+constexpr int BF_RAW_BYTES = 128 * BW_BK * 4;                // 32 KB of fp32
+constexpr int BF_STAGE_BYTES = BF_RAW_BYTES + 4 * BW_PART_BYTES;   // raw | A_hi | A_lo | B_hi | B_lo = 96 KB
+
+struct FoldSrc {
+    const float* lvl[FC_MAX_LEVELS];
+    int H[FC_MAX_LEVELS], W[FC_MAX_LEVELS], Wp[FC_MAX_LEVELS], msize[FC_MAX_LEVELS];
+    int L;
+};
+
+template <int OP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BF_THREADS, 1)
+tc_bwd_fold_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_b_hi,
+                   const __grid_constant__ CUtensorMap map_b_lo, const BwdParams P, const FoldSrc F) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + BF_STAGES * BF_STAGE_BYTES);
+    uint64_t* raw_full = bars;                      // per stage: the fp32 box landed (this CTA)
+    uint64_t* raw_empty = raw_full + BF_STAGES;     // the converters have read it (8 warps)
+    uint64_t* b_full = raw_empty + BF_STAGES;       // leader's: feature boxes of BOTH CTAs landed
+    uint64_t* a_part = b_full + BF_STAGES;          // this CTA's converted operand is written (8 warps)
+    uint64_t* a_peer = a_part + BF_STAGES;          // leader's: the peer's relay
+    uint64_t* empty = a_peer + BF_STAGES;           // multicast commit: the MMAs reading this stage retired
+    uint64_t* t_full = empty + BF_STAGES;           // 2
+    uint64_t* t_empty = t_full + 2;                 // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_parts = P.three_pass ? 2 : 1;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int half_n = P.D / 2;
+
+    const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+    const int u_begin = (int)((long long)P.units * cluster_id / n_clusters);
+    const int u_end = (int)((long long)P.units * (cluster_id + 1) / n_clusters);
+    auto decode = [&](int u, int& b, int& m0, int& kb0, int& kb1) {
+        const int am = u / P.ksplit, ks = u - am * P.ksplit;
+        b = am / P.mp;
+        m0 = ((am - b * P.mp) * 2 + (int)rank) * BW_BM;
+        kb0 = (int)((long long)P.kb_total * ks / P.ksplit);
+        kb1 = (int)((long long)P.kb_total * (ks + 1) / P.ksplit);
+    };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < BF_STAGES; ++i) {
+            mbar_init(raw_full + i, 1); mbar_init(raw_empty + i, BF_CONV_WARPS); mbar_init(b_full + i, 1);
+            mbar_init(a_part + i, BF_CONV_WARPS); mbar_init(a_peer + i, 1); mbar_init(empty + i, 1);
+        }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (lane == 0) {
+            const uint32_t b_tx = (uint32_t)(2 * n_parts * half_n * BW_BK * 2);
+            // the gradient volume streams through L2 once; the feature planes are swept again by every row tile
+            const uint64_t stream = l2_policy_evict_first(), keep = l2_policy_evict_last();
+            int it = 0;
+            for (int u = u_begin; u < u_end; ++u) {
+                int b, m0, kb0, kb1;
+                decode(u, b, m0, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % BF_STAGES;
+                    const uint32_t free_parity = ((uint32_t)(it / BF_STAGES) & 1u) ^ 1u;
+                    uint8_t* st = ring + s * BF_STAGE_BYTES;
+                    mbar_wait(raw_empty + s, free_parity);
+                    mbar_expect_tx(raw_full + s, (uint32_t)BF_RAW_BYTES);
+                    if (OP == BW_DF1) tma_load_3d_hint(smem_u32(st), &map_g, smem_u32(raw_full + s), kb * BW_BK, m0, b, stream);   // [128 p][64 q']
+                    else tma_load_3d_hint(smem_u32(st), &map_g, smem_u32(raw_full + s), m0, kb * BW_BK, b, stream);                // [64 p][128 q']
+                    mbar_wait(empty + s, free_parity);
+                    if (leader) mbar_expect_tx(b_full + s, b_tx);
+                    for (int part = 0; part < n_parts; ++part)
+                        tma2_load_2d_hint(st + BF_RAW_BYTES + (2 + part) * BW_PART_BYTES, part ? &map_b_lo : &map_b_hi, b_full + s,
+                                          kb * BW_BK, b * P.D + (int)rank * half_n, keep);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader) / relay (peer) =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(2 * BW_BM, P.D) | (OP == BW_DF2 ? (1u << 15) : 0u);
+            int it = 0, uc = 0;
+            for (int u = u_begin; u < u_end; ++u, ++uc) {
+                int b, m0, kb0, kb1;
+                decode(u, b, m0, kb0, kb1);
+                const int buf = uc & 1;
+                if (leader) {
+                    mbar_wait_cluster(t_empty + buf, ((uint32_t)(uc >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                }
+                const uint32_t d_addr = tmem_base + (uint32_t)(buf * 256);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % BF_STAGES;
+                    const uint32_t parity = (uint32_t)(it / BF_STAGES) & 1u;
+                    mbar_wait(a_part + s, parity);                       // this CTA's half of the G operand
+                    if (!leader) { mbar_arrive_remote_release(a_peer + s, 0); continue; }
+                    mbar_wait_cluster(a_peer + s, parity);               // the peer's half
+                    mbar_wait(b_full + s, parity);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(ring + s * BF_STAGE_BYTES) + BF_RAW_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BW_BK / 16; ++k) {
+                        uint64_t ah, al;
+                        if (OP == BW_DF1) {
+                            ah = umma_desc_sw128(st + k * 32);
+                            al = umma_desc_sw128(st + BW_PART_BYTES + k * 32);
+                        } else {
+                            ah = umma_desc_mn_sw128(st + k * 2048);
+                            al = umma_desc_mn_sw128(st + BW_PART_BYTES + k * 2048);
+                        }
+                        const uint64_t bh = umma_desc_sw128(st + 2 * BW_PART_BYTES + k * 32);
+                        const uint64_t bl = umma_desc_sw128(st + 3 * BW_PART_BYTES + k * 32);
+                        umma2_bf16(d_addr, ah, bh, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                        if (P.three_pass) {
+                            umma2_bf16(d_addr, al, bh, idesc, 1u);
+                            umma2_bf16(d_addr, ah, bl, idesc, 1u);
+                        }
+                    }
+                    umma2_commit(empty + s);
+                }
+                if (leader) umma2_commit(t_full + buf);
+            }
+        }
+    } else if (warp < BF_CONV0) {
+        // ================= epilogue: TMEM -> scale -> red.add into (B, D, N) =================
+        const int quarter = warp & 3;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        int uc = 0;
+        for (int u = u_begin; u < u_end; ++u, ++uc) {
+            int b, m0, kb0, kb1;
+            decode(u, b, m0, kb0, kb1);
+            const int buf = uc & 1;
+            const int r = m0 + quarter * 32 + lane;
+            int col = -1;
+            if (r < P.M) {
+                if (OP == BW_DF1) {
+                    col = r;
+                } else {
+                    int y, x;
+                    tile_inv(r, P.Wp, y, x);
+                    if (y < P.H && x < P.W) col = y * P.W + x;
+                }
+            }
+            float* dst = P.out + (long long)b * P.D * P.N + col;
+            mbar_wait(t_full + buf, (uint32_t)(uc >> 1) & 1u);
+            tc_fence_after();
+            for (int c0 = 0; c0 < P.D; c0 += 32) {
+                float v[32];
+                tmem_ld32(lane_addr + (uint32_t)(buf * 256 + c0), v);
+                tmem_ld_wait();
+                if (col >= 0) {
+                    float* d = dst + (long long)c0 * P.N;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j, d += P.N) red_add_f32(d, v[j] * P.scale);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(t_empty + buf, 0);
+        }
+    } else {
+        // ================= converters: fp32 box (+ folded coarse levels) -> bf16 hi/lo swizzled operand =================
+        // thread = one patch row (8 consecutive targets of one map row) of one query; 4 sweeps cover the box.  The coarse
+        // cells over a patch row are 4 + 2 + 1 (+ 1 + 1) values: they are fetched ONE K-BLOCK AHEAD into registers (global
+        // latency would otherwise sit between every two k-blocks of a warp).
+        constexpr int C = (OP == BW_DF1) ? 64 : 128;        // targets per row of the box
+        constexpr int R = 128 * BW_BK / C;                  // rows (queries) of the box
+        constexpr int CPR = C / 8;                          // patch rows per box row
+        constexpr int RPS = 256 / CPR;                      // box rows per sweep of the 256 converter threads
+        constexpr int SWEEPS = R / RPS;                     // 4
+        const int ctid = threadIdx.x - BF_CONV0 * 32;
+        const int c = (ctid % CPR) * 8, r0 = ctid / CPR;
+        const uint32_t ring_s = smem_u32(ring);
+        const uint32_t raw_off = (uint32_t)(r0 * C + c) * 4u;
+        const uint32_t a_off = (uint32_t)(BF_RAW_BYTES + (c >> 6) * (R * 128) + r0 * 128 + (((((c & 63) >> 3)) ^ (r0 & 7)) << 4));
+        const int L = F.L;
+        // element strides between this thread's rows of consecutive sweeps, per coarse level
+        const int st1 = L > 1 ? RPS * F.msize[1] : 0, st2 = L > 2 ? RPS * F.msize[2] : 0, st3 = L > 3 ? RPS * F.msize[3] : 0;
+
+        struct Pos { int u, kb, kb1, b, m0; };
+        auto first = [&](Pos& o, int u) {
+            o.u = u;
+            if (u < u_end) { int kb0; decode(u, o.b, o.m0, kb0, o.kb1); o.kb = kb0; }
+        };
+        struct Coarse {                 // the coarse cells over this thread's patch row, per sweep (= per query row)
+            float4 c1[SWEEPS];          // level 1: 4 cells
+            float2 c2[SWEEPS];          // level 2: 2 cells
+            float c3[SWEEPS];           // level 3: 1 cell
+        };
+        // validity of the coarse cells over the patch row at target q: bits 0-3 level-1 cells, 4-5 level-2 cells, 6.. levels
+        // 3, 4, 5; element offsets of the first cell inside the query's level-l map
+        uint32_t ok_n = 0;
+        int off1 = 0, off2 = 0, off3 = 0, off4 = 0, off5 = 0, q_taps = -1;
+        auto taps = [&](int q) {
+            q_taps = q; ok_n = 0;
+            if (L <= 1 || q >= P.NP) return;
+            int y, x;
+            tile_inv(q, P.Wp, y, x);
+#pragma unroll
+            for (int l = 1; l < FC_MAX_LEVELS; ++l) {
+                if (l < L) {
+                    const int yl = y >> l, xl = x >> l, n = l == 1 ? 4 : (l == 2 ? 2 : 1);
+                    const int o_l = tile_off(yl, xl, F.Wp[l]);
+                    const int bit0 = l == 1 ? 0 : (l == 2 ? 4 : 3 + l);
+                    if (yl < F.H[l]) {
+#pragma unroll
+                        for (int j = 0; j < n; ++j)
+                            if (xl + j < F.W[l]) ok_n |= 1u << (bit0 + j);
+                    }
+                    if (l == 1) off1 = o_l; else if (l == 2) off2 = o_l; else if (l == 3) off3 = o_l;
+                    else if (l == 4) off4 = o_l; else off5 = o_l;
+                }
+            }
+        };
+        auto fetch = [&](const Pos& o, Coarse& f) {
+            const int q = (OP == BW_DF1 ? o.kb * BW_BK : o.m0) + c;
+            if (q != q_taps) taps(q);
+            const int p0 = (OP == BW_DF1 ? o.m0 : o.kb * BW_BK) + r0;
+            const long long row = (long long)o.b * P.N + p0;
+            const float* g1 = (ok_n & 0x1u) ? F.lvl[1] + row * F.msize[1] + off1 : nullptr;
+            const float* g2 = (ok_n & 0x10u) ? F.lvl[2] + row * F.msize[2] + off2 : nullptr;
+            const float* g3 = (ok_n & 0x40u) ? F.lvl[3] + row * F.msize[3] + off3 : nullptr;
+#pragma unroll
+            for (int i = 0; i < SWEEPS; ++i) {
+                const bool pv = p0 + i * RPS < P.N;
+                f.c1[i] = (pv && g1) ? __ldg(reinterpret_cast<const float4*>(g1 + i * st1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                f.c2[i] = (pv && g2) ? __ldg(reinterpret_cast<const float2*>(g2 + i * st2)) : make_float2(0.f, 0.f);
+                f.c3[i] = (pv && g3) ? __ldg(g3 + i * st3) : 0.f;
+            }
+        };
+
+        Pos cur;
+        first(cur, u_begin);
+        Coarse nxt_f;
+        if (cur.u < u_end) fetch(cur, nxt_f);
+        for (int it = 0; cur.u < u_end; ++it) {
+            const int s = it % BF_STAGES;
+            const uint32_t parity = (uint32_t)(it / BF_STAGES) & 1u;
+            // fold the prefetched coarse cells into one addend per pair of targets (frees their registers for the next fetch)
+            float w1[SWEEPS][4];
+#pragma unroll
+            for (int i = 0; i < SWEEPS; ++i) {
+                float v = 0.f;                               // levels >= 3: one cell over the patch row, coarsest first
+                if (L > 4) {
+                    const int p = (OP == BW_DF1 ? cur.m0 : cur.kb * BW_BK) + r0 + i * RPS;
+                    if (p < P.N) {
+                        const long long row = (long long)cur.b * P.N + p;
+                        if (L > 5 && (ok_n >> 8 & 1u)) v = __ldg(F.lvl[5] + row * F.msize[5] + off5);
+                        v = (ok_n >> 7 & 1u) ? __ldg(F.lvl[4] + row * F.msize[4] + off4) + 0.25f * v : 0.f;
+                    }
+                }
+                v = (ok_n >> 6 & 1u) ? nxt_f.c3[i] + 0.25f * v : 0.f;
+                const float w2a = (ok_n >> 4 & 1u) ? nxt_f.c2[i].x + 0.25f * v : 0.f;
+                const float w2b = (ok_n >> 5 & 1u) ? nxt_f.c2[i].y + 0.25f * v : 0.f;
+                w1[i][0] = (ok_n & 1u) ? 0.25f * (nxt_f.c1[i].x + 0.25f * w2a) : 0.f;
+                w1[i][1] = (ok_n & 2u) ? 0.25f * (nxt_f.c1[i].y + 0.25f * w2a) : 0.f;
+                w1[i][2] = (ok_n & 4u) ? 0.25f * (nxt_f.c1[i].z + 0.25f * w2b) : 0.f;
+                w1[i][3] = (ok_n & 8u) ? 0.25f * (nxt_f.c1[i].w + 0.25f * w2b) : 0.f;
+            }
+            Pos nx = cur;
+            if (++nx.kb >= nx.kb1) first(nx, nx.u + 1);
+            if (nx.u < u_end) fetch(nx, nxt_f);             // in flight while this k-block is converted
+            const uint32_t st = ring_s + (uint32_t)(s * BF_STAGE_BYTES);
+            mbar_wait(raw_full + s, parity);
+            mbar_wait(empty + s, parity ^ 1u);              // the MMAs that read this stage's operand two k-blocks ago retired
+#pragma unroll
+            for (int i = 0; i < SWEEPS; ++i) {
+                float x[8];
+                lds128(st + raw_off + i * (RPS * C * 4), x);
+                lds128(st + raw_off + i * (RPS * C * 4) + 16, x + 4);
+                if (L > 1) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] += w1[i][j >> 1];
+                }
+                uint32_t h[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+                    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                    const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * j] - __uint_as_float(h[j] << 16),
+                                                                    x[2 * j + 1] - __uint_as_float(h[j] & 0xffff0000u));
+                    lo[j] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
+                sts128(st + a_off + i * (RPS * 128), h);
+                if (P.three_pass) sts128(st + a_off + BW_PART_BYTES + i * (RPS * 128), lo);
+            }
+            fence_proxy_async_smem();                       // generic-proxy writes -> the tensor core's reads
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(raw_empty + s); mbar_arrive(a_part + s); }
+            cur = nx;
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+    }
+}
+
 // ---------------------------------------------------------------- host side
 static int encode_bf16(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
                        const cuuint64_t* strides_bytes, const cuuint32_t* box) {
@@ -391,9 +728,12 @@ static BwdLayout bwd_layout(int B, int D, int N, int NP) {
     return L;
 }
 
+// the default (fold-in-the-GEMM) backward takes any map size; FLOWCORR_BWD_FUSED=0 selects the round-1 pipeline
+// (fold + pack pass, then GEMMs from the in-place bf16 planes), which stages a whole query row in shared memory
+static bool bwd_fold_in_gemm() { return tunables().bwd_fused != 0; }
 bool tc_bwd_supported(int D, int H, int W) {
     const long long NP = (long long)round_up(H, 2) * round_up(W, 8);
-    return D % 64 == 0 && D <= 256 && NP <= BW_MAX_NP;
+    return D % 64 == 0 && D <= 256 && (bwd_fold_in_gemm() || NP <= BW_MAX_NP);
 }
 
 size_t tc_bwd_workspace_bytes(int B, int D, int H, int W) {
@@ -438,6 +778,33 @@ static int launch_bwd_gemm(const CUtensorMap* maps, BwdParams P, int B, cudaStre
     return FC_OK;
 }
 
+template <int OP>
+static int launch_bwd_fold_gemm(const CUtensorMap* maps, BwdParams P, const FoldSrc& F, int B, cudaStream_t s) {
+    const size_t smem = 1024 + (size_t)BF_STAGES * BF_STAGE_BYTES + 256;
+    FC_SMEM_ATTR_ONCE((tc_bwd_fold_kernel<OP>), smem);
+    static std::atomic<int> clusters_of[64];
+    int dev = 0;
+    FC_CUDA(cudaGetDevice(&dev));
+    int n_clusters = clusters_of[dev & 63].load(std::memory_order_acquire);
+    if (n_clusters == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(sm_count_cached() & ~1); cfg.blockDim = dim3(BF_THREADS); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        FC_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, tc_bwd_fold_kernel<OP>, &cfg));
+        clusters_of[dev & 63].store(n_clusters, std::memory_order_release);
+    }
+    if (n_clusters < 1) { set_error("fc_build_bwd: no CTA pair of the tensor-core kernel fits on this device"); return FC_ECUDA; }
+    P.ksplit = pick_ksplit(B * P.mp, P.kb_total, n_clusters);
+    P.units = B * P.mp * P.ksplit;
+    if (n_clusters > P.units) n_clusters = P.units;
+    tc_bwd_fold_kernel<OP><<<dim3(2 * n_clusters), BF_THREADS, smem, s>>>(maps[0], maps[2], maps[3], P, F);
+    FC_LAUNCH_CHECK("tc_bwd_fold_kernel");
+    return FC_OK;
+}
+
 int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float* d2, const Pyramid& pyr,
                  int D, int H, int W, int math, void* ws, size_t ws_bytes, cudaStream_t s) {
     const int B = pyr.B, N = pyr.N, Wp = pyr.lv[0].Wp, NP = pyr.lv[0].Hp * Wp;
@@ -454,7 +821,14 @@ int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float
     const int three = (math == FC_MATH_TC_3XBF16) ? 1 : 0;
     float* g0 = gpyr + pyr.lv[0].offset;
 
-    {   // fold the pyramid into level 0 and split it into bf16 planes, in place
+    const bool fused = bwd_fold_in_gemm();
+    FoldSrc FS{};
+    FS.L = pyr.L;
+    for (int l = 0; l < pyr.L; ++l) {
+        FS.lvl[l] = gpyr + pyr.lv[l].offset;
+        FS.H[l] = pyr.lv[l].H; FS.W[l] = pyr.lv[l].W; FS.Wp[l] = pyr.lv[l].Wp; FS.msize[l] = pyr.lv[l].Hp * pyr.lv[l].Wp;
+    }
+    if (!fused) {   // fold the pyramid into level 0 and split it into bf16 planes, in place
         FoldParams F{};
         F.L = pyr.L; F.NP = NP; F.two_planes = three;
         int so = 0;
@@ -497,6 +871,11 @@ int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float
     const uint8_t* g_lo = g_hi + (size_t)NP * 2;
     const cuuint64_t gdims[3] = {(cuuint64_t)NP, (cuuint64_t)N, (cuuint64_t)B};
     const cuuint64_t gstr[2] = {(cuuint64_t)NP * 4, (cuuint64_t)N * NP * 4};
+    auto encode_raw = [&](CUtensorMap* map, cuuint32_t box_q, cuuint32_t box_p) {      // fp32 level 0 as {q', p, b}
+        const cuuint32_t box[3] = {box_q, box_p, 1};
+        return encode_tiled_cached(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, g0, gdims, gstr, box, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    };
 
     BwdParams P{};
     P.D = D; P.N = N; P.NP = NP; P.H = H; P.W = W; P.Wp = Wp;
@@ -506,26 +885,34 @@ int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float
     if (d1) {
         FC_CUDA(cudaMemsetAsync(d1, 0, (size_t)B * D * N * 4, s));
         const cuuint32_t abox[3] = {(cuuint32_t)BW_BK, (cuuint32_t)BW_BM, 1};
-        if (int e = encode_bf16(&maps[0], g_hi, 3, gdims, gstr, abox)) return e;
-        if (int e = encode_bf16(&maps[1], three ? g_lo : g_hi, 3, gdims, gstr, abox)) return e;
+        if (fused) {
+            if (int e = encode_raw(&maps[0], BW_BK, BW_BM)) return e;
+        } else {
+            if (int e = encode_bf16(&maps[0], g_hi, 3, gdims, gstr, abox)) return e;
+            if (int e = encode_bf16(&maps[1], three ? g_lo : g_hi, 3, gdims, gstr, abox)) return e;
+        }
         const cuuint64_t bdims[2] = {(cuuint64_t)NP, (cuuint64_t)B * D};
         const cuuint64_t bstr[1] = {(cuuint64_t)L.NPk * 2};
         if (int e = encode_bf16(&maps[2], f2_hi, 2, bdims, bstr, bbox)) return e;
         if (int e = encode_bf16(&maps[3], three ? f2_lo : f2_hi, 2, bdims, bstr, bbox)) return e;
         P.out = d1; P.M = N; P.kb_total = (NP + BW_BK - 1) / BW_BK; P.mp = (N + 2 * BW_BM - 1) / (2 * BW_BM);
-        if (int e = launch_bwd_gemm<BW_DF1>(maps, P, B, s)) return e;
+        if (int e = fused ? launch_bwd_fold_gemm<BW_DF1>(maps, P, FS, B, s) : launch_bwd_gemm<BW_DF1>(maps, P, B, s)) return e;
     }
     if (d2) {
         FC_CUDA(cudaMemsetAsync(d2, 0, (size_t)B * D * N * 4, s));
         const cuuint32_t abox[3] = {64, 64, 1};
-        if (int e = encode_bf16(&maps[0], g_hi, 3, gdims, gstr, abox)) return e;
-        if (int e = encode_bf16(&maps[1], three ? g_lo : g_hi, 3, gdims, gstr, abox)) return e;
+        if (fused) {
+            if (int e = encode_raw(&maps[0], BW_BM, BW_BK)) return e;
+        } else {
+            if (int e = encode_bf16(&maps[0], g_hi, 3, gdims, gstr, abox)) return e;
+            if (int e = encode_bf16(&maps[1], three ? g_lo : g_hi, 3, gdims, gstr, abox)) return e;
+        }
         const cuuint64_t bdims[2] = {(cuuint64_t)N, (cuuint64_t)B * D};
         const cuuint64_t bstr[1] = {(cuuint64_t)L.N8 * 2};
         if (int e = encode_bf16(&maps[2], f1_hi, 2, bdims, bstr, bbox)) return e;
         if (int e = encode_bf16(&maps[3], three ? f1_lo : f1_hi, 2, bdims, bstr, bbox)) return e;
         P.out = d2; P.M = NP; P.kb_total = (N + BW_BK - 1) / BW_BK; P.mp = (NP + 2 * BW_BM - 1) / (2 * BW_BM);
-        if (int e = launch_bwd_gemm<BW_DF2>(maps, P, B, s)) return e;
+        if (int e = fused ? launch_bwd_fold_gemm<BW_DF2>(maps, P, FS, B, s) : launch_bwd_gemm<BW_DF2>(maps, P, B, s)) return e;
     }
     return FC_OK;
 }
