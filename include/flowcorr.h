@@ -134,10 +134,12 @@ int fc_lookup_bwd(const float* grad_out, const float* coords, float* grad_pyrami
 size_t fc_build_bwd_workspace_bytes(int B, int D, int H, int W, int num_levels, int math);
 
 /* Backward of CorrBlock.__init__ (autograd of corr.py:21-27,52-60): folds the
- * gradient pyramid to level 0 (avg_pool2d backward; grad_pyramid is consumed /
- * overwritten), scales by 1/sqrt(D) and contracts:
+ * gradient pyramid to level 0 (avg_pool2d backward), scales by 1/sqrt(D) and contracts:
  *   dfmap1[b,:,p] = sum_q dC[b,p,q] fmap2[b,:,q],  dfmap2[b,:,q] = sum_p dC[b,p,q] fmap1[b,:,p].
- * dfmap1 / dfmap2: (B, D, H, W) fp32, overwritten; either may be NULL to skip. */
+ * dfmap1 / dfmap2: (B, D, H, W) fp32, overwritten; either may be NULL to skip.
+ * grad_pyramid must be treated as consumed: the tensor-core modes' default kernels only read it (the fold
+ * and the bf16 split happen inside the GEMMs), but FC_MATH_FP32 and the FLOWCORR_BWD_FUSED=0 pipeline fold
+ * it in place.  Its pad cells must be zero (fc_lookup_bwd never writes them). */
 int fc_build_bwd(float* grad_pyramid, const float* fmap1, const float* fmap2,
                  float* dfmap1, float* dfmap2,
                  int B, int D, int H, int W, int num_levels, int math,

@@ -109,11 +109,13 @@ def _grads(fsb, math, f1, f2, coords, gouts, L=4, r=4):
                                        ((1, 64, 19, 27), 4, 4),       # odd everything, D = 64
                                        ((2, 128, 24, 40), 3, 3),      # RAFT-small
                                        ((1, 192, 16, 24), 1, 4),      # single level: no fold
-                                       ((1, 256, 47, 156), 4, 4)])    # KITTI geometry (Wp = 160)
+                                       ((1, 256, 47, 156), 4, 4),     # KITTI geometry (Wp = 160)
+                                       ((1, 64, 64, 96), 6, 2),       # six levels: the two coarsest are read at use
+                                       ((1, 64, 35, 50), 5, 2)])      # five levels, odd maps
 @pytest.mark.parametrize("math,tol", [("3xbf16", 3e-5), ("bf16", 2e-2)])
 def test_tc_backward_matches_fp32_mode(fsb, shape, L, r, math, tol):
-    """Fused fold + in-place bf16 split + the two tcgen05 GEMMs (K-major and MN-major reads of
-    the same gradient planes) against the fp32 CUDA-core mode of the same library; three
+    """The two tcgen05 GEMMs with the fold + bf16 split of the gradient pyramid inside them (K-major and MN-major
+    reads of the same converted tile) against the fp32 CUDA-core mode of the same library; three
     lookups accumulate into one gradient pyramid.  3xbf16 <= 3e-5 of the gradient's max
     magnitude (inside the 1e-4 contract); bf16 stated separately <= 2e-2."""
     B, D, H, W = shape
@@ -129,6 +131,58 @@ def test_tc_backward_matches_fp32_mode(fsb, shape, L, r, math, tol):
     e1 = float((d1 - r1).abs().max() / r1.abs().max())
     e2 = float((d2 - r2).abs().max() / r2.abs().max())
     assert e1 < tol and e2 < tol, (e1, e2)
+
+
+def _build_bwd_switch(fsb, value):
+    from flow_supervisor_b200 import _lib
+    _lib.check(_lib.load().fc_tunable_set(b"bwd_fused", int(value)), "fc_tunable_set")
+
+
+@pytest.mark.parametrize("shape,L", [((2, 256, 46, 62), 4), ((1, 64, 19, 27), 4), ((1, 256, 47, 156), 4),
+                                     ((2, 128, 24, 40), 3), ((1, 64, 64, 96), 6)])
+@pytest.mark.parametrize("math", ["3xbf16", "bf16"])
+def test_tc_backward_fold_in_gemm_matches_the_separate_fold_pass(fsb, shape, L, math):
+    """fc_build_bwd's default (fold + bf16 split inside the GEMMs, gradient pyramid only read) against the round-1
+    pipeline (fold + pack pass, GEMMs from the in-place planes; FLOWCORR_BWD_FUSED=0): same products of the same
+    rounded operands, only the accumulation order of the split-K pieces differs -> <= 2e-6 of the gradient's
+    max; and the default leaves the gradient pyramid untouched."""
+    from flow_supervisor_b200 import _lib, ops
+    B, D, H, W = shape
+    gen = torch.Generator().manual_seed(11)
+    f1 = (1.57 * torch.randn(B, D, H, W, generator=gen)).cuda()
+    f2 = (1.57 * torch.randn(B, D, H, W, generator=gen) + 0.1).cuda()
+    src = torch.randn(ops.pyramid_numel(B, H, W, L), generator=gen).cuda()
+    m = _lib.MATH_TC_3XBF16 if math == "3xbf16" else _lib.MATH_TC_BF16
+    try:
+        gp = src.clone()
+        a1, a2 = ops.build_bwd(gp, f1, f2, L, m)
+        torch.cuda.synchronize()
+        assert torch.equal(gp, src), "the default backward must not modify the gradient pyramid"
+        _build_bwd_switch(fsb, 0)
+        b1, b2 = ops.build_bwd(src.clone(), f1, f2, L, m)
+    finally:
+        _build_bwd_switch(fsb, 1)
+    for a, b in ((a1, b1), (a2, b2)):
+        assert float((a - b).abs().max() / b.abs().max()) < 2e-6
+
+
+def test_tc_backward_takes_maps_past_the_old_row_in_shared_memory_limit(fsb):
+    """136x240 tokens (cfg 5's 1/8 map, 32 640 padded targets): the round-1 backward fell to the fp32 CUDA-core
+    contractions above 16 384 targets; the fold-in-GEMM kernels have no such limit.  Checked against that fp32 mode."""
+    from flow_supervisor_b200 import _lib, ops
+    B, D, H, W, L = 1, 64, 136, 240, 4
+    assert _lib.load().fc_build_bwd_workspace_bytes(B, D, H, W, L, _lib.MATH_TC_3XBF16) > 0     # tensor-core route taken
+    gen = torch.Generator().manual_seed(5)
+    f1 = torch.randn(B, D, H, W, generator=gen).cuda()
+    f2 = torch.randn(B, D, H, W, generator=gen).cuda()
+    src = torch.zeros(ops.pyramid_numel(B, H, W, L), device="cuda")
+    # a sparse gradient pyramid (a dense one is 5.7 GB of randn): 2 M random cells over all levels
+    idx = torch.randint(0, src.numel(), (2_000_000,), generator=gen).cuda()
+    src[idx] = torch.randn(idx.numel(), generator=gen).cuda()
+    d1, d2 = ops.build_bwd(src.clone(), f1, f2, L, _lib.MATH_TC_3XBF16)
+    r1, r2 = ops.build_bwd(src.clone(), f1, f2, L, _lib.MATH_FP32)
+    for a, b in ((d1, r1), (d2, r2)):
+        assert float((a - b).abs().max() / b.abs().max()) < 3e-5
 
 
 @pytest.mark.parametrize("shape", [(1, 256, 46, 96), (1, 256, 54, 128), (2, 128, 23, 50)])
