@@ -397,6 +397,18 @@ constexpr int BF_STAGES = 2;
 constexpr int BF_RAW_BYTES = 128 * BW_BK * 4;                // 32 KB of fp32
 constexpr int BF_STAGE_BYTES = BF_RAW_BYTES + 4 * BW_PART_BYTES;   // raw | A_hi | A_lo | B_hi | B_lo = 96 KB
 
+// Timeline probe (FC_PROBES builds only; tools/probe_bwd_trace.py): CTA 0 stamps clock64() at the hand-offs of its first
+// 256 k-blocks.  producer: 0 box buffer free, 1 operand stage free; converter thread 0: 2 ready for the k-block, 3 box
+// landed, 4 operand stage free, 5 operand stored; MMA thread: 6 own half converted, 7 peer's half, 8 feature boxes,
+// 9 MMAs issued + committed
+#ifdef FC_PROBES
+constexpr int BF_TRACE_SLOTS = 10;
+__device__ unsigned long long fc_bwd_trace_buf[2][256 * BF_TRACE_SLOTS];
+#define BF_TRACE(it, k) do { if (blockIdx.x == 0 && (it) < 256) fc_bwd_trace_buf[OP][(it) * BF_TRACE_SLOTS + (k)] = clock64(); } while (0)
+#else
+#define BF_TRACE(it, k) do {} while (0)
+#endif
+
 struct FoldSrc {
     const float* lvl[FC_MAX_LEVELS];
     int H[FC_MAX_LEVELS], W[FC_MAX_LEVELS], Wp[FC_MAX_LEVELS], msize[FC_MAX_LEVELS];
@@ -473,10 +485,12 @@ tc_bwd_fold_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
                     const uint32_t free_parity = ((uint32_t)(it / BF_STAGES) & 1u) ^ 1u;
                     uint8_t* st = ring + s * BF_STAGE_BYTES;
                     mbar_wait(raw_empty + s, free_parity);
+                    BF_TRACE(it, 0);
                     mbar_expect_tx(raw_full + s, (uint32_t)BF_RAW_BYTES);
                     if (OP == BW_DF1) tma_load_3d_hint(smem_u32(st), &map_g, smem_u32(raw_full + s), kb * BW_BK, m0, b, stream);   // [128 p][64 q']
                     else tma_load_3d_hint(smem_u32(st), &map_g, smem_u32(raw_full + s), m0, kb * BW_BK, b, stream);                // [64 p][128 q']
                     mbar_wait(empty + s, free_parity);
+                    BF_TRACE(it, 1);
                     if (leader) mbar_expect_tx(b_full + s, b_tx);
                     for (int part = 0; part < n_parts; ++part)
                         tma2_load_2d_hint(st + BF_RAW_BYTES + (2 + part) * BW_PART_BYTES, part ? &map_b_lo : &map_b_hi, b_full + s,
@@ -502,9 +516,12 @@ tc_bwd_fold_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
                     const int s = it % BF_STAGES;
                     const uint32_t parity = (uint32_t)(it / BF_STAGES) & 1u;
                     mbar_wait(a_part + s, parity);                       // this CTA's half of the G operand
+                    BF_TRACE(it, 6);
                     if (!leader) { mbar_arrive_remote_release(a_peer + s, 0); continue; }
                     mbar_wait_cluster(a_peer + s, parity);               // the peer's half
+                    BF_TRACE(it, 7);
                     mbar_wait(b_full + s, parity);
+                    BF_TRACE(it, 8);
                     tc_fence_after();
                     const uint32_t st = smem_u32(ring + s * BF_STAGE_BYTES) + BF_RAW_BYTES;
 #pragma unroll
@@ -526,6 +543,7 @@ tc_bwd_fold_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
                         }
                     }
                     umma2_commit(empty + s);
+                    BF_TRACE(it, 9);
                 }
                 if (leader) umma2_commit(t_full + buf);
             }
@@ -670,8 +688,11 @@ tc_bwd_fold_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
             if (++nx.kb >= nx.kb1) first(nx, nx.u + u_step);
             if (nx.u < u_end) fetch(nx, nxt_f);             // in flight while this k-block is converted
             const uint32_t st = ring_s + (uint32_t)(s * BF_STAGE_BYTES);
+            if (ctid == 0) BF_TRACE(it, 2);
             mbar_wait(raw_full + s, parity);
+            if (ctid == 0) BF_TRACE(it, 3);
             mbar_wait(empty + s, parity ^ 1u);              // the MMAs that read this stage's operand two k-blocks ago retired
+            if (ctid == 0) BF_TRACE(it, 4);
 #pragma unroll
             for (int i = 0; i < SWEEPS; ++i) {
                 float x[8];
@@ -696,6 +717,7 @@ tc_bwd_fold_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
             fence_proxy_async_smem();                       // generic-proxy writes -> the tensor core's reads
             __syncwarp();
             if (lane == 0) { mbar_arrive(raw_empty + s); mbar_arrive(a_part + s); }
+            if (ctid == 0) BF_TRACE(it, 5);
             cur = nx;
         }
     }
@@ -920,3 +942,9 @@ int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float
 }
 
 }  // namespace fc
+
+#ifdef FC_PROBES
+extern "C" int fc_debug_bwd_trace(unsigned long long* host_out) {      // 2 x 256 x BF_TRACE_SLOTS stamps (see BF_TRACE)
+    return cudaMemcpyFromSymbol(host_out, fc::fc_bwd_trace_buf, sizeof(fc::fc_bwd_trace_buf)) == cudaSuccess ? 0 : 1;
+}
+#endif
