@@ -22,10 +22,20 @@
 
 namespace fc {
 
-constexpr int LB_GROUPS = 3;                                  // independent warp groups per CTA
+#ifndef FC_LB_GROUPS
+#define FC_LB_GROUPS 3
+#endif
+#ifndef FC_LB_STAGES
+#define FC_LB_STAGES 2
+#endif
+#ifndef FC_LB_PREFETCH
+#define FC_LB_PREFETCH 1
+#endif
+constexpr int LB_GROUPS = FC_LB_GROUPS;                       // independent warp groups per CTA
 constexpr int LB_GWARPS = 3;                                  // warps per group (window column thirds)
 constexpr int LB_THREADS = 32 * LB_GROUPS * LB_GWARPS;        // 288
-constexpr int LB_STAGES = 2;                                  // window buffers per group
+constexpr int LB_STAGES = FC_LB_STAGES;                       // window buffers per group
+constexpr bool LB_PREFETCH = FC_LB_PREFETCH != 0;             // inputs of the next tile loaded one tile ahead
 constexpr int LB_WIN_BYTES = 6 * 3 * 64;                      // 6 row pairs x 3 patches x 64 B = 1152
 constexpr int LB_STAGE_BYTES = QT * LB_WIN_BYTES;             // 36 864
 
@@ -98,7 +108,7 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
     for (int it = 0;; ++it) {
         const int next = tile + n_groups;
         T nxt = cur;
-        if (next < n_tiles) { ti.advance(hop_q, hop_l, hop_qm, L); nxt.load(P, ti, lane); }   // in flight while this tile is processed
+        if (LB_PREFETCH && next < n_tiles) { ti.advance(hop_q, hop_l, hop_qm, L); nxt.load(P, ti, lane); }   // in flight while this tile is processed
 
         const int level = cur.level;
         const float cx = __fmul_rn(cur.cx, P.inv_scale[level]), cy = __fmul_rn(cur.cy, P.inv_scale[level]);
@@ -130,7 +140,7 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
         const bool touches = near_ && n_rp > 0 && n_pc > 0 && ybase < Hl && xbase < Wl;
 
         // ---- the buffer used two tiles ago must have been read by its reduce-adds
-        const uint32_t stage = gbase + (uint32_t)((it & 1) * LB_STAGE_BYTES);
+        const uint32_t stage = gbase + (uint32_t)((it % LB_STAGES) * LB_STAGE_BYTES);
         tma_wait_group_read<LB_STAGES - 1>();                            // every lane waits for its own reduce-adds
         group_sync(g);
 #pragma unroll
@@ -202,7 +212,9 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
         }
         tma_commit_group();
         if (next >= n_tiles) break;
-        tile = next; cur = nxt;
+        tile = next;
+        if (LB_PREFETCH) cur = nxt;
+        else { ti.advance(hop_q, hop_l, hop_qm, L); cur.load(P, ti, lane); }
     }
     tma_wait_group<0>();
 }
