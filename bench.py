@@ -345,11 +345,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident step: value
-    # per-kernel CUDA events ride on every EV_STRIDE-th timed step only: an event record between two launches opens a gap
-    # of 1-2 us, which 14 times per step would cost the whole-job figure ~2 %
+    # per-kernel CUDA events ride on every EV_STRIDE-th timed step only (an event record between two launches opens a gap
+    # of 1-2 us)
     EV_STRIDE = 4
     ev_steps = [s for s in range(args.steps) if s % EV_STRIDE == 0]
-    ev = {s: [torch.cuda.Event(enable_timing=True) for _ in range(iters + 2)] for s in ev_steps}
+    # three events per sampled step: start, after the build, after the last lookup -- the lookup's figure is the average
+    # of its 12 back-to-back launches (an event between every two of them added ~3 us to each)
+    ev = {s: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for s in ev_steps}
 
     def step_resident(events=None):
         if events: events[0].record()
@@ -358,7 +360,7 @@ def main():
         out = None
         for t in range(iters):
             out = blk(coords[t])
-            if events: events[t + 2].record()
+        if events: events[2].record()
         return out
 
     for _ in range(max(args.warmup, 3)):
@@ -380,7 +382,7 @@ def main():
     if sampler: sampler.pause()
     elapsed_ms = t_start.elapsed_time(t_end)
     build_ms = sum(e[0].elapsed_time(e[1]) for e in ev.values()) / len(ev)
-    look_ms = sum(e[t + 1].elapsed_time(e[t + 2]) for e in ev.values() for t in range(iters)) / (len(ev) * iters)
+    look_ms = sum(e[1].elapsed_time(e[2]) for e in ev.values()) / (len(ev) * iters)
 
     # ---- end-to-end step through the public API with HOST buffers: e2e
     out_host = torch.empty(iters, B, K_CH, H, W, dtype=torch.float32).pin_memory()
@@ -497,7 +499,8 @@ def main():
             "config": workload_config(args, H, W),
             "arm": {"math": args.math, "parallelism": f"batch-sharded x{world}, no collective",
                     "l2": f"inputs larger than L2 (pyramid {pyr_bytes / 1e9:.2f} GB/GPU, L2 126 MB): no flush needed",
-                    "kernel_events": f"per-kernel CUDA events on every {EV_STRIDE}th timed step"},
+                    "kernel_events": f"CUDA events (start, after the build, after the 12th lookup) on every {EV_STRIDE}th timed step; "
+                                     "the lookup's duration is the mean of its 12 back-to-back launches"},
             "lookups_per_s": world * B * N * iters * args.steps / (elapsed_ms * 1e-3),
             "wall_s": wall,
             "roofline": dominant, "roofline_other": other,
