@@ -618,11 +618,23 @@ tc_bwd_fold_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
         // 3, 4, 5; element offsets of the first cell inside the query's level-l map
         uint32_t ok_n = 0;
         int off1 = 0, off2 = 0, off3 = 0, off4 = 0, off5 = 0, q_taps = -1;
+        // the patch (row pair py, patch px of the row) this thread's 8 targets lie in.  dF1 walks the targets 4 patches per
+        // k-block: the position is carried along (one division per work unit instead of one per k-block)
+        const int ppr = P.Wp >> 3;
+        int py = 0, px = 0;
         auto taps = [&](int q) {
+            if (L > 1 && q < P.NP) {
+                if (OP == BW_DF1 && q == q_taps + BW_BK) {
+                    px += BW_BK / 16;
+                    while (px >= ppr) { px -= ppr; ++py; }
+                } else {
+                    const int pt = q >> 4;
+                    py = pt / ppr; px = pt - py * ppr;
+                }
+            }
             q_taps = q; ok_n = 0;
             if (L <= 1 || q >= P.NP) return;
-            int y, x;
-            tile_inv(q, P.Wp, y, x);
+            const int y = 2 * py + ((q >> 3) & 1), x = 8 * px;
 #pragma unroll
             for (int l = 1; l < FC_MAX_LEVELS; ++l) {
                 if (l < L) {
@@ -693,11 +705,15 @@ tc_bwd_fold_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
             if (ctid == 0) BF_TRACE(it, 3);
             mbar_wait(empty + s, parity ^ 1u);              // the MMAs that read this stage's operand two k-blocks ago retired
             if (ctid == 0) BF_TRACE(it, 4);
+            float xs[SWEEPS][8];                             // all shared loads first: the sweeps below then overlap
 #pragma unroll
             for (int i = 0; i < SWEEPS; ++i) {
-                float x[8];
-                lds128(st + raw_off + i * (RPS * C * 4), x);
-                lds128(st + raw_off + i * (RPS * C * 4) + 16, x + 4);
+                lds128(st + raw_off + i * (RPS * C * 4), xs[i]);
+                lds128(st + raw_off + i * (RPS * C * 4) + 16, xs[i] + 4);
+            }
+#pragma unroll
+            for (int i = 0; i < SWEEPS; ++i) {
+                float* x = xs[i];
                 if (L > 1) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) x[j] += w1[i][j >> 1];
