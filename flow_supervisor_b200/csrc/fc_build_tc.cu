@@ -179,6 +179,20 @@ struct TcParams {
                            // 5 = pooled-level stores off, 6 = level-0 stores off, 7 = no target-operand loads
 };
 
+// Timeline probe (FC_PROBES builds only; tools/probe_build_trace.py): CTA 0 stamps clock64() per tile (accumulator).
+// MMA thread: 0 accumulator free, 1 all MMAs of the tile issued + committed, 2 cycles spent waiting for ring stages;
+// first epilogue warp: 3 ready for the tile, 4 accumulator complete, 5 accumulator drained (handed back), 6 tile's stores issued;
+// producer: 7 cycles spent waiting for free ring stages
+#ifdef FC_PROBES
+constexpr int TB_SLOTS = 8;
+__device__ unsigned long long fc_build_trace_buf[512 * TB_SLOTS];
+#define TB_TRACE(tile, k, v) do { if (blockIdx.x == 0 && (tile) < 512) fc_build_trace_buf[(tile) * TB_SLOTS + (k)] = (v); } while (0)
+#define TB_CLOCK() clock64()
+#else
+#define TB_TRACE(tile, k, v) do {} while (0)
+#define TB_CLOCK() 0ll
+#endif
+
 template <int KB, int EW, int VB>   // KB = D / 64 k-blocks, EW = epilogue warps (4 or 8), VB = 1: bf16 volume
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc_threads(EW), 1)
 tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -262,7 +276,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
         if (lane == 0) {
-            int a_use = 0, cur_am = -1, slot = 0;
+            int a_use = 0, cur_am = -1, slot = 0, ptile = 0;
             uint32_t phase = 0;                                // ring position: stage `slot`, use parity `phase`
             for (int u = u_begin; u < u_end; ++u) {
                 int b, m0, t0, t1;
@@ -281,6 +295,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 // target operand: stages of [NT/2 rows][64 k], hi then lo of each k-block
                 for (int h = 0; h < P.halves; ++h)                 // tile order of a unit: half 0 of its 4 row pairs, then half 1
                   for (int rp = t0; rp < t1; ++rp) {
+                    long long pw = 0;
                     const int ncols = h ? P.NT2 : P.NT;            // each CTA streams its half of the tile's targets
                     const int row0 = b * P.NP + rp * 2 * P.Wp + h * P.NT + (int)rank * (ncols >> 1);
                     for (int kb = 0; kb < KB; ++kb)
@@ -288,7 +303,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             const int s = slot;
                             const uint32_t ph = phase;
                             if (++slot == P.stages) { slot = 0; phase ^= 1u; }
-                            mbar_wait(b_empty + s, ph ^ 1u);
+                            { const long long w0 = TB_CLOCK(); mbar_wait(b_empty + s, ph ^ 1u); pw += TB_CLOCK() - w0; }
                             if (FC_PROBE_VAL(P) == 7) {                // no target loads (stage probe)
                                 if (leader) mbar_arrive(b_full + s);
                                 continue;
@@ -297,6 +312,8 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             const CUtensorMap* mp = part == 0 ? (h ? &map_b2_hi : &map_b_hi) : (h ? &map_b2_lo : &map_b_lo);
                             tma2_load_2d(ring + s * TC_STAGE_BYTES, mp, b_full + s, kb * TC_BK, row0);
                         }
+                    TB_TRACE(ptile, 7, (unsigned long long)pw);
+                    ++ptile;
                   }
             }
         }
@@ -321,13 +338,15 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     const int buf = tc & 1;
                     mbar_wait(t_empty + buf, ((uint32_t)(tc >> 1) & 1u) ^ 1u);
                     tc_fence_after();
+                    TB_TRACE(tc, 0, (unsigned long long)TB_CLOCK());
+                    long long rw = 0;
                     const uint32_t d_addr = tmem_base + (uint32_t)(buf * 256);
                     for (int kb = 0; kb < KB; ++kb)
                         for (int part = 0; part < n_parts; ++part) {
                             const int s = slot;
                             const uint32_t ph = phase;
                             if (++slot == P.stages) { slot = 0; phase ^= 1u; }
-                            mbar_wait(b_full + s, ph);
+                            { const long long w0 = TB_CLOCK(); mbar_wait(b_full + s, ph); rw += TB_CLOCK() - w0; }
                             tc_fence_after();
                             const uint32_t b_addr = smem_u32(ring + s * TC_STAGE_BYTES);
                             const uint32_t ah_addr = smem_u32(a_hi + kb * TC_ABLK_BYTES);
@@ -344,6 +363,8 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             umma2_commit(b_empty + s);         // frees the ring slot in both CTAs when these MMAs retire
                         }
                     umma2_commit(t_full + buf);                // accumulator complete: both epilogues
+                    TB_TRACE(tc, 1, (unsigned long long)TB_CLOCK());
+                    TB_TRACE(tc, 2, (unsigned long long)rw);
                 }
             }
         }
@@ -393,8 +414,10 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // row pairs, then half 1, so one set of stashes serves both.
         auto tile_body = [&](const int H, int rp) {
             const int buf = tc & 1;
+            if (ew == 0 && lane == 0) TB_TRACE(tc, 3, (unsigned long long)TB_CLOCK());
             mbar_wait(t_full + buf, (uint32_t)(tc >> 1) & 1u);
             tc_fence_after();
+            if (ew == 0 && lane == 0) TB_TRACE(tc, 4, (unsigned long long)TB_CLOCK());
             const int q0 = rp * 2 * P.Wp + H * P.NT;           // first padded target of the tile
             const int ncols = H ? P.NT2 : P.NT;
             const int n_chunks = (ncols + 31) >> 5;            // 32-column chunks of the tile (the last may be 16 wide)
@@ -506,6 +529,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(t_empty + buf, 0);
+            if (ew == 0 && lane == 0) TB_TRACE(tc, 5, (unsigned long long)TB_CLOCK());
 
             if (P.n_fused > 2 && (rp & 1) && FC_PROBE_VAL(P) != 3) {
                 // ---- level 2: row y2 = rp / 2, columns [4 gc, 4 gc + 4) per chunk -> 32-byte runs per chunk pair
@@ -560,6 +584,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         for (int g = half_id; g * 8 < wp; g += NH) vol_store8(rowp + g * 16, z);
                     }
             }
+            if (ew == 0 && lane == 0) TB_TRACE(tc, 6, (unsigned long long)TB_CLOCK());
             ++tc;
         };
 
@@ -772,3 +797,9 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
 }
 
 }  // namespace fc
+
+#ifdef FC_PROBES
+extern "C" int fc_debug_build_trace(unsigned long long* host_out) {     // 512 x TB_SLOTS stamps (see TB_TRACE)
+    return cudaMemcpyFromSymbol(host_out, fc::fc_build_trace_buf, sizeof(fc::fc_build_trace_buf)) == cudaSuccess ? 0 : 1;
+}
+#endif
