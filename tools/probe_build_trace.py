@@ -34,6 +34,13 @@ t0 = t[8, 0]
 for i in range(8, min(n, 40)):
     r = t[i]
     print(f"{i:4d} {r[0]-t0:9d} {r[1]-t0:8d} {r[2]:9d} | {r[3]-t0:9d} {r[4]-t0:10d} {r[5]-t0:8d} {r[6]-t0:10d} | {r[7]:8d}")
+span = t[n - 1, 6] - t[0, 0]
+d = np.diff(t[:n, 1])
+big = np.argsort(-d)[:8]
+print("whole run: %d cycles from tile 0's accumulator to the last tile's stores; median tile period %d; the 8 largest periods: %s" %
+      (span, int(np.median(d)), ", ".join(f"tile {int(i) + 1}: {int(d[i])}" for i in sorted(big))))
+print("first tile issued %d cycles after the first accumulator wait; last tile: issued -> stores issued %d" %
+      (t[0, 1] - t[0, 0], t[n - 1, 6] - t[n - 1, 1]))
 w = t[8:n - 2]
 per = np.diff(w[:, 1]).mean()
 print("mean cycles per tile (issue to issue): %.0f" % per)
