@@ -517,8 +517,8 @@ tc_bwd_fold_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
                     const uint32_t parity = (uint32_t)(it / BF_STAGES) & 1u;
                     mbar_wait(a_part + s, parity);                       // this CTA's half of the G operand
                     BF_TRACE(it, 6);
-                    if (!leader) { mbar_arrive_remote_release(a_peer + s, 0); continue; }
-                    mbar_wait_cluster(a_peer + s, parity);               // the peer's half
+                    if (!leader) { mbar_arrive_remote_default(a_peer + s, 0); continue; }
+                    mbar_wait(a_peer + s, parity);                       // the peer's half
                     BF_TRACE(it, 7);
                     mbar_wait(b_full + s, parity);
                     BF_TRACE(it, 8);
@@ -746,6 +746,351 @@ tc_bwd_fold_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
     }
 }
 
+// ---------------------------------------------------------------- the same GEMMs for patch-row aligned maps
+// When a row of the map holds a multiple of 4 patches (Wp % 32 == 0: 128, 96, 64, 160 ... -- every size the reference's
+// configurations use) a k-block of dF1 (64 targets = 4 patches) and each half of a dF2 row tile (128 targets = 2 x 4
+// patches) lies inside ONE patch row, so the coarse cells over it are three small boxes per level-1..3 map --
+// [rows][2 patches x 8], [rows][8], [rows][4] cells -- that the TMA unit can fetch: no index arithmetic, no global loads
+// and no validity logic in the converter threads (pad cells of the gradient pyramid are zeros and an invalid cell's
+// parents are pads too, so `c1 + (c2 + c3/4)/4` needs no masks), ~270 instead of ~600 dependent instructions per thread
+// and k-block.  The fp32 box is converted IN PLACE (32 KB of fp32 = 16 + 16 KB of bf16 planes, every converter thread
+// holds its part in registers across a named barrier), which makes room for THREE 64 KB stages + a 2-deep ring of
+// coarse boxes (14 KB each).  Everything else (MMA issue, relay, epilogue, round-robin units) is tc_bwd_fold_kernel's.
+constexpr int BA_STAGES = 2;                                             // operand stages: A_hi | A_lo | B_hi | B_lo = 64 KB
+constexpr int BA_STAGE_BYTES = 4 * BW_PART_BYTES;
+constexpr int BA_RSTAGES = 2;                                            // fp32 boxes in flight (32 KB each)
+constexpr int BA_RAW_BYTES = 128 * BW_BK * 4;
+constexpr int BA_CSTAGES = 2;
+constexpr int BA_THREADS = BF_THREADS + 32;                              // + warp 14: the box / coarse-box producer
+constexpr int BA_C1 = 0, BA_C2 = 8192, BA_C3 = 12288, BA_CBYTES = 14336; // coarse boxes of one k-block: level 1 | 2 | 3
+
+__device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::"r"(
+            smem_dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void lds128f(uint32_t addr, float* v) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+
+struct CoarseMaps { CUtensorMap m[3]; };            // levels 1..3 as {8 cells, 2 sub-rows, patches, N, B}
+struct CoarseGeo { int ppr[4]; int L; };            // patches per row of levels 0..3; number of levels (<= 4)
+
+template <int OP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BA_THREADS, 1)
+tc_bwd_fold_aligned_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_b_hi,
+                           const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CoarseMaps CM,
+                           const BwdParams P, const CoarseGeo G) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;
+    uint8_t* rring = ring + BA_STAGES * BA_STAGE_BYTES;
+    uint8_t* cring = rring + BA_RSTAGES * BA_RAW_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cring + BA_CSTAGES * BA_CBYTES);
+    uint64_t* raw_full = bars;                      // per box buffer: the fp32 box landed (this CTA)
+    uint64_t* raw_empty = raw_full + BA_RSTAGES;    // ... and is in the converters' registers (8 warps)
+    uint64_t* b_full = raw_empty + BA_RSTAGES;      // leader's: feature boxes of BOTH CTAs landed
+    uint64_t* a_part = b_full + BA_STAGES;          // this CTA's converted operand is written (8 warps)
+    uint64_t* a_peer = a_part + BA_STAGES;          // leader's: the peer's relay
+    uint64_t* empty = a_peer + BA_STAGES;           // multicast commit: the MMAs reading this stage retired
+    uint64_t* c_full = empty + BA_STAGES;           // coarse boxes landed
+    uint64_t* c_empty = c_full + BA_CSTAGES;        // ... and read (8 warps)
+    uint64_t* t_full = c_empty + BA_CSTAGES;        // 2
+    uint64_t* t_empty = t_full + 2;                 // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_parts = P.three_pass ? 2 : 1;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int half_n = P.D / 2;
+
+    const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+    const int u_begin = cluster_id, u_end = P.units, u_step = n_clusters;      // round robin (see tc_bwd_fold_kernel)
+    auto decode = [&](int u, int& b, int& m0, int& kb0, int& kb1) {
+        const int am = u / P.ksplit, ks = u - am * P.ksplit;
+        b = am / P.mp;
+        m0 = ((am - b * P.mp) * 2 + (int)rank) * BW_BM;
+        kb0 = (int)((long long)P.kb_total * ks / P.ksplit);
+        kb1 = (int)((long long)P.kb_total * (ks + 1) / P.ksplit);
+    };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < BA_STAGES; ++i) {
+            mbar_init(b_full + i, 1);
+            mbar_init(a_part + i, BF_CONV_WARPS); mbar_init(a_peer + i, 1); mbar_init(empty + i, 1);
+        }
+        for (int i = 0; i < BA_RSTAGES; ++i) { mbar_init(raw_full + i, 1); mbar_init(raw_empty + i, BF_CONV_WARPS); }
+        for (int i = 0; i < BA_CSTAGES; ++i) { mbar_init(c_full + i, 1); mbar_init(c_empty + i, BF_CONV_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr int ROWS = OP == BW_DF1 ? 128 : 64;   // query rows of a k-block's box
+    const int nlev = G.L;                            // 1 .. 4
+    const uint32_t c_tx = (uint32_t)(ROWS * ((nlev > 1 ? 64 : 0) + (nlev > 2 ? 32 : 0) + (nlev > 3 ? 16 : 0)) * (OP == BW_DF1 ? 1 : 2));
+
+    if (warp == 0) {
+        // ================= TMA producer of the feature operand (both CTAs) =================
+        if (lane == 0) {
+            const uint32_t b_tx = (uint32_t)(2 * n_parts * half_n * BW_BK * 2);
+            const uint64_t keep = l2_policy_evict_last();
+            int it = 0;
+            for (int u = u_begin; u < u_end; u += u_step) {
+                int b, m0, kb0, kb1;
+                decode(u, b, m0, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % BA_STAGES;
+                    uint8_t* st = ring + s * BA_STAGE_BYTES;
+                    mbar_wait(empty + s, ((uint32_t)(it / BA_STAGES) & 1u) ^ 1u);   // the MMAs that read this stage retired (both CTAs)
+                    BF_TRACE(it, 1);
+                    if (leader) mbar_expect_tx(b_full + s, b_tx);
+                    for (int part = 0; part < n_parts; ++part)
+                        tma2_load_2d_hint(st + (2 + part) * BW_PART_BYTES, part ? &map_b_lo : &map_b_hi, b_full + s,
+                                          kb * BW_BK, b * P.D + (int)rank * half_n, keep);
+                }
+            }
+        }
+    } else if (warp == BF_CONV0 + BF_CONV_WARPS) {
+        // ================= TMA producer of the fp32 boxes and the coarse boxes (both CTAs) =================
+        // its own warp: these loads wait for the CONVERTERS (box buffer read), not for the MMAs, and run ahead of them
+        if (lane == 0) {
+            const uint64_t stream = l2_policy_evict_first();
+            // the coarse boxes over 4 patches starting at patch px0 of patch row py (levels 1..3), `rows` queries from p0
+            auto coarse = [&](uint32_t dst, uint32_t bar, int py, int px0, int p0, int b, int rows_off) {
+                if (nlev > 1) tma_load_5d(dst + BA_C1 + rows_off * 64, &CM.m[0], bar, 0, py & 1, (py >> 1) * G.ppr[1] + (px0 >> 1), p0, b);
+                if (nlev > 2) tma_load_5d(dst + BA_C2 + rows_off * 32, &CM.m[1], bar, 0, (py >> 1) & 1, (py >> 2) * G.ppr[2] + (px0 >> 2), p0, b);
+                if (nlev > 3) tma_load_5d(dst + BA_C3 + rows_off * 16, &CM.m[2], bar, px0 & 4, (py >> 2) & 1, (py >> 3) * G.ppr[3] + (px0 >> 3), p0, b);
+            };
+            int it = 0;
+            for (int u = u_begin; u < u_end; u += u_step) {
+                int b, m0, kb0, kb1;
+                decode(u, b, m0, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    if (nlev > 1) {
+                        const int cs = it % BA_CSTAGES;
+                        mbar_wait(c_empty + cs, ((uint32_t)(it / BA_CSTAGES) & 1u) ^ 1u);
+                        mbar_expect_tx(c_full + cs, c_tx);
+                        const uint32_t dst = smem_u32(cring + cs * BA_CBYTES), bar = smem_u32(c_full + cs);
+                        if (OP == BW_DF1) {
+                            const int pt = kb * (BW_BK / 16);                 // first patch of the k-block
+                            const int py = pt / G.ppr[0];
+                            coarse(dst, bar, py, pt - py * G.ppr[0], m0, b, 0);
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) {                     // the two 4-patch halves of this CTA's row tile
+                                const int pt = (m0 >> 4) + 4 * g;
+                                const int py = pt / G.ppr[0];
+                                coarse(dst, bar, py, pt - py * G.ppr[0], kb * BW_BK, b, g * ROWS);
+                            }
+                        }
+                    }
+                    const int rs = it % BA_RSTAGES;
+                    mbar_wait(raw_empty + rs, ((uint32_t)(it / BA_RSTAGES) & 1u) ^ 1u);
+                    BF_TRACE(it, 0);
+                    mbar_expect_tx(raw_full + rs, (uint32_t)BA_RAW_BYTES);
+                    const uint32_t dst = smem_u32(rring + rs * BA_RAW_BYTES);
+                    if (OP == BW_DF1) tma_load_3d_hint(dst, &map_g, smem_u32(raw_full + rs), kb * BW_BK, m0, b, stream);   // [128 p][64 q']
+                    else tma_load_3d_hint(dst, &map_g, smem_u32(raw_full + rs), m0, kb * BW_BK, b, stream);                // [64 p][128 q']
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader) / relay (peer) =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(2 * BW_BM, P.D) | (OP == BW_DF2 ? (1u << 15) : 0u);
+            int it = 0, uc = 0;
+            for (int u = u_begin; u < u_end; u += u_step, ++uc) {
+                int b, m0, kb0, kb1;
+                decode(u, b, m0, kb0, kb1);
+                const int buf = uc & 1;
+                if (leader) {
+                    mbar_wait_cluster(t_empty + buf, ((uint32_t)(uc >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                }
+                const uint32_t d_addr = tmem_base + (uint32_t)(buf * 256);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % BA_STAGES;
+                    const uint32_t parity = (uint32_t)(it / BA_STAGES) & 1u;
+                    mbar_wait(a_part + s, parity);                       // this CTA's half of the G operand
+                    BF_TRACE(it, 6);
+                    if (!leader) { mbar_arrive_remote_default(a_peer + s, 0); continue; }
+                    mbar_wait(a_peer + s, parity);                       // the peer's half
+                    BF_TRACE(it, 7);
+                    mbar_wait(b_full + s, parity);
+                    BF_TRACE(it, 8);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(ring + s * BA_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BW_BK / 16; ++k) {
+                        uint64_t ah, al;
+                        if (OP == BW_DF1) {
+                            ah = umma_desc_sw128(st + k * 32);
+                            al = umma_desc_sw128(st + BW_PART_BYTES + k * 32);
+                        } else {
+                            ah = umma_desc_mn_sw128(st + k * 2048);
+                            al = umma_desc_mn_sw128(st + BW_PART_BYTES + k * 2048);
+                        }
+                        const uint64_t bh = umma_desc_sw128(st + 2 * BW_PART_BYTES + k * 32);
+                        const uint64_t bl = umma_desc_sw128(st + 3 * BW_PART_BYTES + k * 32);
+                        umma2_bf16(d_addr, ah, bh, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                        if (P.three_pass) {
+                            umma2_bf16(d_addr, al, bh, idesc, 1u);
+                            umma2_bf16(d_addr, ah, bl, idesc, 1u);
+                        }
+                    }
+                    umma2_commit(empty + s);
+                    BF_TRACE(it, 9);
+                }
+                if (leader) umma2_commit(t_full + buf);
+            }
+        }
+    } else if (warp < BF_CONV0) {
+        // ================= epilogue: TMEM -> scale -> red.add into (B, D, N) =================
+        const int quarter = warp & 3;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        int uc = 0;
+        for (int u = u_begin; u < u_end; u += u_step, ++uc) {
+            int b, m0, kb0, kb1;
+            decode(u, b, m0, kb0, kb1);
+            const int buf = uc & 1;
+            const int r = m0 + quarter * 32 + lane;
+            int col = -1;
+            if (r < P.M) {
+                if (OP == BW_DF1) {
+                    col = r;
+                } else {
+                    int y, x;
+                    tile_inv(r, P.Wp, y, x);
+                    if (y < P.H && x < P.W) col = y * P.W + x;
+                }
+            }
+            float* dst = P.out + (long long)b * P.D * P.N + col;
+            mbar_wait(t_full + buf, (uint32_t)(uc >> 1) & 1u);
+            tc_fence_after();
+            for (int c0 = 0; c0 < P.D; c0 += 32) {
+                float v[32];
+                tmem_ld32(lane_addr + (uint32_t)(buf * 256 + c0), v);
+                tmem_ld_wait();
+                if (col >= 0) {
+                    float* d = dst + (long long)c0 * P.N;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j, d += P.N) red_add_f32(d, v[j] * P.scale);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(t_empty + buf, 0);
+        }
+    } else if (warp < BF_CONV0 + BF_CONV_WARPS) {
+        // ================= converters =================
+        // thread = one patch row (8 consecutive targets of one map row) of one query; 4 sweeps cover the box
+        constexpr int C = (OP == BW_DF1) ? 64 : 128;        // targets per row of the box
+        constexpr int CPR = C / 8;                          // patch rows per box row
+        constexpr int RPS = 256 / CPR;                      // box rows per sweep
+        constexpr int SWEEPS = ROWS / RPS;                  // 4
+        const int ctid = threadIdx.x - BF_CONV0 * 32;
+        const int j = ctid % CPR, r0 = ctid / CPR, c = j * 8;
+        const uint32_t ring_s = smem_u32(ring), rring_s = smem_u32(rring), cring_s = smem_u32(cring);
+        const uint32_t raw_off = (uint32_t)(r0 * C + c) * 4u;
+        const uint32_t a_off = (uint32_t)((c >> 6) * (ROWS * 128) + r0 * 128 + (((((c & 63) >> 3)) ^ (r0 & 7)) << 4));
+        // this thread's cells inside the coarse boxes: patch pg of 4-patch group g (dF1: one group)
+        const int g = j >> 3, pg = (j >> 1) & 3;
+        const uint32_t c1_off = (uint32_t)(BA_C1 + (g * ROWS + r0) * 64 + pg * 16);
+        const uint32_t c2_off = (uint32_t)(BA_C2 + (g * ROWS + r0) * 32 + pg * 8);
+        const uint32_t c3_off = (uint32_t)(BA_C3 + (g * ROWS + r0) * 16 + pg * 4);
+        int n_it = 0;
+        for (int u = u_begin; u < u_end; u += u_step) {
+            int b, m0, kb0, kb1;
+            decode(u, b, m0, kb0, kb1);
+            n_it += kb1 - kb0;
+        }
+        for (int it = 0; it < n_it; ++it) {
+            const int s = it % BA_STAGES, cs = it % BA_CSTAGES, rs = it % BA_RSTAGES;
+            float w1[SWEEPS][4];
+            if (ctid == 0) BF_TRACE(it, 2);
+            if (nlev > 1) {
+                mbar_wait(c_full + cs, (uint32_t)(it / BA_CSTAGES) & 1u);
+                if (ctid == 0) BF_TRACE(it, 0);
+                const uint32_t cb = cring_s + (uint32_t)(cs * BA_CBYTES);
+#pragma unroll
+                for (int i = 0; i < SWEEPS; ++i) {
+                    float c1[4], c2a = 0.f, c2b = 0.f, c3 = 0.f;
+                    lds128f(cb + c1_off + i * (RPS * 64), c1);
+                    if (nlev > 2) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(c2a), "=f"(c2b) : "r"(cb + c2_off + i * (RPS * 32)));
+                    if (nlev > 3) asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(c3) : "r"(cb + c3_off + i * (RPS * 16)));
+                    const float w2a = c2a + 0.25f * c3, w2b = c2b + 0.25f * c3;
+                    w1[i][0] = 0.25f * (c1[0] + 0.25f * w2a);
+                    w1[i][1] = 0.25f * (c1[1] + 0.25f * w2a);
+                    w1[i][2] = 0.25f * (c1[2] + 0.25f * w2b);
+                    w1[i][3] = 0.25f * (c1[3] + 0.25f * w2b);
+                }
+            }
+            const uint32_t st = ring_s + (uint32_t)(s * BA_STAGE_BYTES), rb = rring_s + (uint32_t)(rs * BA_RAW_BYTES);
+            mbar_wait(raw_full + rs, (uint32_t)(it / BA_RSTAGES) & 1u);
+            if (ctid == 0) BF_TRACE(it, 3);
+            float xs[SWEEPS][8];
+#pragma unroll
+            for (int i = 0; i < SWEEPS; ++i) {
+                lds128f(rb + raw_off + i * (RPS * C * 4), xs[i]);
+                lds128f(rb + raw_off + i * (RPS * C * 4) + 16, xs[i] + 4);
+            }
+            uint32_t h[SWEEPS][4], lo[SWEEPS][4];
+#pragma unroll
+            for (int i = 0; i < SWEEPS; ++i) {
+                float* x = xs[i];
+                if (nlev > 1) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) x[k] += w1[i][k >> 1];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);
+                    h[i][k] = *reinterpret_cast<const uint32_t*>(&hh);
+                    const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * k] - __uint_as_float(h[i][k] << 16),
+                                                                    x[2 * k + 1] - __uint_as_float(h[i][k] & 0xffff0000u));
+                    lo[i][k] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
+            }
+            // the box is in registers: hand its buffer back (the vote makes the arrival depend on the converted values,
+            // i.e. on the shared loads having completed), THEN wait for the operand stage -- the conversion above overlaps
+            // the MMAs that still read it
+            {
+                const bool landed = __any_sync(0xffffffffu, lo[SWEEPS - 1][3] != 0x7fc1dead);
+                if (lane == 0 && landed) { mbar_arrive(raw_empty + rs); if (nlev > 1) mbar_arrive(c_empty + cs); }
+            }
+            mbar_wait(empty + s, ((uint32_t)(it / BA_STAGES) & 1u) ^ 1u);
+            if (ctid == 0) BF_TRACE(it, 4);
+#pragma unroll
+            for (int i = 0; i < SWEEPS; ++i) {
+                sts128(st + a_off + i * (RPS * 128), h[i]);
+                if (P.three_pass) sts128(st + a_off + BW_PART_BYTES + i * (RPS * 128), lo[i]);
+            }
+            fence_proxy_async_smem();                       // generic-proxy writes -> the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_part + s);
+            if (ctid == 0) BF_TRACE(it, 5);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+    }
+}
+
 // ---------------------------------------------------------------- host side
 static int encode_bf16(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
                        const cuuint64_t* strides_bytes, const cuuint32_t* box) {
@@ -845,6 +1190,47 @@ static int launch_bwd_fold_gemm(const CUtensorMap* maps, BwdParams P, const Fold
     return FC_OK;
 }
 
+template <int OP>
+static int launch_bwd_fold_aligned(const CUtensorMap* maps, const CoarseMaps& CMp, BwdParams P, const CoarseGeo& G, int B, cudaStream_t s) {
+    const size_t smem = 1024 + (size_t)BA_STAGES * BA_STAGE_BYTES + (size_t)BA_RSTAGES * BA_RAW_BYTES + (size_t)BA_CSTAGES * BA_CBYTES + 256;
+    FC_SMEM_ATTR_ONCE((tc_bwd_fold_aligned_kernel<OP>), smem);
+    static std::atomic<int> clusters_of[64];
+    int dev = 0;
+    FC_CUDA(cudaGetDevice(&dev));
+    int n_clusters = clusters_of[dev & 63].load(std::memory_order_acquire);
+    if (n_clusters == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(sm_count_cached() & ~1); cfg.blockDim = dim3(BA_THREADS); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        FC_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, tc_bwd_fold_aligned_kernel<OP>, &cfg));
+        clusters_of[dev & 63].store(n_clusters, std::memory_order_release);
+    }
+    if (n_clusters < 1) { set_error("fc_build_bwd: no CTA pair of the tensor-core kernel fits on this device"); return FC_ECUDA; }
+    P.ksplit = pick_ksplit(B * P.mp, P.kb_total, n_clusters);
+    P.units = B * P.mp * P.ksplit;
+    if (n_clusters > P.units) n_clusters = P.units;
+    tc_bwd_fold_aligned_kernel<OP><<<dim3(2 * n_clusters), BA_THREADS, smem, s>>>(maps[0], maps[2], maps[3], CMp, P, G);
+    FC_LAUNCH_CHECK("tc_bwd_fold_aligned_kernel");
+    return FC_OK;
+}
+
+// the coarse levels 1..3 of the gradient pyramid as 5-D tensors {8 cells of a patch sub-row, 2 sub-rows, patches, N, B}
+// with the boxes tc_bwd_fold_aligned_kernel fetches per k-block: [rows][2 patches x 8], [rows][8], [rows][4] cells
+static int encode_coarse(CoarseMaps& CMp, float* gpyr, const Pyramid& pyr, int rows) {
+    for (int l = 1; l < pyr.L && l < 4; ++l) {
+        const cuuint64_t ms = (cuuint64_t)pyr.lv[l].Hp * pyr.lv[l].Wp;
+        const cuuint64_t dims[5] = {8, 2, ms / 16, (cuuint64_t)pyr.N, (cuuint64_t)pyr.B};
+        const cuuint64_t str[4] = {32, 64, ms * 4, (cuuint64_t)pyr.N * ms * 4};
+        const cuuint32_t box[5] = {l == 3 ? 4u : 8u, 1, l == 1 ? 2u : 1u, (cuuint32_t)rows, 1};
+        if (int e = encode_tiled_cached(&CMp.m[l - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, gpyr + pyr.lv[l].offset, dims, str, box,
+                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE)) return e;
+    }
+    return FC_OK;
+}
+
 int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float* d2, const Pyramid& pyr,
                  int D, int H, int W, int math, void* ws, size_t ws_bytes, cudaStream_t s) {
     const int B = pyr.B, N = pyr.N, Wp = pyr.lv[0].Wp, NP = pyr.lv[0].Hp * Wp;
@@ -862,6 +1248,13 @@ int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float
     float* g0 = gpyr + pyr.lv[0].offset;
 
     const bool fused = bwd_fold_in_gemm();
+    // patch-row aligned maps (a multiple of 4 patches per map row, at most 4 levels) take the kernel with TMA-fetched coarse
+    // boxes; FLOWCORR_BWD_FUSED=2 keeps the generic fold-in-GEMM kernel for them too
+    const bool aligned = fused && tunables().bwd_fused == 1 && pyr.L <= 4 && ((Wp >> 3) & 3) == 0;
+    CoarseGeo CG{};
+    CG.L = pyr.L;
+    for (int l = 0; l < pyr.L && l < 4; ++l) CG.ppr[l] = pyr.lv[l].Wp >> 3;
+    CoarseMaps CMp{};
     FoldSrc FS{};
     FS.L = pyr.L;
     for (int l = 0; l < pyr.L; ++l) {
@@ -936,7 +1329,10 @@ int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float
         if (int e = encode_bf16(&maps[2], f2_hi, 2, bdims, bstr, bbox)) return e;
         if (int e = encode_bf16(&maps[3], three ? f2_lo : f2_hi, 2, bdims, bstr, bbox)) return e;
         P.out = d1; P.M = N; P.kb_total = (NP + BW_BK - 1) / BW_BK; P.mp = (N + 2 * BW_BM - 1) / (2 * BW_BM);
-        if (int e = fused ? launch_bwd_fold_gemm<BW_DF1>(maps, P, FS, B, s) : launch_bwd_gemm<BW_DF1>(maps, P, B, s)) return e;
+        if (aligned) {
+            if (int e = encode_coarse(CMp, gpyr, pyr, BW_BM)) return e;
+            if (int e = launch_bwd_fold_aligned<BW_DF1>(maps, CMp, P, CG, B, s)) return e;
+        } else if (int e = fused ? launch_bwd_fold_gemm<BW_DF1>(maps, P, FS, B, s) : launch_bwd_gemm<BW_DF1>(maps, P, B, s)) return e;
     }
     if (d2) {
         FC_CUDA(cudaMemsetAsync(d2, 0, (size_t)B * D * N * 4, s));
@@ -952,7 +1348,10 @@ int tc_build_bwd(float* gpyr, const float* f1, const float* f2, float* d1, float
         if (int e = encode_bf16(&maps[2], f1_hi, 2, bdims, bstr, bbox)) return e;
         if (int e = encode_bf16(&maps[3], three ? f1_lo : f1_hi, 2, bdims, bstr, bbox)) return e;
         P.out = d2; P.M = NP; P.kb_total = (N + BW_BK - 1) / BW_BK; P.mp = (NP + 2 * BW_BM - 1) / (2 * BW_BM);
-        if (int e = fused ? launch_bwd_fold_gemm<BW_DF2>(maps, P, FS, B, s) : launch_bwd_gemm<BW_DF2>(maps, P, B, s)) return e;
+        if (aligned) {
+            if (int e = encode_coarse(CMp, gpyr, pyr, BW_BK)) return e;
+            if (int e = launch_bwd_fold_aligned<BW_DF2>(maps, CMp, P, CG, B, s)) return e;
+        } else if (int e = fused ? launch_bwd_fold_gemm<BW_DF2>(maps, P, FS, B, s) : launch_bwd_gemm<BW_DF2>(maps, P, B, s)) return e;
     }
     return FC_OK;
 }

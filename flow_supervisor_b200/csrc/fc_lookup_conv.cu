@@ -223,8 +223,8 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
         auto issue = [&](int i) {
             const int bb = i % LC_NB, db = i & 1;
             mbar_wait(b_part + bb, (uint32_t)(i / LC_NB) & 1u);                 // this CTA's half of the B operand
-            if (!leader) { mbar_arrive_remote_release(b_peer + bb, 0); return; }
-            mbar_wait_cluster(b_peer + bb, (uint32_t)(i / LC_NB) & 1u);         // the peer's half
+            if (!leader) { mbar_arrive_remote_default(b_peer + bb, 0); return; }
+            mbar_wait(b_peer + bb, (uint32_t)(i / LC_NB) & 1u);                 // the peer's half
             mbar_wait_cluster(t_empty + db, ((uint32_t)(i >> 1) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t d_addr = tmem_base + (db ? LC_D1 : LC_D0);

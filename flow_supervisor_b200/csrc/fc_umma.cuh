@@ -65,6 +65,16 @@ __device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(addr) : "r"(smem_u32(bar)), "r"(rank));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(addr) : "memory");
 }
+// arrive on the barrier at this offset in CTA `rank` with the instruction's default semantics (release at CTA scope) -- the
+// form CUTLASS' ClusterBarrier::arrive(cta_id) uses for consumer -> producer hand-offs between the CTAs of a 2-SM MMA.
+// The writes it publishes here went to the ARRIVING CTA's own shared memory and were already made visible to the async
+// proxy by their writers (fence.proxy.async) before the local barrier this thread waited on; no cluster-wide fence (the
+// MEMBAR a release.cluster costs, ~700 cycles per k-block in the backward GEMMs) is needed for the tensor core to read them.
+__device__ __forceinline__ void mbar_arrive_remote_default(uint64_t* bar, uint32_t rank) {
+    uint32_t addr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(addr) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(addr) : "memory");
+}
 // parity wait with acquire semantics at cluster scope (arrivals come from both CTAs of the pair)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     asm volatile(

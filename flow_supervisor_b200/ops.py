@@ -46,6 +46,21 @@ def level_padded(pyramid: Tensor, B: int, H: int, W: int, L: int) -> List[Tensor
     return out
 
 
+def clear_pads_(pyramid: Tensor, B: int, H: int, W: int, L: int) -> Tensor:
+    """Zero the pad rows / pad columns of every level IN PLACE (the pyramid invariant of include/flowcorr.h).  The library's
+    own kernels keep it; a caller that fills a (gradient) pyramid itself -- tests, probes -- restores it with this."""
+    off, Q = 0, B * H * W
+    for h, w, wp in geometry(H, W, L):
+        hp = _hp(h)
+        n = Q * hp * wp
+        t = pyramid[off:off + n].view(Q, hp // 2, wp // 8, 2, 8)                    # (q, row pair, patch, sub-row, x)
+        y = 2 * torch.arange(hp // 2, device=pyramid.device)[:, None, None, None] + torch.arange(2, device=pyramid.device)[None, None, :, None]
+        x = 8 * torch.arange(wp // 8, device=pyramid.device)[None, :, None, None] + torch.arange(8, device=pyramid.device)[None, None, None, :]
+        t.mul_(((y < h) & (x < w)).to(pyramid.dtype)[None])
+        off += n
+    return pyramid
+
+
 def level_views(pyramid: Tensor, B: int, H: int, W: int, L: int) -> List[Tensor]:
     """The reference's ``corr_pyramid`` list ((B*N, 1, Hl, Wl), corr.py:14-27), gathered out
     of the patch layout (copies; nothing on the hot path reads them)."""

@@ -142,28 +142,33 @@ def _build_bwd_switch(fsb, value):
                                      ((2, 128, 24, 40), 3), ((1, 64, 64, 96), 6)])
 @pytest.mark.parametrize("math", ["3xbf16", "bf16"])
 def test_tc_backward_fold_in_gemm_matches_the_separate_fold_pass(fsb, shape, L, math):
-    """fc_build_bwd's default (fold + bf16 split inside the GEMMs, gradient pyramid only read) against the round-1
-    pipeline (fold + pack pass, GEMMs from the in-place planes; FLOWCORR_BWD_FUSED=0): same products of the same
-    rounded operands, only the accumulation order of the split-K pieces differs -> <= 2e-6 of the gradient's
-    max; and the default leaves the gradient pyramid untouched."""
+    """fc_build_bwd's default (fold + bf16 split inside the GEMMs, gradient pyramid only read; maps with a multiple of 4
+    patches per row take the kernel whose coarse cells arrive as TMA boxes -- (46, 62), (19, 27), (47, 156) here --, the
+    others the generic one) against the generic kernel (FLOWCORR_BWD_FUSED=2) and the round-1 pipeline (fold + pack pass,
+    GEMMs from the in-place planes; FLOWCORR_BWD_FUSED=0): same products of the same rounded operands, only the
+    accumulation order of the split-K pieces differs -> <= 2e-6 of the gradient's max; and the default leaves the
+    gradient pyramid untouched."""
     from flow_supervisor_b200 import _lib, ops
     B, D, H, W = shape
     gen = torch.Generator().manual_seed(11)
     f1 = (1.57 * torch.randn(B, D, H, W, generator=gen)).cuda()
     f2 = (1.57 * torch.randn(B, D, H, W, generator=gen) + 0.1).cuda()
-    src = torch.randn(ops.pyramid_numel(B, H, W, L), generator=gen).cuda()
+    src = ops.clear_pads_(torch.randn(ops.pyramid_numel(B, H, W, L), generator=gen).cuda(), B, H, W, L)
     m = _lib.MATH_TC_3XBF16 if math == "3xbf16" else _lib.MATH_TC_BF16
     try:
         gp = src.clone()
         a1, a2 = ops.build_bwd(gp, f1, f2, L, m)
         torch.cuda.synchronize()
         assert torch.equal(gp, src), "the default backward must not modify the gradient pyramid"
-        _build_bwd_switch(fsb, 0)
-        b1, b2 = ops.build_bwd(src.clone(), f1, f2, L, m)
+        others = []
+        for sw in (2, 0):            # 2: the generic fold-in-GEMM kernel (any map), 0: the round-1 pipeline
+            _build_bwd_switch(fsb, sw)
+            others.append(ops.build_bwd(src.clone(), f1, f2, L, m))
     finally:
         _build_bwd_switch(fsb, 1)
-    for a, b in ((a1, b1), (a2, b2)):
-        assert float((a - b).abs().max() / b.abs().max()) < 2e-6
+    for b1, b2 in others:
+        for a, b in ((a1, b1), (a2, b2)):
+            assert float((a - b).abs().max() / b.abs().max()) < 2e-6
 
 
 def test_tc_backward_takes_maps_past_the_old_row_in_shared_memory_limit(fsb):
@@ -179,6 +184,7 @@ def test_tc_backward_takes_maps_past_the_old_row_in_shared_memory_limit(fsb):
     # a sparse gradient pyramid (a dense one is 5.7 GB of randn): 2 M random cells over all levels
     idx = torch.randint(0, src.numel(), (2_000_000,), generator=gen).cuda()
     src[idx] = torch.randn(idx.numel(), generator=gen).cuda()
+    ops.clear_pads_(src, B, H, W, L)
     d1, d2 = ops.build_bwd(src.clone(), f1, f2, L, _lib.MATH_TC_3XBF16)
     r1, r2 = ops.build_bwd(src.clone(), f1, f2, L, _lib.MATH_FP32)
     for a, b in ((d1, r1), (d2, r2)):

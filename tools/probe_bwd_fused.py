@@ -24,11 +24,12 @@ def one(B, D, H, W, reps=10, check_fp32=True):
     f1 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
     f2 = (1.57 * torch.randn(B, D, H, W, generator=g)).cuda()
     numel = ops.pyramid_numel(B, H, W, L)
-    src = torch.randn(numel, device="cuda")
+    src = ops.clear_pads_(torch.randn(numel, device="cuda"), B, H, W, L)      # pads of a gradient pyramid are zeros
     gp = src.clone()
     out = {"geometry": f"B={B} D={D} {H}x{W}"}
     res = {}
-    for name, v in (("fused", 1), ("separate", 0)):
+    # 1: default (patch-row aligned maps take the TMA-coarse-box kernel), 2: the generic fold-in-GEMM kernel, 0: round-1 pipeline
+    for name, v in (("fused", 1), ("generic", 2), ("separate", 0)):
         switch(v)
         gp.copy_(src)
         try:

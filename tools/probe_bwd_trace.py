@@ -26,7 +26,9 @@ lib = _lib.load()
 buf = np.zeros((2, 256, SLOTS), dtype=np.uint64)
 lib.fc_debug_bwd_trace.argtypes = [ctypes.c_void_p]
 assert lib.fc_debug_bwd_trace(buf.ctypes.data) == 0
-names = ["box_free", "stage_free", "conv_ready", "box_landed", "conv_stage_free", "stored", "own_half", "peer_half",
+# aligned kernel (default for these maps): slot 0 = coarse boxes landed, slot 4 = all converters past the named barrier;
+# generic kernel (FLOWCORR_BWD_FUSED=2): slot 0 = box buffer free, slot 4 = operand stage free
+names = ["coarse/box_free", "stage_free", "conv_ready", "box_landed", "barrier/stage_free", "stored", "own_half", "peer_half",
          "features", "issued"]
 print(f"B={B} D={D} {H}x{W}, CTA 0 (leader of pair 0); clock64 cycles")
 for op in (0, 1):
