@@ -753,9 +753,16 @@ tc_bwd_fold_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
 // [rows][2 patches x 8], [rows][8], [rows][4] cells -- that the TMA unit can fetch: no index arithmetic, no global loads
 // and no validity logic in the converter threads (pad cells of the gradient pyramid are zeros and an invalid cell's
 // parents are pads too, so `c1 + (c2 + c3/4)/4` needs no masks), ~270 instead of ~600 dependent instructions per thread
-// and k-block.  The fp32 box is converted IN PLACE (32 KB of fp32 = 16 + 16 KB of bf16 planes, every converter thread
-// holds its part in registers across a named barrier), which makes room for THREE 64 KB stages + a 2-deep ring of
-// coarse boxes (14 KB each).  Everything else (MMA issue, relay, epilogue, round-robin units) is tc_bwd_fold_kernel's.
+// and k-block.  What the timeline of the generic kernel asked for (tools/probe_bwd_trace.py) is built in:
+//   * the fp32 boxes have their own 2-deep ring, filled by their own producer warp as soon as the converters hold the
+//     previous box in registers -- their DRAM latency (~2200 cycles under load) is outside the loop MMAs retire ->
+//     operand stage free -> converted -> MMAs;
+//   * a converter thread reads its part of the box, folds and splits it BEFORE it waits for the operand stage, so only
+//     the 8 shared stores sit between "the MMAs two k-blocks back retired" and "this k-block's operand is ready";
+//   * the peer CTA's relay arrives on the leader's barrier with the instruction's default (CTA-scope release) semantics:
+//     a release at cluster scope cost a MEMBAR of ~700 cycles per k-block (see mbar_arrive_remote_default).
+// Measured (B = 6, 54x128 / 46x96): 0.82 / 0.36 ms against 0.97 / 0.43 for the generic kernel and 1.20 / 0.50 for the
+// round-1 pipeline; ~1950 cycles per k-block, the 12 MMAs of a k-block retire in ~1850.
 constexpr int BA_STAGES = 2;                                             // operand stages: A_hi | A_lo | B_hi | B_lo = 64 KB
 constexpr int BA_STAGE_BYTES = 4 * BW_PART_BYTES;
 constexpr int BA_RSTAGES = 2;                                            // fp32 boxes in flight (32 KB each)
