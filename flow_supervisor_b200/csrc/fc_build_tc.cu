@@ -134,6 +134,11 @@ __device__ __forceinline__ void st_v8(float* dst, const float* v) {
 }
 
 // 8 / 4 consecutive volume elements from fp32 registers: fp32 volume = 32 / 16 bytes, bf16 volume = 16 / 8 bytes (RN)
+// explicit shared-space 16-byte store: through a generic pointer the staging writes compiled to ST.E.128, which ride the
+// global pipeline's long scoreboard -- every chunk's proxy fence then waited for them (ncu: long_sb on the fence / BSYNC)
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     const __nv_bfloat162 v(__float2bfloat16_rn(lo), __float2bfloat16_rn(hi));
     return *reinterpret_cast<const uint32_t*>(&v);
@@ -458,32 +463,32 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         ++use;
                         if (lane == 0) tma_wait_group_read<NBUF - 1>();   // the store that last read this box is done
                         __syncwarp();
+                        const uint32_t sb32 = smem_u32(sbuf);
                         if (VB) {
                             // bf16 volume: rows of 64 bytes (SWIZZLE_64B box of 32 columns) or 32 bytes (plain box of 16)
-                            uint4* sb = reinterpret_cast<uint4*>(sbuf);
                             if (rem >= 32) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
-                                    sb[lane * 4 + (k ^ ((lane >> 1) & 3))] =
-                                        make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
-                                                   pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+                                    st_shared_v4(sb32 + 16u * (uint32_t)(lane * 4 + (k ^ ((lane >> 1) & 3))),
+                                                 pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                                                 pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
                             } else {
 #pragma unroll
                                 for (int k = 0; k < 2; ++k)
-                                    sb[lane * 2 + k] =
-                                        make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
-                                                   pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+                                    st_shared_v4(sb32 + 16u * (uint32_t)(lane * 2 + k),
+                                                 pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                                                 pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
                             }
                         } else if (rem >= 32) {
 #pragma unroll
                             for (int k = 0; k < 8; ++k)
-                                *reinterpret_cast<float4*>(sbuf + lane * 32 + ((k ^ (lane & 7)) << 2)) =
-                                    make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                                st_shared_v4(sb32 + 4u * (uint32_t)(lane * 32 + ((k ^ (lane & 7)) << 2)), __float_as_uint(v[4 * k]),
+                                             __float_as_uint(v[4 * k + 1]), __float_as_uint(v[4 * k + 2]), __float_as_uint(v[4 * k + 3]));
                         } else {
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                *reinterpret_cast<float4*>(sbuf + lane * 16 + ((k ^ ((lane >> 1) & 3)) << 2)) =
-                                    make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                                st_shared_v4(sb32 + 4u * (uint32_t)(lane * 16 + ((k ^ ((lane >> 1) & 3)) << 2)), __float_as_uint(v[4 * k]),
+                                             __float_as_uint(v[4 * k + 1]), __float_as_uint(v[4 * k + 2]), __float_as_uint(v[4 * k + 3]));
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
