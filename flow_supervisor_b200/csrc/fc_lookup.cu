@@ -53,21 +53,22 @@ __device__ __forceinline__ float lds_f32b(uint32_t addr) {
 
 // Raw per-lane inputs of one tile: coordinates and the output gradients of the taps this warp
 // needs.  Loaded one tile AHEAD (nothing here depends on the coordinates' values).
-template <int RADIUS, int WI>
+// The three warps of a group run the SAME code on their own third of the window columns (c_lo is a run-time value):
+// column-specialised copies of the loop made the kernel 4160 instructions = 66 KB, and ncu showed 27 % of the stall
+// samples waiting for instruction fetch with a time that did not move when the warps per SM were doubled.
+template <int RADIUS>
 struct LbTile {
     static constexpr int R = 2 * RADIUS + 1;
     static constexpr int NCOL = R + 1;
     static constexpr int CPW = (NCOL + LB_GWARPS - 1) / LB_GWARPS;      // window columns per warp (4 for r = 4)
-    static constexpr int C_LO = WI * CPW < NCOL ? WI * CPW : NCOL;      // this warp's columns [C_LO, C_HI)
-    static constexpr int C_HI = C_LO + CPW < NCOL ? C_LO + CPW : NCOL;
-    static constexpr int NT = C_HI > C_LO ? C_HI - C_LO + 1 : 0;       // x-taps a = C_LO - 1 + k, k < NT
+    static constexpr int NT = CPW + 1;                                  // x-taps a = c_lo - 1 + k, k < NT
     int level, gq;
     bool live;
     float cx, cy;                                                        // raw (unscaled) coordinates
-    float gv[NT > 0 ? NT : 1][R];
+    float gv[NT][R];
     const float* gptr;
 
-    __device__ __forceinline__ void load(const LookupParams& P, const TileIt& it, int lane) {
+    __device__ __forceinline__ void load(const LookupParams& P, const TileIt& it, int lane, int c_lo) {
         level = it.level(P.L);
         gq = it.qt * QT + lane;
         live = gq < P.Q;
@@ -82,19 +83,21 @@ struct LbTile {
         gptr = P.io + ((long long)b * P.K + level * R * R) * P.N + p;
 #pragma unroll
         for (int k = 0; k < NT; ++k) {
-            const int a = C_LO - 1 + k;                                  // compile-time
+            const int a = c_lo - 1 + k;
+            const bool ok = live && a >= 0 && a < R;
+            const float* g = gptr + (long long)(ok ? a * R : 0) * P.N;
 #pragma unroll
-            for (int i = 0; i < R; ++i)
-                gv[k][i] = (live && a >= 0 && a < R) ? __ldg(gptr + (long long)(a * R + i) * P.N) : 0.f;
+            for (int i = 0; i < R; ++i) gv[k][i] = ok ? __ldg(g + (long long)i * P.N) : 0.f;
         }
     }
 };
 
-template <int RADIUS, int CM, int WI>
-__device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams& P, int n_tiles, int g, int lane,
-                                        uint32_t gbase) {
-    using T = LbTile<RADIUS, WI>;
-    constexpr int R = T::R, C_LO = T::C_LO;
+template <int RADIUS, int CM>
+__device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams& P, int n_tiles, int g, int WI, int lane,
+                                        uint32_t gbase, volatile uint8_t* reg_flags) {
+    using T = LbTile<RADIUS>;
+    constexpr int R = T::R;
+    const int C_LO = WI * T::CPW;                                        // this warp's window columns [C_LO, C_LO + CPW)
     const int tg = WI * 32 + lane;                                       // thread index inside the group
     const int n_groups = gridDim.x * LB_GROUPS;
     int tile = blockIdx.x * LB_GROUPS + g;
@@ -104,11 +107,11 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
     TileIt ti;
     ti.qt = tile / L; ti.slot = tile - ti.qt * L; ti.qm = ti.qt % L;
     T cur;
-    cur.load(P, ti, lane);
+    cur.load(P, ti, lane, C_LO);
     for (int it = 0;; ++it) {
         const int next = tile + n_groups;
         T nxt = cur;
-        if (LB_PREFETCH && next < n_tiles) { ti.advance(hop_q, hop_l, hop_qm, L); nxt.load(P, ti, lane); }   // in flight while this tile is processed
+        if (LB_PREFETCH && next < n_tiles) { ti.advance(hop_q, hop_l, hop_qm, L); nxt.load(P, ti, lane, C_LO); }   // in flight while this tile is processed
 
         const int level = cur.level;
         const float cx = __fmul_rn(cur.cx, P.inv_scale[level]), cy = __fmul_rn(cur.cy, P.inv_scale[level]);
@@ -118,20 +121,30 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
         int y0[R]; float wy0[R], wy1[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) axis_tap<CM>(cy, j - RADIUS, P.ay[level], y0[j], wy0[j], wy1[j]);
-        int x0a[R]; float wx0a[R], wx1a[R];
-#pragma unroll
-        for (int a = 0; a < R; ++a) axis_tap<CM>(cx, a - RADIUS, P.ax[level], x0a[a], wx0a[a], wx1a[a]);
+        // x: this warp's taps a = C_LO - 1 + k (weights 0 outside [0, R)), plus the first and the last tap for the box
+        int x0o[T::NT]; float wx0o[T::NT], wx1o[T::NT];
+        int x_first, x_last;
+        { float d0, d1; axis_tap<CM>(cx, -RADIUS, P.ax[level], x_first, d0, d1); axis_tap<CM>(cx, RADIUS, P.ax[level], x_last, d0, d1); }
         bool regular = true;
 #pragma unroll
-        for (int j = 1; j < R; ++j) regular = regular && (y0[j] == y0[0] + j) && (x0a[j] == x0a[0] + j);
+        for (int k = 0; k < T::NT; ++k) {
+            const int a = C_LO - 1 + k;
+            axis_tap<CM>(cx, a - RADIUS, P.ax[level], x0o[k], wx0o[k], wx1o[k]);
+            if (a < 0 || a >= R) { wx0o[k] = 0.f; wx1o[k] = 0.f; }
+            else regular = regular && (x0o[k] == x_first + a);
+        }
+#pragma unroll
+        for (int j = 1; j < R; ++j) regular = regular && (y0[j] == y0[0] + j);
+        // every x-tap is checked by one of the three warps: the query is regular if all of them say so
+        reg_flags[tg] = regular ? 1 : 0;
 
         // footprint box as the forward sizes it, but clamped to non-negative tensor coordinates:
         // TMA loads zero-fill at negative coordinates, TMA stores / reductions TRAP there
         // (tools/probes/tma_reduce_probe.cu), while boxes overhanging the far edge are clipped
         // ... and, like the forward's, clipped to the padded map at the far edge as well
-        const int rp_lo = max(y0[0] >> 1, 0), pc_lo = max(x0a[0] >> 3, 0);
+        const int rp_lo = max(y0[0] >> 1, 0), pc_lo = max(x_first >> 3, 0);
         const int n_rp = min(min((y0[R - 1] + 1) >> 1, P.nrp[level] - 1) - rp_lo + 1, 6);
-        const int n_pc = min(min((x0a[R - 1] + 1) >> 3, P.npc[level] - 1) - pc_lo + 1, 3);
+        const int n_pc = min(min((x_last + 1) >> 3, P.npc[level] - 1) - pc_lo + 1, 3);
         const int sel = (n_rp > 0 && n_pc > 0) ? lk_shape(n_rp, n_pc) : 0;
         const int pitch = 64 * n_pc;
         const int ybase = 2 * rp_lo, xbase = 8 * pc_lo;
@@ -143,6 +156,7 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
         const uint32_t stage = gbase + (uint32_t)((it % LB_STAGES) * LB_STAGE_BYTES);
         tma_wait_group_read<LB_STAGES - 1>();                            // every lane waits for its own reduce-adds
         group_sync(g);
+        regular = reg_flags[lane] && reg_flags[32 + lane] && reg_flags[64 + lane];
 #pragma unroll
         for (int i = 0; i < LB_STAGE_BYTES / 16 / (32 * LB_GWARPS); ++i)
             asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n" ::"r"(stage + 16u * (uint32_t)(tg + i * 32 * LB_GWARPS)), "f"(0.f) : "memory");
@@ -153,15 +167,16 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
             // window row n (relative to ybase) sits at (n >> 1) * pitch + (n & 1) * 32 bytes
             const int n0 = y0[0] - ybase;                                  // 0 or 1; negative above the map
 #pragma unroll
-            for (int k = 0; k + 1 < T::NT; ++k) {
-                constexpr int dummy = 0; (void)dummy;
-                const int j = C_LO + k;                                    // window column (compile-time)
-                const int x = x0a[0] + j, xr = x - xbase;                  // 0 <= xr <= 16 when x >= 0
+            for (int k = 0; k < T::CPW; ++k) {
+                const int j = C_LO + k;                                    // window column
+                if (j >= T::NCOL) break;
+                const int x = x_first + j, xr = x - xbase;                 // 0 <= xr <= 16 when x >= 0
                 const bool xin = (x >= 0) && (x < Wl);
                 const uint32_t col = wq + 4u * (uint32_t)(xr + (xr & ~7));
-                // horizontal weights: own tap a = j (left corner), tap a = j - 1 (right corner)
-                const float wl = (j < R) ? wx0a[j < R ? j : 0] : 0.f;
-                const float wr = (j >= 1) ? wx1a[j >= 1 ? j - 1 : 0] : 0.f;
+                // horizontal weights: own tap a = j (left corner, index k + 1), tap a = j - 1 (right corner, index k);
+                // taps outside [0, R) carry zero weights and zero gradients
+                const float wl = wx0o[k + 1];
+                const float wr = wx1o[k];
                 uint32_t rofs = (uint32_t)((n0 >> 1) * pitch + (n0 & 1) * 32);     // wraps for n0 < 0: never stored
                 uint32_t step = (n0 & 1) ? (uint32_t)pitch - 32u : 32u;
                 float hprev = 0.f;
@@ -214,7 +229,7 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
         if (next >= n_tiles) break;
         tile = next;
         if (LB_PREFETCH) cur = nxt;
-        else { ti.advance(hop_q, hop_l, hop_qm, L); cur.load(P, ti, lane); }
+        else { ti.advance(hop_q, hop_l, hop_qm, L); cur.load(P, ti, lane, C_LO); }
     }
     tma_wait_group<0>();
 }
@@ -226,10 +241,8 @@ lookup_bwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, in
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = warp / LB_GWARPS, w = warp - g * LB_GWARPS;
     const uint32_t gbase = smem_u32(lb_smem) + (uint32_t)(g * LB_STAGES * LB_STAGE_BYTES);
-    // the three warps of a group run the same loop specialised on their window columns
-    if (w == 0) lb_warp<RADIUS, CM, 0>(M, P, n_tiles, g, lane, gbase);
-    else if (w == 1) lb_warp<RADIUS, CM, 1>(M, P, n_tiles, g, lane, gbase);
-    else lb_warp<RADIUS, CM, 2>(M, P, n_tiles, g, lane, gbase);
+    __shared__ uint8_t reg_flags[LB_GROUPS][32 * LB_GWARPS];
+    lb_warp<RADIUS, CM>(M, P, n_tiles, g, w, lane, gbase, reg_flags[g]);
 }
 
 template <int RADIUS>
