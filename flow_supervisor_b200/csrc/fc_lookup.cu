@@ -26,7 +26,7 @@ namespace fc {
 #define FC_LB_GROUPS 3
 #endif
 #ifndef FC_LB_STAGES
-#define FC_LB_STAGES 2
+#define FC_LB_STAGES 1
 #endif
 #ifndef FC_LB_PREFETCH
 #define FC_LB_PREFETCH 1
@@ -38,6 +38,11 @@ constexpr int LB_STAGES = FC_LB_STAGES;                       // window buffers 
 constexpr bool LB_PREFETCH = FC_LB_PREFETCH != 0;             // inputs of the next tile loaded one tile ahead
 constexpr int LB_WIN_BYTES = 6 * 3 * 64;                      // 6 row pairs x 3 patches x 64 B = 1152
 constexpr int LB_STAGE_BYTES = QT * LB_WIN_BYTES;             // 36 864
+// the output gradients of a tile ((2r+1)^2 channels x 32 queries) arrive as ONE TMA box per tile, one tile ahead: issued as
+// 45 predicated loads per lane they took a third of a tile's time (2200 of 6600 cycles: the load/store unit's queue of
+// outstanding requests, not DRAM, set the pace -- tools/probe_lookup_bwd_trace.py)
+constexpr int LB_GBOX_FLOATS = 81 * QT;                       // room for radius 4: [(2r+1)^2 channels][32 queries]
+constexpr int LB_GBOX_BYTES = (LB_GBOX_FLOATS * 4 + 127) / 128 * 128;
 
 __device__ __forceinline__ void group_sync(int g) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(g + 1), "n"(32 * LB_GWARPS) : "memory");
@@ -68,7 +73,8 @@ struct LbTile {
     float gv[NT][R];
     const float* gptr;
 
-    __device__ __forceinline__ void load(const LookupParams& P, const TileIt& it, int lane, int c_lo) {
+    // coordinates + bookkeeping only (the gradients come from the staged box, see take())
+    __device__ __forceinline__ void head(const LookupParams& P, const TileIt& it, int lane) {
         level = it.level(P.L);
         gq = it.qt * QT + lane;
         live = gq < P.Q;
@@ -81,6 +87,20 @@ struct LbTile {
             cy = __ldg(c + P.N);
         }
         gptr = P.io + ((long long)b * P.K + level * R * R) * P.N + p;
+    }
+    // this warp's taps out of the staged box [channel a * R + i][query]
+    __device__ __forceinline__ void take(uint32_t box, int lane, int c_lo) {
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            const int a = c_lo - 1 + k;
+            const bool ok = live && a >= 0 && a < R;
+            const uint32_t src = box + 4u * (uint32_t)((ok ? a * R : 0) * QT + lane);
+#pragma unroll
+            for (int i = 0; i < R; ++i) gv[k][i] = ok ? lds_f32b(src + 4u * (uint32_t)(i * QT)) : 0.f;
+        }
+    }
+    // the same taps straight from global memory (tiles whose 32 queries straddle two samples, unaligned tensors)
+    __device__ __forceinline__ void direct(const LookupParams& P, int c_lo) {
 #pragma unroll
         for (int k = 0; k < NT; ++k) {
             const int a = c_lo - 1 + k;
@@ -92,9 +112,19 @@ struct LbTile {
     }
 };
 
+// Timeline probe (FC_PROBES builds only; tools/probe_lookup_bwd_trace.py): warp 0 of group 0 of CTA 0 stamps clock64() per tile:
+// 0 loop top, 1 taps done, 2 previous reduce-adds read + first group barrier, 3 window zeroed + barrier, 4 window written,
+// 5 fence + barrier, 6 reduce-adds issued
+#ifdef FC_PROBES
+__device__ unsigned long long fc_lb_trace_buf[64 * 8];
+#define LB_TRACE(it, k) do { if (blockIdx.x == 0 && g == 0 && WI == 0 && lane == 0 && (it) < 64) fc_lb_trace_buf[(it) * 8 + (k)] = clock64(); } while (0)
+#else
+#define LB_TRACE(it, k) do {} while (0)
+#endif
+
 template <int RADIUS, int CM>
-__device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams& P, int n_tiles, int g, int WI, int lane,
-                                        uint32_t gbase, volatile uint8_t* reg_flags) {
+__device__ __forceinline__ void lb_warp(const LookupMaps& M, const CUtensorMap* gmap, const LookupParams& P, int n_tiles, int g,
+                                        int WI, int lane, uint32_t gbase, uint32_t gbox, uint64_t* gfull, volatile uint8_t* reg_flags) {
     using T = LbTile<RADIUS>;
     constexpr int R = T::R;
     const int C_LO = WI * T::CPW;                                        // this warp's window columns [C_LO, C_LO + CPW)
@@ -106,13 +136,46 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
     const int L = P.L, hop_q = n_groups / L, hop_l = n_groups - hop_q * L, hop_qm = hop_q % L;
     TileIt ti;
     ti.qt = tile / L; ti.slot = tile - ti.qt * L; ti.qm = ti.qt % L;
+    // a tile's gradients come as one TMA box [(2r+1)^2 channels][32 queries] when its queries lie in one sample
+    auto boxable = [&](int qt, int& b0, int& p0) {
+        if (gmap == nullptr) return false;
+        split_query(P, qt * QT, b0, p0);
+        return qt * QT < P.Q && p0 + QT <= P.N;
+    };
+    auto issue_box = [&](const TileIt& t, int b0, int p0, int buf) {
+        if (WI == 0 && lane == 0) {
+            mbar_expect_tx(gfull + buf, (uint32_t)(R * R * QT * 4));
+            tma_load_3d(gbox + (uint32_t)(buf * LB_GBOX_BYTES), gmap, smem_u32(gfull + buf), p0, t.level(P.L) * R * R, b0);
+        }
+    };
     T cur;
-    cur.load(P, ti, lane, C_LO);
+    cur.head(P, ti, lane);
+    int b0 = 0, p0 = 0;
+    bool cur_box = boxable(ti.qt, b0, p0);
+    if (cur_box) issue_box(ti, b0, p0, 0);
+    uint32_t uses[2] = {0u, 0u};                                           // boxable tiles each buffer has served (barrier parity)
     for (int it = 0;; ++it) {
         const int next = tile + n_groups;
+        // next tile: coordinates by two loads, gradients by a TMA box into the other buffer (all warps read the tile before
+        // last out of it before that tile's first group barrier)
         T nxt = cur;
-        if (LB_PREFETCH && next < n_tiles) { ti.advance(hop_q, hop_l, hop_qm, L); nxt.load(P, ti, lane, C_LO); }   // in flight while this tile is processed
+        bool nxt_box = false;
+        if (next < n_tiles) {
+            ti.advance(hop_q, hop_l, hop_qm, L);
+            nxt.head(P, ti, lane);
+            nxt_box = boxable(ti.qt, b0, p0);
+            if (nxt_box) issue_box(ti, b0, p0, (it + 1) & 1);
+        }
+        if (cur_box) {
+            const int buf = it & 1;
+            mbar_wait(gfull + buf, uses[buf] & 1u);
+            ++uses[buf];
+            cur.take(gbox + (uint32_t)(buf * LB_GBOX_BYTES), lane, C_LO);
+        } else {
+            cur.direct(P, C_LO);
+        }
 
+        LB_TRACE(it, 0);
         const int level = cur.level;
         const float cx = __fmul_rn(cur.cx, P.inv_scale[level]), cy = __fmul_rn(cur.cy, P.inv_scale[level]);
         const bool near_ = cur.live && (fabsf(cx) < 1048576.f) && (fabsf(cy) < 1048576.f);
@@ -152,16 +215,19 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
         // some part of the window lies inside the map
         const bool touches = near_ && n_rp > 0 && n_pc > 0 && ybase < Hl && xbase < Wl;
 
+        LB_TRACE(it, 1);
         // ---- the buffer used two tiles ago must have been read by its reduce-adds
         const uint32_t stage = gbase + (uint32_t)((it % LB_STAGES) * LB_STAGE_BYTES);
         tma_wait_group_read<LB_STAGES - 1>();                            // every lane waits for its own reduce-adds
         group_sync(g);
+        LB_TRACE(it, 2);
         regular = reg_flags[lane] && reg_flags[32 + lane] && reg_flags[64 + lane];
 #pragma unroll
         for (int i = 0; i < LB_STAGE_BYTES / 16 / (32 * LB_GWARPS); ++i)
             asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n" ::"r"(stage + 16u * (uint32_t)(tg + i * 32 * LB_GWARPS)), "f"(0.f) : "memory");
         group_sync(g);
 
+        LB_TRACE(it, 3);
         const uint32_t wq = stage + (uint32_t)(lane * LB_WIN_BYTES);
         if (touches && regular) {
             // window row n (relative to ybase) sits at (n >> 1) * pitch + (n & 1) * 32 bytes
@@ -217,45 +283,57 @@ __device__ __forceinline__ void lb_warp(const LookupMaps& M, const LookupParams&
                 }
             }
         }
+        LB_TRACE(it, 4);
         fence_proxy_async_smem();
         group_sync(g);
+        LB_TRACE(it, 5);
         // every warp holds every query's box geometry: the 32 reduce-adds of the tile (one per lane, serialised
         // by the hardware's uniform-operand issue) are dealt out over the group's three warps
         if (touches && FC_PROBE_VAL(P) != 1 && (lane % LB_GWARPS) == WI) {
             if (FC_PROBE_VAL(P) == 2) tma_store_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, cur.gq);
-            else tma_reduce_add_3d(&M.m[level][sel], wq, 16 * pc_lo, rp_lo, cur.gq);
+            else tma_reduce_add_3d(&M.m[level][FC_PROBE_VAL(P) == 3 ? lk_shape(1, 1) : sel], wq, 16 * pc_lo, rp_lo, cur.gq);   // probe 3: one box shape
         }
         tma_commit_group();
+        LB_TRACE(it, 6);
         if (next >= n_tiles) break;
         tile = next;
-        if (LB_PREFETCH) cur = nxt;
-        else { ti.advance(hop_q, hop_l, hop_qm, L); cur.load(P, ti, lane, C_LO); }
+        cur.level = nxt.level; cur.gq = nxt.gq; cur.live = nxt.live; cur.cx = nxt.cx; cur.cy = nxt.cy; cur.gptr = nxt.gptr;
+        cur_box = nxt_box;
     }
     tma_wait_group<0>();
 }
 
 template <int RADIUS, int CM>
 __global__ void __launch_bounds__(LB_THREADS, 1)
-lookup_bwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, int n_tiles) {
+lookup_bwd_kernel(const __grid_constant__ LookupMaps M, const __grid_constant__ CUtensorMap gmap, const LookupParams P, int n_tiles,
+                  int staged) {
     extern __shared__ __align__(1024) uint8_t lb_smem[];
+    __shared__ __align__(8) uint64_t gfull[LB_GROUPS][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = warp / LB_GWARPS, w = warp - g * LB_GWARPS;
     const uint32_t gbase = smem_u32(lb_smem) + (uint32_t)(g * LB_STAGES * LB_STAGE_BYTES);
+    const uint32_t gbox = smem_u32(lb_smem) + (uint32_t)(LB_GROUPS * LB_STAGES * LB_STAGE_BYTES + g * 2 * LB_GBOX_BYTES);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < LB_GROUPS; ++i) { mbar_init(&gfull[i][0], 1); mbar_init(&gfull[i][1], 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
     __shared__ uint8_t reg_flags[LB_GROUPS][32 * LB_GWARPS];
-    lb_warp<RADIUS, CM>(M, P, n_tiles, g, w, lane, gbase, reg_flags[g]);
+    lb_warp<RADIUS, CM>(M, staged ? &gmap : nullptr, P, n_tiles, g, w, lane, gbase, gbox, gfull[g], reg_flags[g]);
 }
 
 template <int RADIUS>
-static int launch_bwd(const LookupMaps& M, const LookupParams& P, int n_tiles, int n_sm, int coord_mode, cudaStream_t s) {
-    const size_t smem = (size_t)LB_GROUPS * LB_STAGES * LB_STAGE_BYTES;
+static int launch_bwd(const LookupMaps& M, const CUtensorMap& gmap, int staged, const LookupParams& P, int n_tiles, int n_sm, int coord_mode,
+                      cudaStream_t s) {
+    const size_t smem = (size_t)LB_GROUPS * (LB_STAGES * LB_STAGE_BYTES + 2 * LB_GBOX_BYTES);
     const int want = (n_tiles + LB_GROUPS - 1) / LB_GROUPS;
     const int grid = want < n_sm ? want : n_sm;
     if (coord_mode == FC_COORD_CUDA) {
         FC_SMEM_ATTR_ONCE((lookup_bwd_kernel<RADIUS, FC_COORD_CUDA>), smem);
-        lookup_bwd_kernel<RADIUS, FC_COORD_CUDA><<<grid, LB_THREADS, smem, s>>>(M, P, n_tiles);
+        lookup_bwd_kernel<RADIUS, FC_COORD_CUDA><<<grid, LB_THREADS, smem, s>>>(M, gmap, P, n_tiles, staged);
     } else {
         FC_SMEM_ATTR_ONCE((lookup_bwd_kernel<RADIUS, FC_COORD_CPU>), smem);
-        lookup_bwd_kernel<RADIUS, FC_COORD_CPU><<<grid, LB_THREADS, smem, s>>>(M, P, n_tiles);
+        lookup_bwd_kernel<RADIUS, FC_COORD_CPU><<<grid, LB_THREADS, smem, s>>>(M, gmap, P, n_tiles, staged);
     }
     FC_LAUNCH_CHECK("lookup_bwd_kernel");
     return FC_OK;
@@ -285,10 +363,28 @@ extern "C" int fc_lookup_bwd(const float* grad_out, const float* coords, float* 
     if (int e = sm_count(n_sm)) return e;
     const int n_tiles = ((P.Q + QT - 1) / QT) * pyr.L;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // the output gradient as {N, K, B} with boxes of 32 queries x (2r+1)^2 channels (needs 16-byte aligned rows)
+    CUtensorMap gmap;
+    memset(&gmap, 0, sizeof(gmap));
+    const int RR = (2 * radius + 1) * (2 * radius + 1);
+    int staged = (pyr.N % 4 == 0) && (reinterpret_cast<uintptr_t>(grad_out) & 15u) == 0 && pyr.N >= QT;
+    if (staged) {
+        const cuuint64_t dims[3] = {(cuuint64_t)pyr.N, (cuuint64_t)P.K, (cuuint64_t)B};
+        const cuuint64_t str[2] = {(cuuint64_t)pyr.N * 4, (cuuint64_t)pyr.N * P.K * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)QT, (cuuint32_t)RR, 1};
+        if (int e = encode_tiled_cached(&gmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, grad_out, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_NONE)) return e;
+    }
     switch (radius) {
-        case 1: return launch_bwd<1>(M, P, n_tiles, n_sm, coord_mode, s);
-        case 2: return launch_bwd<2>(M, P, n_tiles, n_sm, coord_mode, s);
-        case 3: return launch_bwd<3>(M, P, n_tiles, n_sm, coord_mode, s);
-        default: return launch_bwd<4>(M, P, n_tiles, n_sm, coord_mode, s);
+        case 1: return launch_bwd<1>(M, gmap, staged, P, n_tiles, n_sm, coord_mode, s);
+        case 2: return launch_bwd<2>(M, gmap, staged, P, n_tiles, n_sm, coord_mode, s);
+        case 3: return launch_bwd<3>(M, gmap, staged, P, n_tiles, n_sm, coord_mode, s);
+        default: return launch_bwd<4>(M, gmap, staged, P, n_tiles, n_sm, coord_mode, s);
     }
 }
+
+#ifdef FC_PROBES
+extern "C" int fc_debug_lookup_bwd_trace(unsigned long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, fc::fc_lb_trace_buf, sizeof(fc::fc_lb_trace_buf)) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -24,4 +24,16 @@ for (B, H, W) in ((6, 46, 96), (6, 54, 128)):
     torch.cuda.synchronize()
     out[f"{H}x{W}_checksum"] = float(gp.double().abs().sum())
     out[f"{H}x{W}_us"] = 1e3 * timed(lambda: ops.lookup_bwd(gout, c, gp, L, R, _lib.COORD_CUDA), 10, inner=12)
+    # the same 12 launches replayed from a CUDA graph: the eager figure above includes the host's ~45 us per call
+    # (torch custom-op dispatch) whenever the kernel is shorter than that
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.lookup_bwd(gout, c, gp, L, R, _lib.COORD_CUDA)
+    torch.cuda.current_stream().wait_stream(side)
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for _ in range(12):
+            ops.lookup_bwd(gout, c, gp, L, R, _lib.COORD_CUDA)
+    out[f"{H}x{W}_graph_us"] = 1e3 * timed(gr.replay, 10) / 12
 print(json.dumps(out), flush=True)
