@@ -101,7 +101,7 @@ class _Lookup(torch.autograd.Function):
     def forward(ctx, token, coords, state):
         ctx.save_for_backward(coords)
         ctx.state = state
-        return ops.lookup(state.pyramid, coords, state.L, state.radius, state.coord)
+        return _lookup_fn()(state.pyramid, coords, state.L, state.radius, state.coord)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -110,7 +110,8 @@ class _Lookup(torch.autograd.Function):
         if state.grad_pyramid is None:
             state.grad_pyramid = torch.zeros(state.pyramid.numel(), dtype=torch.float32,
                                              device=state.pyramid.device)
-        ops.lookup_bwd(grad_out, coords, state.grad_pyramid, state.L, state.radius, state.coord)
+        (ops.lookup_bwd if torch.compiler.is_compiling() else ops.lookup_bwd_direct)(
+            grad_out, coords, state.grad_pyramid, state.L, state.radius, state.coord)
         # coords get no gradient: the reference always passes them detached (raft.py:123)
         return grad_out.new_zeros(1), None, None
 

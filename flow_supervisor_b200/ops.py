@@ -180,16 +180,20 @@ def _(pyramid, coords, num_levels, radius, coord_mode):
 
 
 # ----------------------------------------------------------------------------- backward
-@custom_op("flowcorr::lookup_bwd", mutates_args=("grad_pyramid",))
-def lookup_bwd(grad_out: Tensor, coords: Tensor, grad_pyramid: Tensor, num_levels: int, radius: int,
-               coord_mode: int) -> None:
-    """Scatter-add one lookup's output gradient into the block's gradient pyramid."""
+def lookup_bwd_direct(grad_out: Tensor, coords: Tensor, grad_pyramid: Tensor, num_levels: int, radius: int,
+                      coord_mode: int) -> None:
+    """Scatter-add one lookup's output gradient into the block's gradient pyramid.  The plain function behind
+    ``torch.ops.flowcorr.lookup_bwd``: the autograd functions call it directly in eager mode (the kernel runs 26-58 us,
+    the dispatcher alone costs the host about as much per call)."""
     _need_cuda(grad_out, coords, grad_pyramid)
     g, c = _f32c(grad_out), _f32c(coords)
     B, _, H, W = c.shape
     with torch.cuda.device(c.device):
         _lib.check(_lib.load().fc_lookup_bwd(g.data_ptr(), c.data_ptr(), grad_pyramid.data_ptr(), B, H, W,
                                              num_levels, radius, coord_mode, _stream()), "fc_lookup_bwd")
+
+
+lookup_bwd = custom_op("flowcorr::lookup_bwd", mutates_args=("grad_pyramid",))(lookup_bwd_direct)
 
 
 @custom_op("flowcorr::build_bwd", mutates_args=("grad_pyramid",))
