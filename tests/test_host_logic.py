@@ -158,3 +158,17 @@ def test_build_schedule_covers_every_unit_once():
                         seen.append(u)
                 assert sorted(seen) == list(range(units)), (n_pt, groups, n_clusters)
                 assert most <= -(-units // n_clusters) + (groups if tail_units else 0)
+
+
+def test_clear_pads_zeroes_exactly_the_pad_cells():
+    """ops.clear_pads_ restores the pyramid invariant of include/flowcorr.h (pad rows / columns of every level are zeros)
+    on a caller-filled buffer: after it, the un-patched levels hold zeros outside H_l x W_l and the data inside."""
+    import torch
+    from flow_supervisor_b200 import ops
+    B, H, W, L = 2, 5, 11, 3
+    src = torch.arange(1, ops.pyramid_numel(B, H, W, L) + 1, dtype=torch.float32)
+    p = ops.clear_pads_(src.clone(), B, H, W, L)
+    for lvl, ref, (h, w, wp) in zip(ops.level_padded(p, B, H, W, L), ops.level_padded(src, B, H, W, L), ops.geometry(H, W, L)):
+        assert torch.equal(lvl[:, :h, :w], ref[:, :h, :w])
+        assert not lvl[:, h:, :].any() and not lvl[:, :, w:].any()
+        assert lvl.shape[1] % 2 == 0 and lvl.shape[2] == wp
