@@ -139,6 +139,20 @@ __device__ __forceinline__ void st_v8(float* dst, const float* v) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// one leader thread of a converged warp (elect.sync): the compiler then knows the guarded code runs in exactly one thread and
+// moves a TMA instruction's operands to uniform registers in a straight line; behind `lane == 0` it builds a loop over the
+// possibly divergent lanes (R2UR + predicate juggling + BRA.U.ANY, ~180 cycles per store in the epilogue's timeline)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     const __nv_bfloat162 v(__float2bfloat16_rn(lo), __float2bfloat16_rn(hi));
     return *reinterpret_cast<const uint32_t*>(&v);
@@ -193,7 +207,12 @@ constexpr int TB_SLOTS = 8;
 __device__ unsigned long long fc_build_trace_buf[512 * TB_SLOTS];
 #define TB_TRACE(tile, k, v) do { if (blockIdx.x == 0 && (tile) < 512) fc_build_trace_buf[(tile) * TB_SLOTS + (k)] = (v); } while (0)
 #define TB_CLOCK() clock64()
+// finer: the chunks of tiles 16..23 of the same warp: 0 before the TMEM load, 1 loaded, 2 staging box free, 3 store issued, 4 pooled
+__device__ unsigned long long fc_build_chunk_trace[8 * 8 * 8];
+#define TB_CHUNK(tile, cc, k) do { if (blockIdx.x == 0 && ew == 0 && lane == 0 && (tile) >= 16 && (tile) < 24) \
+    fc_build_chunk_trace[(((tile) - 16) * 8 + (cc)) * 8 + (k)] = clock64(); } while (0)
 #else
+#define TB_CHUNK(tile, cc, k) do {} while (0)
 #define TB_TRACE(tile, k, v) do {} while (0)
 #define TB_CLOCK() 0ll
 #endif
@@ -280,7 +299,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
-        if (lane == 0) {
+        if (elect_one()) {
             int a_use = 0, cur_am = -1, slot = 0, ptile = 0;
             uint32_t phase = 0;                                // ring position: stage `slot`, use parity `phase`
             for (int u = u_begin; u < u_end; ++u) {
@@ -324,7 +343,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         }
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA only) =================
-        if (lane == 0 && leader) {
+        if (leader && elect_one()) {
             const uint32_t idesc0 = umma_idesc_bf16(2 * TC_BM, P.NT), idesc1 = umma_idesc_bf16(2 * TC_BM, P.NT2 > 0 ? P.NT2 : P.NT);
             int tc = 0, a_use = 0, cur_am = -1, slot = 0;
             uint32_t phase = 0;
@@ -441,8 +460,10 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const int gc = H * (P.NT >> 5) + c;                      // chunk inside the row pair: level-0 columns [16 gc, 16 gc + 16)
                 if (cc < CH && c * 32 < ncols) {
                     float v[32];
+                    TB_CHUNK(tc, cc, 0);
                     tmem_ld32(lane_addr + (uint32_t)(buf * 256 + c * 32), v);
                     tmem_ld_wait();
+                    TB_CHUNK(tc, cc, 1);
                     if (do_scale) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] *= P.scale;
@@ -461,8 +482,9 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         // ---- level 0: staging (swizzled like the store map) -> TMA store
                         float* sbuf = sbuf0 + (use & (NBUF - 1)) * TC_STG_FLOATS;
                         ++use;
-                        if (lane == 0) tma_wait_group_read<NBUF - 1>();   // the store that last read this box is done
+                        if (elect_one()) tma_wait_group_read<NBUF - 1>();   // the store that last read this box is done
                         __syncwarp();
+                        TB_CHUNK(tc, cc, 2);
                         const uint32_t sb32 = smem_u32(sbuf);
                         if (VB) {
                             // bf16 volume: rows of 64 bytes (SWIZZLE_64B box of 32 columns) or 32 bytes (plain box of 16)
@@ -490,12 +512,15 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                                 st_shared_v4(sb32 + 4u * (uint32_t)(lane * 16 + ((k ^ ((lane >> 1) & 3)) << 2)), __float_as_uint(v[4 * k]),
                                              __float_as_uint(v[4 * k + 1]), __float_as_uint(v[4 * k + 2]), __float_as_uint(v[4 * k + 3]));
                         }
+                        TB_CHUNK(tc, cc, 5);
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0 && rows_valid > 0 && FC_PROBE_VAL(P) != 1 && FC_PROBE_VAL(P) != 6) {
+                        TB_CHUNK(tc, cc, 6);
+                        if (elect_one() && rows_valid > 0 && FC_PROBE_VAL(P) != 1 && FC_PROBE_VAL(P) != 6) {
                             tma_store_3d(rem >= 32 ? &SM.l0_c32 : &SM.l0_c16, smem_u32(sbuf), q0 + c * 32, row0, b);
                             tma_commit_group();
                         }
+                        TB_CHUNK(tc, cc, 3);
                     }
                     if (fused) {
                         // ---- level 1: row rp, columns [8 gc, 8 gc + 8); ((a + b) + c) + d, then * 0.25:
@@ -524,6 +549,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             }
                         }
                     }
+                    TB_CHUNK(tc, cc, 4);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) l2[cc][j] = 0.f;
@@ -603,7 +629,7 @@ tc_build_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             for (int h = 0; h < P.halves; ++h)
                 for (int rp = t0; rp < t1; ++rp) tile_body(h, rp);
         }
-        if (lane == 0) tma_wait_group<0>();                    // staging is read and the stores have landed
+        if (elect_one()) tma_wait_group<0>();                  // staging is read and the stores have landed
         __syncwarp();
     }
 
@@ -804,6 +830,9 @@ int tc_build(const float* f1, const float* f2, void* pyramid, const Pyramid& pyr
 }  // namespace fc
 
 #ifdef FC_PROBES
+extern "C" int fc_debug_build_chunk_trace(unsigned long long* host_out) {    // 8 tiles x 8 chunks x 5 stamps (see TB_CHUNK)
+    return cudaMemcpyFromSymbol(host_out, fc::fc_build_chunk_trace, sizeof(fc::fc_build_chunk_trace)) == cudaSuccess ? 0 : 1;
+}
 extern "C" int fc_debug_build_trace(unsigned long long* host_out) {     // 512 x TB_SLOTS stamps (see TB_TRACE)
     return cudaMemcpyFromSymbol(host_out, fc::fc_build_trace_buf, sizeof(fc::fc_build_trace_buf)) == cudaSuccess ? 0 : 1;
 }

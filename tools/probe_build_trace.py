@@ -49,3 +49,13 @@ print("MMA thread: waiting for a free accumulator %.0f | issuing (incl. ring wai
 print("epilogue warp 0: waiting for the accumulator %.0f | drain (TMEM -> staging -> store issue) %.0f | pooled levels after the hand-back %.0f" %
       ((w[:, 4] - w[:, 3]).mean(), (w[:, 5] - w[:, 4]).mean(), (w[:, 6] - w[:, 5]).mean()))
 print("producer: waiting for free ring stages per tile %.0f" % w[:, 7].mean())
+
+cb = np.zeros((8, 8, 8), dtype=np.uint64)
+lib.fc_debug_build_chunk_trace.argtypes = [ctypes.c_void_p]
+assert lib.fc_debug_build_chunk_trace(cb.ctypes.data) == 0
+c = cb.astype(np.int64)
+print("epilogue warp 0, tiles 16..23, mean cycles per chunk phase (8 chunks of 32 columns per tile):")
+print("  TMEM load + wait %.0f | wait for the staging box %.0f | 8 swizzled shared stores %.0f | proxy fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) + syncwarp %.0f | "
+      "TMA store issue + commit %.0f | pooled levels (level-1 store, stashes) %.0f | chunk to chunk %.0f"
+      % ((c[:, :, 1] - c[:, :, 0]).mean(), (c[:, :, 2] - c[:, :, 1]).mean(), (c[:, :, 5] - c[:, :, 2]).mean(), (c[:, :, 6] - c[:, :, 5]).mean(),
+         (c[:, :, 3] - c[:, :, 6]).mean(), (c[:, :, 4] - c[:, :, 3]).mean(), np.diff(c[:, :, 0], axis=1).mean()))
