@@ -139,20 +139,6 @@ __device__ __forceinline__ void st_v8(float* dst, const float* v) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// one leader thread of a converged warp (elect.sync): the compiler then knows the guarded code runs in exactly one thread and
-// moves a TMA instruction's operands to uniform registers in a straight line; behind `lane == 0` it builds a loop over the
-// possibly divergent lanes (R2UR + predicate juggling + BRA.U.ANY, ~180 cycles per store in the epilogue's timeline)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t p;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t"
-        "}\n"
-        : "=r"(p));
-    return p != 0;
-}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     const __nv_bfloat162 v(__float2bfloat16_rn(lo), __float2bfloat16_rn(hi));
     return *reinterpret_cast<const uint32_t*>(&v);

@@ -262,7 +262,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t stage_tx = (uint32_t)(2 * n_parts * (BW_PART_BYTES + half_n * BW_BK * 2));
             int it = 0;
             for (int u = u_begin; u < u_end; ++u) {
@@ -291,7 +291,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         }
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA only) =================
-        if (lane == 0 && leader) {
+        if (leader && elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(2 * BW_BM, P.D) | (OP == BW_DF2 ? (1u << 15) : 0u);
             int it = 0, uc = 0;
             for (int u = u_begin; u < u_end; ++u, ++uc) {
@@ -472,7 +472,7 @@ tc_bwd_fold_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t b_tx = (uint32_t)(2 * n_parts * half_n * BW_BK * 2);
             // the gradient volume streams through L2 once; the feature planes are swept again by every row tile
             const uint64_t stream = l2_policy_evict_first(), keep = l2_policy_evict_last();
@@ -500,7 +500,7 @@ tc_bwd_fold_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
         }
     } else if (warp == 1) {
         // ================= MMA issuer (leader) / relay (peer) =================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(2 * BW_BM, P.D) | (OP == BW_DF2 ? (1u << 15) : 0u);
             int it = 0, uc = 0;
             for (int u = u_begin; u < u_end; u += u_step, ++uc) {
@@ -849,7 +849,7 @@ tc_bwd_fold_aligned_kernel(const __grid_constant__ CUtensorMap map_g, const __gr
 
     if (warp == 0) {
         // ================= TMA producer of the feature operand (both CTAs) =================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t b_tx = (uint32_t)(2 * n_parts * half_n * BW_BK * 2);
             const uint64_t keep = l2_policy_evict_last();
             int it = 0;
@@ -871,7 +871,7 @@ tc_bwd_fold_aligned_kernel(const __grid_constant__ CUtensorMap map_g, const __gr
     } else if (warp == BF_CONV0 + BF_CONV_WARPS) {
         // ================= TMA producer of the fp32 boxes and the coarse boxes (both CTAs) =================
         // its own warp: these loads wait for the CONVERTERS (box buffer read), not for the MMAs, and run ahead of them
-        if (lane == 0) {
+        if (elect_one()) {
             const uint64_t stream = l2_policy_evict_first();
             // the coarse boxes over 4 patches starting at patch px0 of patch row py (levels 1..3), `rows` queries from p0
             auto coarse = [&](uint32_t dst, uint32_t bar, int py, int px0, int p0, int b, int rows_off) {
@@ -914,7 +914,7 @@ tc_bwd_fold_aligned_kernel(const __grid_constant__ CUtensorMap map_g, const __gr
         }
     } else if (warp == 1) {
         // ================= MMA issuer (leader) / relay (peer) =================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(2 * BW_BM, P.D) | (OP == BW_DF2 ? (1u << 15) : 0u);
             int it = 0, uc = 0;
             for (int u = u_begin; u < u_end; u += u_step, ++uc) {

@@ -35,6 +35,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------- device: TMA
+// one leader thread of a converged warp (elect.sync): the compiler then knows the guarded code runs in exactly one thread and
+// moves a TMA instruction's operands to uniform registers in a straight line; behind `lane == 0` it builds a loop over the
+// possibly divergent lanes (R2UR + predicate juggling + BRA.U.ANY, ~180 cycles per store in the epilogue's timeline)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
