@@ -96,7 +96,7 @@ fnet_tail_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(w_full, (uint32_t)(n_parts * KBN * wblk));
             for (int kb = 0; kb < KBN; ++kb) {
                 tma_load_2d(w_hi + kb * wblk, &map_w_hi, w_full, kb * FT_BK, 0);
@@ -115,7 +115,7 @@ fnet_tail_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(FT_TOK, P.D);
             mbar_wait(w_full, 0);
             for (int j = 0; j < n_local; ++j) {

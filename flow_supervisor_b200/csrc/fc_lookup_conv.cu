@@ -242,12 +242,12 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
             umma2_commit(t_full + db);               // both CTAs: accumulator complete
         };
         if (warp == LC_EW0 && n_mine > 0) {
-            if (lane == 0) issue(0);
+            if (elect_one()) issue(0);
             __syncwarp();
         }
         for (int i = 0; i < n_mine; ++i) {
             if (warp == LC_EW0 && i + 1 < n_mine) {      // the next pair-tile's MMAs before this one's epilogue
-                if (lane == 0) issue(i + 1);
+                if (elect_one()) issue(i + 1);
                 __syncwarp();
             }
             const int T = pair + i * n_pairs, db = i & 1;

@@ -383,3 +383,7 @@ if __name__ == "__main__":
         row_ondemand(2, 136, 240, a.reps)
     if "samegpu" in a.rows:
         row_same_gpu(8, 436, 1024, a.reps)
+    if "convc1" in a.rows:
+        row_lookup_convc1(8, 55, 128, a.reps)
+    if "fnet" in a.rows:
+        row_fnet_tail(8, 55, 128, a.reps)
