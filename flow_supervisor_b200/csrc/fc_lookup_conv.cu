@@ -55,9 +55,11 @@ constexpr int LC_QT = 64;                                 // queries per pair-ti
 constexpr int LC_BPLANE = (LC_K / 64) * QT * 128;         // 24 KB: [6 k-blocks][32 rows][128 B]
 constexpr int LC_BBUF = 2 * LC_BPLANE;                    // hi + lo
 constexpr uint32_t LC_D0 = 0, LC_D1 = 64, LC_AHI = 128, LC_ALO = LC_AHI + LC_K / 2;    // TMEM columns
+constexpr int LC_WP = LC_K + 8;                           // packed weight row pitch in elements: 784 B, rows 16 B apart modulo 128 B
+constexpr int LC_WPLANE_BYTES = 128 * LC_WP * 2;          // one CTA's half of one plane: 100 352 B
 
 struct ConvParams {
-    const __nv_bfloat16* w_hi;      // [256][384] slot-ordered, zero at pad slots
+    const __nv_bfloat16* w_hi;      // [256][392] slot-ordered (384 slots + 8 pad elements per row), zero at pad slots
     const __nv_bfloat16* w_lo;
     const float* bias;              // [256]
     float* out;                     // (B, 256, N)
@@ -109,10 +111,29 @@ __device__ __forceinline__ LfQuery lc_query(const LookupParams& P, const ConvPar
     return q;
 }
 
+// Timeline probe (FC_PROBES builds only; tools/probe_lookup_convc1_trace.py): per CTA, thread 0: 0 kernel start, 1 barriers /
+// TMEM ready, 2 weights in tensor memory + B zeroed (main loop starts), 3 main loop done
+#ifdef FC_PROBES
+__device__ unsigned long long fc_lc_trace_buf[148 * 4];
+#define LC_TRACE(k) do { if (threadIdx.x == 0 && blockIdx.x < 148) fc_lc_trace_buf[blockIdx.x * 4 + (k)] = clock64(); } while (0)
+#else
+#define LC_TRACE(k) do {} while (0)
+#endif
+
+__device__ __forceinline__ void lc_bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 template <int CM, int VB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LC_THREADS, 1)
 lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, const ConvParams C) {
     constexpr int LF_STAGE_BYTES = lf_stage_bytes(VB);
+    // both weight planes fit the staging area at once with the fp32 volume's ring; with the bf16 volume's (half the bytes) they
+    // are staged one after the other
+    constexpr bool W_BOTH = 2 * LC_WPLANE_BYTES <= LC_NB * LC_BBUF + LC_STAGES * LF_STAGE_BYTES;
+    LC_TRACE(0);
     extern __shared__ __align__(1024) uint8_t lc_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lc_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* bbuf = smem;                                               // [LC_NB][hi plane | lo plane]
@@ -124,7 +145,8 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
     uint64_t* b_empty = bars + 4;        // 2, one multicast commit
     uint64_t* t_full = bars + 6;         // 2, one multicast commit
     uint64_t* t_empty = bars + 8;        // 2, used in the leader: 2 CTAs x 4 epilogue warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* w_full = bars + 10;        // 1: both weight planes of this CTA landed in the staging area
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -138,7 +160,14 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
             mbar_init(b_part + i, LC_L * LF_GWARPS); mbar_init(b_peer + i, 1); mbar_init(b_empty + i, 1);
             mbar_init(t_full + i, 1); mbar_init(t_empty + i, 2 * 4);
         }
+        mbar_init(w_full, 1);
         mbar_fence_init();
+        // this CTA's 128 channels of both weight planes: two bulk copies into the (still idle) B buffers + footprint ring, issued
+        // before anything else (the per-thread copy loop + two block barriers they replace were most of a 12 400-cycle prologue)
+        static_assert(LC_WPLANE_BYTES <= LC_NB * LC_BBUF + LC_STAGES * lf_stage_bytes(1), "weight staging fits B buffers + ring");
+        mbar_expect_tx(w_full, (W_BOTH ? 2u : 1u) * LC_WPLANE_BYTES);
+        lc_bulk_load(smem_u32(smem), C.w_hi + (long long)rank * 128 * LC_WP, LC_WPLANE_BYTES, w_full);
+        if (W_BOTH) lc_bulk_load(smem_u32(smem) + LC_WPLANE_BYTES, C.w_lo + (long long)rank * 128 * LC_WP, LC_WPLANE_BYTES, w_full);
     }
     if (warp == LC_EW0) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
@@ -148,40 +177,37 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    LC_TRACE(1);
 
     // weights of this CTA's 128 output channels -> tensor memory (lane = channel, 32-bit column = two consecutive slots).
-    // A thread needs its channel's whole row (768 B per plane): read straight from global that is one sector per lane and
-    // load instruction (all 148 CTAs hammering the same 393 KB: ~40 us of prologue, ncu long-scoreboard 8.6 per issue), so
-    // each plane is first copied coalesced into the (still idle) footprint ring at a conflict-free row pitch.
-    {
-        constexpr int WPITCH = LC_K * 2 + 16;                              // 784 B: rows 16 B apart modulo 128 B
-        static_assert(128 * WPITCH <= LC_NB * LC_BBUF + LC_STAGES * lf_stage_bytes(1), "weight staging fits B buffers + ring");
-        uint8_t* stagew = smem;
-        for (int plane = 0; plane < 2; ++plane) {
-            const uint4* src = reinterpret_cast<const uint4*>((plane ? C.w_lo : C.w_hi) + (long long)rank * 128 * LC_K);
-            for (int i = threadIdx.x; i < 128 * (LC_K * 2 / 16); i += LC_THREADS) {
-                const int row = i / (LC_K * 2 / 16), ch = i - row * (LC_K * 2 / 16);
-                *reinterpret_cast<uint4*>(stagew + row * WPITCH + ch * 16) = __ldg(src + i);
+    // A thread needs its channel's whole row (768 B per plane); the packed rows have a pitch of 784 B, so the 32 lanes of a
+    // warp read their rows out of the staging area without bank conflicts.
+    for (int plane = 0; plane < 2; ++plane) {
+        if (!W_BOTH && plane == 1) {
+            __syncthreads();                                       // plane 0 is in tensor memory: its staging bytes are free
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(w_full, (uint32_t)LC_WPLANE_BYTES);
+                lc_bulk_load(smem_u32(smem), C.w_lo + (long long)rank * 128 * LC_WP, LC_WPLANE_BYTES, w_full);
             }
-            __syncthreads();
-            if (warp >= LC_EW0 && warp < LC_CW0) {
-                const int quarter = warp & 3;
-                const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-                const uint4* rowp = reinterpret_cast<const uint4*>(stagew + (quarter * 32 + lane) * WPITCH);
-                for (int part = 0; part < LC_K / 64; ++part) {
-                    uint32_t v[32];
+        }
+        if (warp >= LC_EW0 && warp < LC_CW0) {
+            if (plane == 0 || !W_BOTH) mbar_wait(w_full, (uint32_t)(W_BOTH ? 0 : plane));
+            const int quarter = warp & 3;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            const uint4* rowp = reinterpret_cast<const uint4*>(smem + (W_BOTH ? plane : 0) * LC_WPLANE_BYTES + (quarter * 32 + lane) * (LC_WP * 2));
+            for (int part = 0; part < LC_K / 64; ++part) {
+                uint32_t v[32];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const uint4 t = rowp[part * 8 + i];
-                        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-                    }
-                    tmem_st32(lane_addr + (plane ? LC_ALO : LC_AHI) + (uint32_t)(part * 32), v);
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 t = rowp[part * 8 + i];
+                    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
                 }
-                asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+                tmem_st32(lane_addr + (plane ? LC_ALO : LC_AHI) + (uint32_t)(part * 32), v);
             }
-            __syncthreads();
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         }
     }
+    __syncthreads();
     // the B operand starts out as zeros: pad slots (y-offset 9 of every x-offset, slots 90..95 of every level) are never
     // written again and must not hold NaN patterns (their weights are zero)
     for (int i = threadIdx.x; i < LC_NB * LC_BBUF / 16; i += LC_THREADS) reinterpret_cast<uint4*>(bbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -190,6 +216,7 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
     __syncthreads();
     cluster_sync_all();                  // both CTAs: barriers initialised, weights in place
     tc_fence_after();
+    LC_TRACE(2);
 
     if (warp < LC_PRODUCERS) {
         // ================= footprint producers: lookup tiles pw, pw + LC_PRODUCERS, ... =================
@@ -317,6 +344,7 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
         }
     }
 
+    LC_TRACE(3);
     // neither CTA may leave while its peer can still touch its barriers / tensor memory
     tc_fence_before();
     cluster_sync_all();
@@ -326,15 +354,15 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
     }
 }
 
-// convc1 weights (256, 324) fp32 -> slot-ordered bf16 hi/lo [256][384] + bias
+// convc1 weights (256, 324) fp32 -> slot-ordered bf16 hi/lo [256][384 slots + 8 pad] + bias
 __global__ void convc1_prepare_kernel(const float* __restrict__ w, const float* __restrict__ bias, __nv_bfloat16* hi, __nv_bfloat16* lo,
                                       float* bias_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < LC_COUT * LC_K) {
-        const int co = i / LC_K, kp = i - co * LC_K;
+    if (i < LC_COUT * LC_WP) {
+        const int co = i / LC_WP, kp = i - co * LC_WP;                   // kp >= LC_K: the row's 8 pad elements
         const int l = kp / LC_KL, s = kp - l * LC_KL, a = s / (LC_R + 1), j = s - a * (LC_R + 1);
         float v = 0.f;
-        if (a < LC_R && j < LC_R) v = w[(long long)co * (LC_L * LC_R * LC_R) + l * LC_R * LC_R + a * LC_R + j];
+        if (kp < LC_K && a < LC_R && j < LC_R) v = w[(long long)co * (LC_L * LC_R * LC_R) + l * LC_R * LC_R + a * LC_R + j];
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         hi[i] = h;
         lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -342,7 +370,7 @@ __global__ void convc1_prepare_kernel(const float* __restrict__ w, const float* 
     if (i < LC_COUT) bias_out[i] = bias ? bias[i] : 0.f;
 }
 
-static size_t convc1_packed_bytes() { return (size_t)LC_COUT * LC_K * 2 * 2 + (size_t)LC_COUT * 4; }
+static size_t convc1_packed_bytes() { return (size_t)LC_COUT * LC_WP * 2 * 2 + (size_t)LC_COUT * 4; }
 
 template <int CM>
 static int launch_lc(const LookupMaps& M, const LookupParams& P, const ConvParams& C, int vb, cudaStream_t s) {
@@ -376,9 +404,9 @@ extern "C" int fc_convc1_prepare(const float* weight, const float* bias, void* p
     FC_REQUIRE(weight && packed, "fc_convc1_prepare: null pointer");
     FC_REQUIRE(packed_bytes >= convc1_packed_bytes(), "fc_convc1_prepare: buffer %zu < %zu bytes", packed_bytes, convc1_packed_bytes());
     __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(packed);
-    __nv_bfloat16* lo = hi + (size_t)LC_COUT * LC_K;
-    float* b = reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + (size_t)LC_COUT * LC_K * 4);
-    const int n = LC_COUT * LC_K;
+    __nv_bfloat16* lo = hi + (size_t)LC_COUT * LC_WP;
+    float* b = reinterpret_cast<float*>(static_cast<uint8_t*>(packed) + (size_t)LC_COUT * LC_WP * 4);
+    const int n = LC_COUT * LC_WP;
     convc1_prepare_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(weight, bias, hi, lo, b);
     FC_LAUNCH_CHECK("convc1_prepare_kernel");
     return FC_OK;
@@ -406,11 +434,17 @@ extern "C" int fc_lookup_convc1_fwd(const void* pyramid, const float* coords, co
     ConvParams C{};
     const uint8_t* pw = static_cast<const uint8_t*>(packed_weights);
     C.w_hi = reinterpret_cast<const __nv_bfloat16*>(pw);
-    C.w_lo = C.w_hi + (size_t)LC_COUT * LC_K;
-    C.bias = reinterpret_cast<const float*>(pw + (size_t)LC_COUT * LC_K * 4);
+    C.w_lo = C.w_hi + (size_t)LC_COUT * LC_WP;
+    C.bias = reinterpret_cast<const float*>(pw + (size_t)LC_COUT * LC_WP * 4);
     C.out = out; C.B = B;
     C.tiles_per_sample = (pyr.N + LC_QT - 1) / LC_QT;
     C.n_pair_tiles = B * C.tiles_per_sample;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return coord_mode == FC_COORD_CUDA ? launch_lc<FC_COORD_CUDA>(M, P, C, vb, s) : launch_lc<FC_COORD_CPU>(M, P, C, vb, s);
 }
+
+#ifdef FC_PROBES
+extern "C" int fc_debug_lookup_convc1_trace(unsigned long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, fc::fc_lc_trace_buf, sizeof(fc::fc_lc_trace_buf)) == cudaSuccess ? 0 : 1;
+}
+#endif
