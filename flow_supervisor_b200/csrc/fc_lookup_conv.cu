@@ -94,6 +94,30 @@ __device__ __forceinline__ uint32_t lc_pack2(float a, float b) {
 }
 __device__ __forceinline__ float lc_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
 
+// A consumer warp's 3 x 9 lookup values of one level -> bf16 hi / lo pairs in the K-major SWIZZLE_128B B operand.
+// Slot kp = 96 l + 10 (3 W + aa) + j.  With the warp W and the level's parity LODD as template parameters, kp = 64 m + c with
+// m = (96 l) >> 6 a run-time row block and c a compile-time constant: the 128-byte row block, the 16-byte chunk before the
+// swizzle and the position inside the chunk are immediates, and the lane's eight swizzled chunk offsets sw[] are computed
+// once per kernel (the run-time slot arithmetic was ~8 integer instructions in front of every store).
+template <int W, int LODD, int APW, int NR>
+__device__ __forceinline__ void lc_store_b(uint32_t hi_row, int m, const uint32_t (&sw)[8], const float (&o)[APW][NR]) {
+#pragma unroll
+    for (int aa = 0; aa < APW; ++aa) {
+#pragma unroll
+        for (int jj = 0; jj < (NR + 1) / 2; ++jj) {
+            constexpr int dummy = 0; (void)dummy;
+            const int c = 32 * LODD + (W * APW + aa) * (NR + 1) + 2 * jj;          // compile-time after unrolling
+            const float v0 = o[aa][2 * jj], v1 = (2 * jj + 1 < NR) ? o[aa][2 * jj + 1 < NR ? 2 * jj + 1 : 0] : 0.f;
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - __uint_as_float(hb << 16), v1 - __uint_as_float(hb & 0xffff0000u));
+            const uint32_t addr = hi_row + (uint32_t)((m + (c >> 6)) * (QT * 128)) + sw[(c & 63) >> 3] + (uint32_t)((c & 7) * 2);
+            asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(addr), "r"(hb) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(addr + LC_BPLANE), "r"(*reinterpret_cast<const uint32_t*>(&ll)) : "memory");
+        }
+    }
+}
+
 // the query of lane `lane` in lookup tile (pair-tile T, level l) of CTA `rank`
 __device__ __forceinline__ LfQuery lc_query(const LookupParams& P, const ConvParams& C, int T, int level, int rank, int lane) {
     LfQuery q;
@@ -116,8 +140,13 @@ __device__ __forceinline__ LfQuery lc_query(const LookupParams& P, const ConvPar
 #ifdef FC_PROBES
 __device__ unsigned long long fc_lc_trace_buf[148 * 4];
 #define LC_TRACE(k) do { if (threadIdx.x == 0 && blockIdx.x < 148) fc_lc_trace_buf[blockIdx.x * 4 + (k)] = clock64(); } while (0)
+// main loop of CTA 0: consumer group 0 / warp 0 per lookup tile k (0 top, 1 interpolated, 2 B buffer free, 3 B written);
+// epilogue warp 0 per pair-tile i (4 issue start, 5 issue end, 6 accumulator complete, 7 drained + stored)
+__device__ unsigned long long fc_lc_loop_trace[64 * 8];
+#define LC_LOOP(idx, k) do { if (blockIdx.x == 0 && lane == 0 && (idx) < 64) fc_lc_loop_trace[(idx) * 8 + (k)] = clock64(); } while (0)
 #else
 #define LC_TRACE(k) do {} while (0)
+#define LC_LOOP(idx, k) do {} while (0)
 #endif
 
 __device__ __forceinline__ void lc_bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -273,14 +302,17 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
             __syncwarp();
         }
         for (int i = 0; i < n_mine; ++i) {
+            if (warp == LC_EW0) LC_LOOP(i, 4);
             if (warp == LC_EW0 && i + 1 < n_mine) {      // the next pair-tile's MMAs before this one's epilogue
                 if (elect_one()) issue(i + 1);
                 __syncwarp();
             }
+            if (warp == LC_EW0) LC_LOOP(i, 5);
             const int T = pair + i * n_pairs, db = i & 1;
             const int b = T / C.tiles_per_sample, p0 = (T - b * C.tiles_per_sample) * LC_QT;
             mbar_wait(t_full + db, (uint32_t)(i >> 1) & 1u);
             tc_fence_after();
+            if (warp == LC_EW0) LC_LOOP(i, 6);
             float v[LC_QT];
             tmem_ld32(lane_addr + (db ? LC_D1 : LC_D0), v);
             tmem_ld32(lane_addr + (db ? LC_D1 : LC_D0) + 32u, v + 32);
@@ -300,16 +332,21 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
                 for (int j = 0; j < LC_QT; ++j)
                     if (j < n_valid) dst[j] = fmaxf(v[j] + bias, 0.f);
             }
+            if (warp == LC_EW0) LC_LOOP(i, 7);
         }
     } else {
         // ================= lookup consumers: interpolate, split, write the B operand =================
         const int cw = warp - LC_CW0, g = cw / LF_GWARPS, w = cw - g * LF_GWARPS;
         constexpr int APW = (LC_R + LF_GWARPS - 1) / LF_GWARPS;              // 3 x-offsets per warp
         const int n_k = n_mine * LC_L;
+        uint32_t sw[8];                                                 // this lane's row: chunk ch sits at (ch ^ (lane & 7)) * 16
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) sw[ch] = (uint32_t)((ch ^ (lane & 7)) << 4);
         LfQuery q{};
         if (g < n_k) q = lc_query(P, C, pair + (g / LC_L) * n_pairs, g % LC_L, (int)rank, lane);
         for (int k = g; k < n_k; k += LC_GROUPS) {
             const int i = k / LC_L, l = k - i * LC_L, bb = i % LC_NB;
+            if (cw == 0) LC_LOOP(k / LC_GROUPS, 0);
             LfQuery qn = q;
             const int kn = k + LC_GROUPS;
             if (kn < n_k) qn = lc_query(P, C, pair + (kn / LC_L) * n_pairs, kn % LC_L, (int)rank, lane);   // coordinates one turn ahead
@@ -320,26 +357,25 @@ lookup_convc1_kernel(const __grid_constant__ LookupMaps M, const LookupParams P,
 #pragma unroll
                 for (int j = 0; j < LC_R; ++j) sink.o[aa][j] = 0.f;
             lf_consume<LC_RADIUS, CM, false, VB>(P, sh, win, q, k % LC_STAGES, (uint32_t)(k / LC_STAGES) & 1u, lane, w, sink);
+            if (cw == 0) LC_LOOP(k / LC_GROUPS, 1);
             // the MMAs that read this buffer LC_NB pair-tiles ago have retired
             if (i >= LC_NB) mbar_wait(b_empty + bb, (uint32_t)(i / LC_NB - 1) & 1u);
-            uint8_t* hi_row = bbuf + bb * LC_BBUF + lane * 128;
-            uint8_t* lo_row = hi_row + LC_BPLANE;
-#pragma unroll
-            for (int aa = 0; aa < APW; ++aa) {
-                const int kp0 = l * LC_KL + (w * APW + aa) * (LC_R + 1);     // slot of (x-offset, y-offset 0): even
-#pragma unroll
-                for (int jj = 0; jj < (LC_R + 1) / 2; ++jj) {
-                    const float v0 = sink.o[aa][2 * jj], v1 = (2 * jj + 1 < LC_R) ? sink.o[aa][2 * jj + 1 < LC_R ? 2 * jj + 1 : 0] : 0.f;
-                    const float h0 = lc_round(v0), h1 = lc_round(v1);
-                    const int kp = kp0 + 2 * jj;
-                    const uint32_t off = (uint32_t)((kp >> 6) * (QT * 128) + ((((kp & 63) >> 3) ^ (lane & 7)) << 4) + (kp & 7) * 2);
-                    *reinterpret_cast<uint32_t*>(hi_row + off) = lc_pack2(h0, h1);
-                    *reinterpret_cast<uint32_t*>(lo_row + off) = lc_pack2(v0 - h0, v1 - h1);
-                }
+            if (cw == 0) LC_LOOP(k / LC_GROUPS, 2);
+            const uint32_t hi_row = smem_u32(bbuf + bb * LC_BBUF + lane * 128);
+            const int m = (l * LC_KL) >> 6;
+            if (l & 1) {
+                if (w == 0) lc_store_b<0, 1, APW, LC_R>(hi_row, m, sw, sink.o);
+                else if (w == 1) lc_store_b<1, 1, APW, LC_R>(hi_row, m, sw, sink.o);
+                else lc_store_b<2, 1, APW, LC_R>(hi_row, m, sw, sink.o);
+            } else {
+                if (w == 0) lc_store_b<0, 0, APW, LC_R>(hi_row, m, sw, sink.o);
+                else if (w == 1) lc_store_b<1, 0, APW, LC_R>(hi_row, m, sw, sink.o);
+                else lc_store_b<2, 0, APW, LC_R>(hi_row, m, sw, sink.o);
             }
             fence_proxy_async_smem();                                  // generic-proxy writes -> the tensor core's reads
             __syncwarp();
             if (lane == 0) mbar_arrive(b_part + bb);
+            if (cw == 0) LC_LOOP(k / LC_GROUPS, 3);
             q = qn;
         }
     }
@@ -444,6 +480,9 @@ extern "C" int fc_lookup_convc1_fwd(const void* pyramid, const float* coords, co
 }
 
 #ifdef FC_PROBES
+extern "C" int fc_debug_lookup_convc1_loop_trace(unsigned long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, fc::fc_lc_loop_trace, sizeof(fc::fc_lc_loop_trace)) == cudaSuccess ? 0 : 1;
+}
 extern "C" int fc_debug_lookup_convc1_trace(unsigned long long* host_out) {
     return cudaMemcpyFromSymbol(host_out, fc::fc_lc_trace_buf, sizeof(fc::fc_lc_trace_buf)) == cudaSuccess ? 0 : 1;
 }

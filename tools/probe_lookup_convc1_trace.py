@@ -32,3 +32,17 @@ t = buf.astype(np.int64)
 print("per CTA, clock64 cycles (mean / max over 148 CTAs): barriers + TMEM alloc %.0f / %d | weights -> tensor memory, B zeroed, cluster sync %.0f / %d | main loop %.0f / %d"
       % ((t[:, 1] - t[:, 0]).mean(), (t[:, 1] - t[:, 0]).max(), (t[:, 2] - t[:, 1]).mean(), (t[:, 2] - t[:, 1]).max(),
          (t[:, 3] - t[:, 2]).mean(), (t[:, 3] - t[:, 2]).max()))
+
+lb = np.zeros((64, 8), dtype=np.uint64)
+lib.fc_debug_lookup_convc1_loop_trace.argtypes = [ctypes.c_void_p]
+assert lib.fc_debug_lookup_convc1_loop_trace(lb.ctypes.data) == 0
+u = lb.astype(np.int64)
+nc = int((u[:, 3] > 0).sum()); ne = int((u[:, 7] > 0).sum())
+c = u[1:nc - 1]
+print("consumer group 0, warp 0, per lookup tile (%d tiles): interpolate (incl. waiting for the footprints) %.0f | wait for a free B buffer %.0f | "
+      "split + swizzled stores + arrive %.0f | tile period %.0f" % (nc, (c[:, 1] - c[:, 0]).mean(), (c[:, 2] - c[:, 1]).mean(), (c[:, 3] - c[:, 2]).mean(),
+      np.diff(u[1:nc, 0]).mean()))
+e = u[1:ne - 1]
+print("epilogue warp 0 (hosts the MMA issue), per pair-tile (%d): issue of the next pair-tile's MMAs (incl. waiting for its B operand) %.0f | "
+      "wait for the accumulator %.0f | drain + bias + ReLU + stores %.0f | period %.0f" % (ne, (e[:, 5] - e[:, 4]).mean(), (e[:, 6] - e[:, 5]).mean(),
+      (e[:, 7] - e[:, 6]).mean(), np.diff(u[1:ne, 4]).mean()))
