@@ -74,6 +74,7 @@ static Tunables& tunables_mut() {
         v.no_fuse = getenv("FLOWCORR_NO_FUSE") != nullptr;
         v.l2_fetch = geti("FLOWCORR_L2_FETCH", 0);
         v.bwd_fused = geti("FLOWCORR_BWD_FUSED", 1);
+        v.pdl = geti("FLOWCORR_PDL", 1);
         v.verbose = geti("FLOWCORR_VERBOSE", 1);
         return v;
     }();
@@ -173,6 +174,7 @@ extern "C" int fc_tunable_set(const char* name, int value) {
     else if (n == "build_epi_warps") t.build_epi_warps = value == 8 ? 8 : 4;
     else if (n == "no_fuse") t.no_fuse = value != 0;
     else if (n == "verbose") t.verbose = value;
+    else if (n == "pdl") t.pdl = value;
     else if (n == "bwd_fused") t.bwd_fused = value;
     else if (n == "l2_fetch") t.l2_fetch = value;
 #ifdef FC_PROBES

@@ -54,6 +54,7 @@ struct Tunables {
     int no_fuse;             // FLOWCORR_NO_FUSE          pyramid by separate pooling launches
     int l2_fetch;            // FLOWCORR_L2_FETCH         32 | 64 | 128: cudaLimitMaxL2FetchGranularity set at the first lookup (0 = leave)
     int bwd_fused;           // FLOWCORR_BWD_FUSED        1 (default): fold + bf16 split inside the backward GEMMs; 0: separate fold + pack pass
+    int pdl;                 // FLOWCORR_PDL              1 (default): lookups launch with programmatic stream serialisation
     int verbose;             // FLOWCORR_VERBOSE          log mode fall-backs (shape not taken by a tensor-core kernel) to stderr
 };
 const Tunables& tunables();

@@ -93,7 +93,15 @@ static int launch_fwd4(const LookupMaps& M, const LookupParams& P, int n_tiles, 
     const size_t smem = (size_t)LF_STAGES * lf_stage_bytes(VB) + sizeof(LfShared);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
     FC_SMEM_ATTR_ONCE((lookup_fwd_kernel<RADIUS, CM, DBG, VB>), smem);
-    lookup_fwd_kernel<RADIUS, CM, DBG, VB><<<grid, LF_THREADS, smem, s>>>(M, P, n_tiles);
+    // programmatic stream serialisation: the grid may be scheduled while the previous kernel of the stream drains (its CTAs
+    // wait in griddepcontrol.wait before they touch memory), which hides the launch latency between the lookups of an iteration
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(LF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = tunables().pdl ? 1 : 0;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    FC_CUDA(cudaLaunchKernelEx(&cfg, lookup_fwd_kernel<RADIUS, CM, DBG, VB>, M, P, n_tiles));
     FC_LAUNCH_CHECK("lookup_fwd_kernel");
     return FC_OK;
 }

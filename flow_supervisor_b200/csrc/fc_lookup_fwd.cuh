@@ -313,6 +313,13 @@ lookup_fwd_kernel(const __grid_constant__ LookupMaps M, const LookupParams P, in
         mbar_fence_init();
     }
     __syncthreads();
+    // programmatic dependent launch (fc_lookup_fwd.cu launches with programmatic stream serialisation): a CTA of this grid
+    // may have become resident while the previous kernel of the stream was still draining; everything above (barrier
+    // set-up) overlapped that.  From here on the coordinates and the pyramid are read: wait for the previous grid's memory.
+    // The NEXT kernel of the stream, if it is launched the same way (the next lookup), may start taking over SMs as soon as
+    // CTAs of this grid exit.
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
 
     // tiles of this CTA: blockIdx.x, + gridDim.x, ...   (k-th local tile lives in stage k % LF_STAGES)
     const int first = blockIdx.x, stride = gridDim.x, L = P.L;
