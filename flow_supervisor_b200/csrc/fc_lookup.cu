@@ -328,12 +328,18 @@ static int launch_bwd(const LookupMaps& M, const CUtensorMap& gmap, int staged, 
     const size_t smem = (size_t)LB_GROUPS * (LB_STAGES * LB_STAGE_BYTES + 2 * LB_GBOX_BYTES);
     const int want = (n_tiles + LB_GROUPS - 1) / LB_GROUPS;
     const int grid = want < n_sm ? want : n_sm;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(LB_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = tunables().pdl ? 1 : 0;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
     if (coord_mode == FC_COORD_CUDA) {
         FC_SMEM_ATTR_ONCE((lookup_bwd_kernel<RADIUS, FC_COORD_CUDA>), smem);
-        lookup_bwd_kernel<RADIUS, FC_COORD_CUDA><<<grid, LB_THREADS, smem, s>>>(M, gmap, P, n_tiles, staged);
+        FC_CUDA(cudaLaunchKernelEx(&cfg, lookup_bwd_kernel<RADIUS, FC_COORD_CUDA>, M, gmap, P, n_tiles, staged));
     } else {
         FC_SMEM_ATTR_ONCE((lookup_bwd_kernel<RADIUS, FC_COORD_CPU>), smem);
-        lookup_bwd_kernel<RADIUS, FC_COORD_CPU><<<grid, LB_THREADS, smem, s>>>(M, gmap, P, n_tiles, staged);
+        FC_CUDA(cudaLaunchKernelEx(&cfg, lookup_bwd_kernel<RADIUS, FC_COORD_CPU>, M, gmap, P, n_tiles, staged));
     }
     FC_LAUNCH_CHECK("lookup_bwd_kernel");
     return FC_OK;
