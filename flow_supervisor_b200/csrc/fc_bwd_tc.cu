@@ -392,7 +392,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 //               CTA's "converted" barrier to the leader with ONE cluster-scope release per k-block
 //   warps 2-5   epilogue as in tc_bwd_kernel
 constexpr int BF_THREADS = 448;
-constexpr int BF_EPI0 = 2, BF_CONV0 = 6, BF_CONV_WARPS = 8;
+constexpr int BF_CONV0 = 6, BF_CONV_WARPS = 8;                // warps 2-5: epilogue, 6-13: converters
 constexpr int BF_STAGES = 2;
 constexpr int BF_RAW_BYTES = 128 * BW_BK * 4;                // 32 KB of fp32
 constexpr int BF_STAGE_BYTES = BF_RAW_BYTES + 4 * BW_PART_BYTES;   // raw | A_hi | A_lo | B_hi | B_lo = 96 KB

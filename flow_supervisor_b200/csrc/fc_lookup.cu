@@ -28,14 +28,10 @@ namespace fc {
 #ifndef FC_LB_STAGES
 #define FC_LB_STAGES 1
 #endif
-#ifndef FC_LB_PREFETCH
-#define FC_LB_PREFETCH 1
-#endif
 constexpr int LB_GROUPS = FC_LB_GROUPS;                       // independent warp groups per CTA
 constexpr int LB_GWARPS = 3;                                  // warps per group (window column thirds)
 constexpr int LB_THREADS = 32 * LB_GROUPS * LB_GWARPS;        // 288
 constexpr int LB_STAGES = FC_LB_STAGES;                       // window buffers per group
-constexpr bool LB_PREFETCH = FC_LB_PREFETCH != 0;             // inputs of the next tile loaded one tile ahead
 constexpr int LB_WIN_BYTES = 6 * 3 * 64;                      // 6 row pairs x 3 patches x 64 B = 1152
 constexpr int LB_STAGE_BYTES = QT * LB_WIN_BYTES;             // 36 864
 // the output gradients of a tile ((2r+1)^2 channels x 32 queries) arrive as ONE TMA box per tile, one tile ahead: issued as

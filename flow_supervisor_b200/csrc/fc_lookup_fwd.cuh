@@ -211,7 +211,6 @@ __device__ __forceinline__ void lf_consume(const LookupParams& P, LfShared& sh, 
 
     mbar_wait(&sh.full[stage], parity);
     const uint32_t wq = win + stage * LF_STAGE_BYTES + lane * LF_WIN_BYTES;
-    const bool fast = q.live && valid && regular;                    // this lane's outputs come from the fast path
     // when no lane needs the per-tap slow path, the ring stage is handed back as soon as the
     // sub-windows sit in registers: a stage is then busy for the loads only, not for the
     // arithmetic and the stores
