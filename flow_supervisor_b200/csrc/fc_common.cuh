@@ -53,7 +53,8 @@ struct Tunables {
     int build_epi_warps;     // FLOWCORR_BUILD_EPI_WARPS  4 | 8 (default 4)
     int no_fuse;             // FLOWCORR_NO_FUSE          pyramid by separate pooling launches
     int l2_fetch;            // FLOWCORR_L2_FETCH         32 | 64 | 128: cudaLimitMaxL2FetchGranularity set at the first lookup (0 = leave)
-    int bwd_fused;           // FLOWCORR_BWD_FUSED        1 (default): fold + bf16 split inside the backward GEMMs; 0: separate fold + pack pass
+    int bwd_fused;           // FLOWCORR_BWD_FUSED        1 (default): fold + bf16 split inside the backward GEMMs (aligned maps: TMA coarse boxes);
+                             //                           2: the generic fold-in-GEMM kernel for every map; 0: separate fold + pack pass
     int pdl;                 // FLOWCORR_PDL              1 (default): lookups launch with programmatic stream serialisation
     int verbose;             // FLOWCORR_VERBOSE          log mode fall-backs (shape not taken by a tensor-core kernel) to stderr
 };
